@@ -134,7 +134,10 @@ def test_scaled_adam_and_eden2_match_reference():
     h = g["hyper"]
     opt = O.ScaledAdamOracle(names, params, lr=h["lr"], clipping_scale=h["clipping_scale"])
     for step, gs in enumerate(g["grads"]):
-        lr = O.eden2_lr(h["lr"], step, h["lr_batches"], h["warmup_batches"], h["warmup_start"])
+        # LRScheduler.__init__ (optim.py:750-763) does not touch lr; step_batch() sets it for
+        # batch = 1, 2, ... so the very first optimizer step runs at the base lr.
+        lr = h["lr"] if step == 0 else O.eden2_lr(h["lr"], step, h["lr_batches"],
+                                                  h["warmup_batches"], h["warmup_start"])
         assert abs(lr - g["lrs"][step]) < 1e-12 * max(1.0, abs(lr)) + 1e-15, step
         opt.g["lr"] = lr
         opt.step(params, gs)
