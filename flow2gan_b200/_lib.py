@@ -1,0 +1,197 @@
+"""ctypes binding of csrc/libflow2gan_b200.so (the C ABI in include/flow2gan_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing, or the device is not
+sm_100, every op raises.  Tensors are passed as raw device pointers; launches go to torch's
+current CUDA stream, so they compose with torch.cuda.graph capture and stream contexts.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libflow2gan_b200.so")
+
+ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_SILU = 0, 1, 2, 3
+SPEC_PACKED, SPEC_MAG, SPEC_POWER = 0, 1, 2
+GEMM_MAX_PROBLEMS = 8
+
+_fp = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_ll = C.c_longlong
+
+
+class F2GGemm(C.Structure):
+    _fields_ = [
+        ("a", _fp), ("b", _fp), ("c", _fp),
+        ("M", _i), ("N", _i), ("K", _i),
+        ("lda", _i), ("ldb", _i), ("ldc", _i),
+        ("a_mn", _i), ("b_mn", _i), ("bn", _i),
+        ("bias", _fp), ("slope", _fp), ("res", _fp), ("res_scale", _fp),
+        ("row_scale", _fp), ("gate", _fp),
+        ("ld_res", _i), ("ld_gate", _i),
+        ("act", _i), ("leaky", _f), ("alpha", _f),
+        ("round_tf32", _i), ("accumulate", _i),
+    ]
+
+
+_SIGS = {
+    "f2g_abi_version": ([], _i),
+    "f2g_last_error": ([], C.c_char_p),
+    "f2g_check_device": ([], _i),
+    "f2g_gemm_tf32": ([C.POINTER(F2GGemm), _i, _fp], _i),
+    "f2g_stft": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _i, _f, _fp, _i, _i, _fp], _i),
+    "f2g_dc_peak": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_irfft_frames": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_ola_combine": ([C.POINTER(_fp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _fp, _fp,
+                         _fp, _i, _i, _i, _f, _f, _i, _fp], _i),
+    "f2g_biasnorm": ([_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp], _i),
+    "f2g_block_pre": ([_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i,
+                       _fp, _i, _fp, _fp, _fp], _i),
+    "f2g_linear_small": ([_fp, _i, _i, _i, _fp, _i, _fp, _i, _i, _fp, _i, _fp], _i),
+    "f2g_time_sinusoid": ([_fp, _i, _i, _fp, _f, _fp, _fp], _i),
+    "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
+    "f2g_im2col_cf": ([_fp, _i, _i, _i, _i, _fp, _i, _i, _fp], _i),
+    "f2g_frame_mask": ([_fp, _i, _i, _i, _fp, _fp], _i),
+}
+
+_lib: Optional[C.CDLL] = None
+_device_ok = False
+
+
+def exported_symbols() -> Sequence[str]:
+    return tuple(_SIGS.keys())
+
+
+def load() -> C.CDLL:
+    """dlopen the library and bind every symbol (no GPU needed).  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"flow2gan_b200: native library not built ({LIB_PATH}); run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` -- there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        if lib.f2g_abi_version() != 1:
+            raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
+        _lib = lib
+    return _lib
+
+
+def lib() -> C.CDLL:
+    """Library handle for compute calls: additionally requires an sm_100 device."""
+    global _device_ok
+    l = load()
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise RuntimeError("flow2gan_b200: no CUDA device; the hot path has no CPU fallback")
+        _check(l.f2g_check_device())
+        _device_ok = True
+    return l
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = load().f2g_last_error().decode(errors="replace")
+        raise RuntimeError(f"flow2gan_b200 native call failed (rc={rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float32, torch.int32), (t.device, t.dtype)
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------
+# thin typed wrappers (shape bookkeeping only; all math happens in the kernels)
+# ---------------------------------------------------------------------------------------
+def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
+              res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
+              act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0) -> F2GGemm:
+    d = F2GGemm()
+    d.a, d.b, d.c = a, b, c
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldb, d.ldc = lda, ldb, ldc
+    d.a_mn, d.b_mn, d.bn = a_mn, b_mn, bn
+    d.bias, d.slope, d.res, d.res_scale = bias, slope, res, res_scale
+    d.row_scale, d.gate = row_scale, gate
+    d.ld_res, d.ld_gate = ld_res, ld_gate
+    d.act, d.leaky, d.alpha = act, leaky, alpha
+    d.round_tf32, d.accumulate = round_tf32, accumulate
+    return d
+
+
+def gemm_group(descs: Sequence[F2GGemm]) -> None:
+    n = len(descs)
+    arr = (F2GGemm * n)(*descs)
+    _check(lib().f2g_gemm_tf32(arr, n, stream()))
+
+
+def stft(audio, B, T, ld_audio, n_fft, hop, mode, out, ld_out, *, pre=None, fb=None, n_filt=0,
+         log_clip=0.0, round_tf32=0):
+    _check(lib().f2g_stft(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(pre), ptr(fb), n_filt,
+                          log_clip, ptr(out), ld_out, round_tf32, stream()))
+
+
+def dc_peak(audio, B, T, ld_audio, pre):
+    _check(lib().f2g_dc_peak(ptr(audio), B, T, ld_audio, ptr(pre), stream()))
+
+
+def irfft_frames(packed, rows, ld, n_fft, frames_out):
+    _check(lib().f2g_irfft_frames(ptr(packed), rows, ld, n_fft, ptr(frames_out), stream()))
+
+
+def ola_combine(frames, n_ffts, hops, n_frames, weight, x, out, B, T, euler, t, dt, clamp):
+    nb = len(frames)
+    fr = (_fp * nb)(*[ptr(f) for f in frames])
+    a1 = (_i * nb)(*n_ffts)
+    a2 = (_i * nb)(*hops)
+    a3 = (_i * nb)(*n_frames)
+    _check(lib().f2g_ola_combine(fr, a1, a2, a3, nb, ptr(weight), ptr(x), ptr(out), B, T,
+                                 int(euler), float(t), float(dt), int(clamp), stream()))
+
+
+def biasnorm(x, rows, Cc, ld, bias, log_scale, y, ld_y):
+    _check(lib().f2g_biasnorm(ptr(x), rows, Cc, ld, ptr(bias), ptr(log_scale), ptr(y), ld_y, stream()))
+
+
+def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
+              factor, zero_row, tscale, ld_ts, out, ld_out, conv_out=None, inv_out=None):
+    _check(lib().f2g_block_pre(ptr(x), B, T, Cc, ld_x, ptr(dw_wT), ptr(dw_b), ptr(bn_bias),
+                               ptr(bn_log_scale), ptr(row_mask), ptr(cond), ld_cond, cond_T, factor,
+                               zero_row, ptr(tscale), ld_ts, ptr(out), ld_out, ptr(conv_out),
+                               ptr(inv_out), stream()))
+
+
+def linear_small(inp, B, K, ld_in, W, ldw, bias, O, act, out, ld_out):
+    _check(lib().f2g_linear_small(ptr(inp), B, K, ld_in, ptr(W), ldw, ptr(bias), O, act, ptr(out),
+                                  ld_out, stream()))
+
+
+def time_sinusoid(t, B, dim, freqs, scale, out):
+    _check(lib().f2g_time_sinusoid(ptr(t), B, dim, ptr(freqs), float(scale), ptr(out), stream()))
+
+
+def pack2d(src, src_rs, src_cs, rows, cols, dst, ld, ld_fill, round_tf32):
+    _check(lib().f2g_pack2d(src, src_rs, src_cs, rows, cols, dst, ld, ld_fill, round_tf32, stream()))
+
+
+def im2col_cf(x, B, Cc, T, ktaps, out, ld, round_tf32):
+    _check(lib().f2g_im2col_cf(ptr(x), B, Cc, T, ktaps, ptr(out), ld, round_tf32, stream()))
+
+
+def frame_mask(lens, B, frames, hop, out):
+    _check(lib().f2g_frame_mask(ptr(lens), B, frames, hop, ptr(out), stream()))

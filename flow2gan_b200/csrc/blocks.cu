@@ -1,0 +1,296 @@
+// ConvNeXt-block SIMT pieces on channel-last rows: BiasNorm, fused depthwise-conv prologue,
+// small dense layers, sinusoidal time embedding, packing helpers.  All HBM/L2-bound.
+// Reference: flow2gan/models/modules.py:217-232 (SinusoidalPosEmb), :286-416 (BiasNorm),
+// :456-495 (ConvNeXtBlock.forward), :523-542 (CondEncoder), :595-627 (ConvNeXtDecoder).
+#include "common.cuh"
+#include "../../include/flow2gan_b200.h"
+
+namespace f2g {
+
+constexpr int MAX_CHUNKS = 8;  // channels <= 8 * 128 = 1024 per row
+
+F2G_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+F2G_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// One warp per row.  y = x * (mean_c (x - bias_c)^2)^-1/2 * exp(log_scale).  No epsilon
+// (modules.py:309-312).
+__global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, int ld,
+                                const float* __restrict__ bias,
+                                const float* __restrict__ log_scale, float* __restrict__ y,
+                                int ld_y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int chunks = C >> 7;
+  float4 v[MAX_CHUNKS];
+  float ssq = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_CHUNKS; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      v[j] = ld4(x + (size_t)row * ld + c);
+      const float4 b = ld4(bias + c);
+      const float d0 = v[j].x - b.x, d1 = v[j].y - b.y, d2 = v[j].z - b.z, d3 = v[j].w - b.w;
+      ssq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+  ssq = warp_sum(ssq);
+  const float scale = (1.0f / sqrtf(ssq / (float)C)) * expf(*log_scale);
+#pragma unroll
+  for (int j = 0; j < MAX_CHUNKS; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      st4(y + (size_t)row * ld_y + c,
+          make_float4(v[j].x * scale, v[j].y * scale, v[j].z * scale, v[j].w * scale));
+    }
+  }
+}
+
+// Fused ConvNeXt-block prologue, one warp per token (b, t):
+//   y = dwconv7(x * mask) + b ; z = BiasNorm(y) + cond_row ; z *= 1 + ts[b] ; out = tf32(z)
+__global__ void block_pre_kernel(const float* __restrict__ x, int B, int T, int C, int ld_x,
+                                 const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
+                                 const float* __restrict__ bn_bias,
+                                 const float* __restrict__ bn_log_scale,
+                                 const float* __restrict__ row_mask,
+                                 const float* __restrict__ cond, int ld_cond, int cond_T,
+                                 int factor, int zero_row, const float* __restrict__ tscale,
+                                 int ld_ts, float* __restrict__ out, int ld_out,
+                                 float* __restrict__ conv_out, float* __restrict__ inv_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const int bi = row / T;
+  const int t = row - bi * T;
+  const int chunks = C >> 7;
+
+  float mk[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int tt = t + k - 3;
+    mk[k] = (tt >= 0 && tt < T) ? (row_mask ? row_mask[bi * T + tt] : 1.f) : 0.f;
+  }
+
+  float4 y[MAX_CHUNKS];
+  float ssq = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_CHUNKS; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      float4 acc = ld4(dw_b + c);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        if (mk[k] != 0.f) {
+          const float4 xv = ld4(x + (size_t)(row + k - 3) * ld_x + c);
+          const float4 w = ld4(dw_wT + k * C + c);
+          acc.x = fmaf(xv.x * mk[k], w.x, acc.x);
+          acc.y = fmaf(xv.y * mk[k], w.y, acc.y);
+          acc.z = fmaf(xv.z * mk[k], w.z, acc.z);
+          acc.w = fmaf(xv.w * mk[k], w.w, acc.w);
+        }
+      }
+      y[j] = acc;
+      const float4 b = ld4(bn_bias + c);
+      const float d0 = acc.x - b.x, d1 = acc.y - b.y, d2 = acc.z - b.z, d3 = acc.w - b.w;
+      ssq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      if (conv_out) st4(conv_out + (size_t)row * C + c, acc);
+    }
+  }
+  ssq = warp_sum(ssq);
+  const float inv = (1.0f / sqrtf(ssq / (float)C)) * expf(*bn_log_scale);
+  if (inv_out && lane == 0) inv_out[row] = inv;
+
+  int crow = zero_row;
+  if (cond && t < cond_T * factor) crow = bi * cond_T + t / factor;
+#pragma unroll
+  for (int j = 0; j < MAX_CHUNKS; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      float4 z = make_float4(y[j].x * inv, y[j].y * inv, y[j].z * inv, y[j].w * inv);
+      if (cond) {
+        const float4 cv = ld4(cond + (size_t)crow * ld_cond + c);
+        z.x += cv.x; z.y += cv.y; z.z += cv.z; z.w += cv.w;
+      }
+      if (tscale) {
+        const float4 s = ld4(tscale + (size_t)bi * ld_ts + c);
+        z.x *= 1.f + s.x; z.y *= 1.f + s.y; z.z *= 1.f + s.z; z.w *= 1.f + s.w;
+      }
+      st4(out + (size_t)row * ld_out + c,
+          make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
+    }
+  }
+}
+
+// out[b,o] = act(bias[o] + sum_k in[b,k] W[o,k]); one warp per output column o, 8 rows a pass.
+__global__ void linear_small_kernel(const float* __restrict__ in, int B, int K, int ld_in,
+                                    const float* __restrict__ W, int ldw,
+                                    const float* __restrict__ bias, int O, int act,
+                                    float* __restrict__ out, int ld_out) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  const float* w = W + (size_t)o * ldw;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (b0 + r < B) acc[r] = fmaf(in[(size_t)(b0 + r) * ld_in + k], wv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float s = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < B) {
+        float v = s + (bias ? bias[o] : 0.f);
+        if (act == F2G_ACT_SILU) v = v / (1.f + expf(-v));
+        out[(size_t)(b0 + r) * ld_out + o] = v;
+      }
+    }
+  }
+}
+
+__global__ void time_sinusoid_kernel(const float* __restrict__ t, int B, int half,
+                                     const float* __restrict__ freqs, float scale,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float a = scale * t[b] * freqs[k];
+  out[(size_t)b * 2 * half + k] = sinf(a);
+  out[(size_t)b * 2 * half + half + k] = cosf(a);
+}
+
+__global__ void pack2d_kernel(const float* __restrict__ src, long long src_rs, long long src_cs,
+                              int rows, int cols, float* __restrict__ dst, int ld, int ld_fill,
+                              int round_tf32) {
+  const long long total = (long long)rows * ld_fill;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_fill), c = (int)(i - (long long)r * ld_fill);
+    float v = 0.f;
+    if (c < cols) v = src[r * src_rs + c * src_cs];
+    dst[(size_t)r * ld + c] = round_tf32 ? tf32_rna(v) : v;
+  }
+}
+
+__global__ void im2col_cf_kernel(const float* __restrict__ x, int B, int C, int T, int ktaps,
+                                 float* __restrict__ out, int ld, int round_tf32) {
+  const long long total = (long long)B * T * ld;
+  const int pad = ktaps / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ld);
+    const long long row = i / ld;
+    const int t = (int)(row % T), b = (int)(row / T);
+    float v = 0.f;
+    if (col < ktaps * C) {
+      const int k = col / C, c = col - k * C;
+      const int tt = t + k - pad;
+      if (tt >= 0 && tt < T) v = x[((size_t)b * C + c) * T + tt];
+    }
+    out[i] = round_tf32 ? tf32_rna(v) : v;
+  }
+}
+
+__global__ void frame_mask_kernel(const int* __restrict__ lens, int B, int frames, int hop,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * frames) return;
+  const int b = i / frames, f = i - b * frames;
+  out[i] = f < 1 + lens[b] / hop ? 1.f : 0.f;
+}
+
+}  // namespace f2g
+
+using namespace f2g;
+
+static int check_channels(const char* who, int C, int ld) {
+  if (C % 128 != 0 || C > MAX_CHUNKS * 128 || ld % 4 != 0) {
+    set_error("%s: channels=%d must be a multiple of 128 (<= %d) and ld=%d a multiple of 4", who, C,
+              MAX_CHUNKS * 128, ld);
+    return F2G_EINVAL;
+  }
+  return 0;
+}
+
+extern "C" int f2g_biasnorm(const float* x, int rows, int C, int ld, const float* bias,
+                            const float* log_scale, float* y, int ld_y, void* stream) {
+  if (int rc = check_channels("f2g_biasnorm", C, ld | ld_y)) return rc;
+  const int wpb = 4;
+  biasnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, C, ld, bias, log_scale, y, ld_y);
+  return check_launch("f2g_biasnorm");
+}
+
+extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, const float* dw_wT,
+                             const float* dw_b, const float* bn_bias, const float* bn_log_scale,
+                             const float* row_mask, const float* cond, int ld_cond, int cond_T,
+                             int factor, int zero_row, const float* tscale, int ld_ts, float* out,
+                             int ld_out, float* conv_out, float* inv_rms_out, void* stream) {
+  if (int rc = check_channels("f2g_block_pre", C, ld_x | ld_out | (cond ? ld_cond : 0) | (tscale ? ld_ts : 0)))
+    return rc;
+  const int wpb = 4;
+  const int rows = B * T;
+  block_pre_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, B, T, C, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
+      factor < 1 ? 1 : factor, zero_row, tscale, ld_ts, out, ld_out, conv_out, inv_rms_out);
+  return check_launch("f2g_block_pre");
+}
+
+extern "C" int f2g_linear_small(const float* in, int B, int K, int ld_in, const float* W, int ldw,
+                                const float* bias, int O, int act, float* out, int ld_out,
+                                void* stream) {
+  const int wpb = 8;
+  linear_small_kernel<<<(O + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, B, K, ld_in, W, ldw, bias, O, act, out, ld_out);
+  return check_launch("f2g_linear_small");
+}
+
+extern "C" int f2g_time_sinusoid(const float* t, int B, int dim, const float* freqs, float scale,
+                                 float* out, void* stream) {
+  const int half = dim / 2;
+  const int total = B * half;
+  time_sinusoid_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, B, half, freqs, scale, out);
+  return check_launch("f2g_time_sinusoid");
+}
+
+extern "C" int f2g_pack2d(const float* src, long long src_rs, long long src_cs, int rows, int cols,
+                          float* dst, int ld, int ld_fill, int round_tf32, void* stream) {
+  if (ld_fill < cols || ld_fill > ld) {
+    set_error("f2g_pack2d: need cols <= ld_fill <= ld (%d, %d, %d)", cols, ld_fill, ld);
+    return F2G_EINVAL;
+  }
+  const long long total = (long long)rows * ld_fill;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  pack2d_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_rs, src_cs, rows,
+                                                                      cols, dst, ld, ld_fill,
+                                                                      round_tf32);
+  return check_launch("f2g_pack2d");
+}
+
+extern "C" int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, float* out, int ld,
+                             int round_tf32, void* stream) {
+  if (ld < ktaps * C) {
+    set_error("f2g_im2col_cf: ld=%d < ktaps*C=%d", ld, ktaps * C);
+    return F2G_EINVAL;
+  }
+  const long long total = (long long)B * T * ld;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col_cf_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, B, C, T, ktaps, out,
+                                                                         ld, round_tf32);
+  return check_launch("f2g_im2col_cf");
+}
+
+extern "C" int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream) {
+  const int total = B * frames;
+  frame_mask_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lens, B, frames, hop, out);
+  return check_launch("f2g_frame_mask");
+}

@@ -1,0 +1,399 @@
+// Grouped, persistent TF32 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )          fp32 in HBM, TF32 operands, fp32 accumulate
+//
+// This is the contraction behind every 1x1 conv / Linear on the Flow2GAN hot path
+// (reference: nn.Conv1d(k=1) / nn.Linear call sites flow2gan/models/modules.py:443-451,
+// 563-593) and, through strided "overlapping-row" tensor maps, the (5,1)/(3,9) Conv2d stacks
+// of the discriminators (flow2gan/models/discriminators.py:65-76,171-184).
+//
+// Structure (one CTA per SM, persistent over a tile list that can span several problems):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1   : MMA issuer     (one elected thread, tcgen05.mma kind::tf32, D in TMEM)
+//   warps 2-5: epilogue       (tcgen05.ld -> regs -> smem transpose -> fused epilogue -> HBM)
+// TMEM holds two accumulator buffers so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Either operand may be K-major or MN-major (needed by dgrad / wgrad).
+#include "common.cuh"
+#include "gemm_tf32.h"
+
+#include <stdio.h>
+
+namespace f2g {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 4;
+constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - EPI_SCRATCH_BYTES - 2048) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct alignas(64) DevProblem {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  float* c;
+  const float* bias;
+  const float* slope;
+  const float* res;
+  const float* res_scale;
+  const float* row_scale;
+  const float* gate;
+  int ldc, ld_res, ld_gate;
+  int M, N, K;
+  int m_tiles, n_tiles, tile_begin;
+  int act, round_tf32, accumulate;
+  float leaky, alpha;
+};
+
+struct alignas(64) DevGroup {
+  DevProblem p[F2G_GEMM_MAX_PROBLEMS];
+  int n_problems;
+  int total_tiles;
+};
+
+struct TileCoord {
+  int prob, m0, n0;
+};
+
+F2G_DEVINL TileCoord decode_tile(const DevGroup& g, int tile) {
+  int pi = 0;
+#pragma unroll 1
+  for (int i = 1; i < g.n_problems; ++i)
+    if (tile >= g.p[i].tile_begin) pi = i;
+  const int local = tile - g.p[pi].tile_begin;
+  const int nt = g.p[pi].n_tiles;
+  TileCoord t;
+  t.prob = pi;
+  t.m0 = (local / nt) * BM;
+  t.n0 = (local % nt);
+  return t;
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  float* scratch_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.n_problems; ++i) {
+      tma_prefetch_desc(&g.p[i].map_a);
+      tma_prefetch_desc(&g.p[i].map_b);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        const DevProblem& pr = g.p[tc.prob];
+        const int n0 = tc.n0 * BN;
+        const int kblocks = (pr.K + BK - 1) / BK;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j)
+              tma_load_2d(sa + j * 4096, &pr.map_a, &full_bar[stage], tc.m0 + 32 * j, kb * BK);
+          } else {
+            tma_load_2d(sa, &pr.map_a, &full_bar[stage], kb * BK, tc.m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d(sb + j * 4096, &pr.map_b, &full_bar[stage], n0 + 32 * j, kb * BK);
+          } else {
+            tma_load_2d(sb, &pr.map_b, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------------
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ab = 0;
+      uint32_t ab_phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        const DevProblem& pr = g.p[tc.prob];
+        const int kblocks = (pr.K + BK - 1) / BK;
+        mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + ab * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: the 4 k-steps live inside one 128B swizzle row -> +32 bytes each.
+            // MN-major: each k-step is one 8-row (1024 B) swizzle atom; MN blocks 4096 B apart.
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 1024, 4096, 1024)
+                                        : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 1024, 4096, 1024)
+                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[ab]);  // accumulator complete -> epilogue
+        ab ^= 1;
+        if (ab == 0) ab_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    float* scratch = scratch_all + (warp - 2) * (32 * 33);
+    int ab = 0;
+    uint32_t ab_phase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(g, tile);
+      const DevProblem& pr = g.p[tc.prob];
+      const int n0 = tc.n0 * BN;
+      const int row_base = tc.m0 + q * 32;
+      mbar_wait(&tmem_full_bar[ab], ab_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= pr.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < pr.N;
+        const float bias = (pr.bias && col_ok) ? __ldg(pr.bias + col) : 0.f;
+        const float slope = (pr.slope && col_ok) ? __ldg(pr.slope + col) : pr.leaky;
+        const float rsc = (pr.res_scale && col_ok) ? __ldg(pr.res_scale + col) : 1.f;
+        const int rows = min(32, pr.M - row_base);
+#pragma unroll 4
+        for (int i = 0; i < rows; ++i) {
+          const int row = row_base + i;
+          float x = scratch[i * 33 + lane] * pr.alpha + bias;
+          if (pr.act == F2G_ACT_PRELU || pr.act == F2G_ACT_LEAKY) {
+            x = x > 0.f ? x : x * slope;
+          } else if (pr.act == F2G_ACT_SILU) {
+            x = x / (1.f + __expf(-x));
+          }
+          if (col_ok) {
+            if (pr.gate) {  // multiply by d(act)/dz evaluated at a saved pre-activation
+              const float z = __ldg(pr.gate + (size_t)row * pr.ld_gate + col);
+              x *= (z > 0.f ? 1.f : slope);
+            }
+            if (pr.res) x += rsc * __ldg(pr.res + (size_t)row * pr.ld_res + col);
+            if (pr.row_scale) x *= __ldg(pr.row_scale + row);
+            float* dst = pr.c + (size_t)row * pr.ldc + col;
+            if (pr.accumulate) x += *dst;
+            *dst = pr.round_tf32 ? tf32_rna(x) : x;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+      ab ^= 1;
+      if (ab == 0) ab_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable (%d)", (int)e);
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D fp32 tensor map, 128B swizzle.  dims/strides innermost first; box = {32, box_rows}.
+static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
+                     uint64_t outer_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return F2G_EDRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems % 4) != 0) {
+    set_error("gemm operand must be 16B aligned with a leading dimension multiple of 4 floats "
+              "(ptr=%p ld=%llu)", (const void*)base, (unsigned long long)outer_stride_elems);
+    return F2G_EINVAL;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {outer_stride_elems * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer,
+              (unsigned long long)outer_stride_elems);
+    return F2G_EDRIVER;
+  }
+  return 0;
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch(const DevGroup& g, int num_sms, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g);
+  return check_launch("gemm_tf32");
+}
+
+static int g_num_sms = 0;
+
+int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
+  if (n < 1 || n > F2G_GEMM_MAX_PROBLEMS) {
+    set_error("gemm group size %d out of range", n);
+    return F2G_EINVAL;
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  DevGroup g;
+  memset(&g, 0, sizeof(g));
+  const int bn = descs[0].bn, a_mn = descs[0].a_mn, b_mn = descs[0].b_mn;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const F2GGemm& d = descs[i];
+    if (d.bn != bn || d.a_mn != a_mn || d.b_mn != b_mn) {
+      set_error("all problems of a gemm group must share bn / operand majors");
+      return F2G_EINVAL;
+    }
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) {
+      set_error("gemm problem %d has empty shape %dx%dx%d", i, d.M, d.N, d.K);
+      return F2G_EINVAL;
+    }
+    DevProblem& p = g.p[i];
+    int rc;
+    rc = a_mn ? encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32) : encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, BM);
+    if (rc) return rc;
+    rc = b_mn ? encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32) : encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn);
+    if (rc) return rc;
+    p.c = d.c; p.ldc = d.ldc;
+    p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
+    p.row_scale = d.row_scale; p.gate = d.gate;
+    p.ld_res = d.ld_res; p.ld_gate = d.ld_gate;
+    p.M = d.M; p.N = d.N; p.K = d.K;
+    p.m_tiles = (d.M + BM - 1) / BM;
+    p.n_tiles = (d.N + bn - 1) / bn;
+    p.tile_begin = tiles;
+    p.act = d.act; p.round_tf32 = d.round_tf32; p.accumulate = d.accumulate;
+    p.leaky = d.leaky; p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
+    tiles += p.m_tiles * p.n_tiles;
+  }
+  g.n_problems = n;
+  g.total_tiles = tiles;
+
+#define F2G_DISPATCH(BN_)                                                        \
+  if (bn == BN_) {                                                               \
+    if (!a_mn && !b_mn) return launch<BN_, 0, 0>(g, g_num_sms, stream);         \
+    if (!a_mn && b_mn) return launch<BN_, 0, 1>(g, g_num_sms, stream);          \
+    if (a_mn && b_mn) return launch<BN_, 1, 1>(g, g_num_sms, stream);           \
+    if (a_mn && !b_mn) return launch<BN_, 1, 0>(g, g_num_sms, stream);          \
+  }
+  F2G_DISPATCH(64)
+  F2G_DISPATCH(128)
+  F2G_DISPATCH(256)
+#undef F2G_DISPATCH
+  set_error("unsupported gemm tile width bn=%d (64/128/256)", bn);
+  return F2G_EINVAL;
+}
+
+}  // namespace f2g

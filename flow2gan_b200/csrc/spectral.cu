@@ -1,0 +1,296 @@
+// STFT / iSTFT family: framing + periodic-hann window + shared-memory Stockham FFT, fused
+// packing / magnitude / filterbank / log epilogues; inverse path = irfft frames + overlap-add
+// + envelope divide + branch fusion + Euler update.  All HBM-bound SIMT kernels.
+// Reference semantics: torch.stft / torch.istft (center=True, reflect pad, onesided) as called
+// from flow2gan/models/modules.py:68-84,105-116 and the torchaudio (Mel)Spectrogram wrappers.
+#include "common.cuh"
+#include "../../include/flow2gan_b200.h"
+
+namespace f2g {
+
+F2G_DEVINL float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Radix-2 Stockham autosort FFT over n = 1 << logn complex points held in shared memory.
+// tw[k] = exp(+2*pi*i*k/n), k < n/2.  Natural order in, natural order out.  Returns the buffer
+// that holds the result.  All threads of the block must call it.
+template <bool INVERSE>
+F2G_DEVINL float2* block_fft(float2* a, float2* b, const float2* tw, int n, int logn) {
+  const int half = n >> 1;
+  for (int s = 0; s < logn; ++s) {
+    const int ns = 1 << s;
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+      const int k = j & (ns - 1);
+      float2 w = tw[k * (half >> s)];
+      if (!INVERSE) w.y = -w.y;
+      const float2 v0 = a[j];
+      const float2 v1 = cmul(a[j + half], w);
+      const int j0 = ((j - k) << 1) + k;
+      b[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+      b[j0 + ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+    }
+    __syncthreads();
+    float2* t = a;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+F2G_DEVINL void fill_twiddles(float2* tw, int n) {
+  for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)k / (float)n, &s, &c);
+    tw[k] = make_float2(c, s);
+  }
+}
+
+// periodic hann from the twiddle table: w[i] = 0.5 - 0.5 cos(2 pi i / n)
+F2G_DEVINL float hann_from_tw(const float2* tw, int i, int n) {
+  const int h = n >> 1;
+  return i < h ? 0.5f - 0.5f * tw[i].x : 0.5f + 0.5f * tw[i - h].x;
+}
+
+__global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
+                            int hop, int frames, int mode, const float* __restrict__ pre,
+                            const float* __restrict__ fb, int n_filt, float log_clip,
+                            float* __restrict__ out, int ld_out, int round_tf32) {
+  extern __shared__ float2 sm[];
+  float2* a = sm;
+  float2* b = sm + n;
+  float2* tw = sm + 2 * n;
+  float* spec = reinterpret_cast<float*>(sm + 2 * n + (n >> 1));
+
+  const int row = blockIdx.x;
+  const int bi = row / frames;
+  const int f = row - bi * frames;
+  const int nb = (n >> 1) + 1;
+
+  fill_twiddles(tw, n);
+  __syncthreads();
+
+  float sub = 0.f, mul = 1.f;
+  if (pre) {
+    sub = pre[2 * bi];
+    mul = pre[2 * bi + 1];
+  }
+  const float* x = audio + (size_t)bi * ld_audio;
+  const int start = f * hop - (n >> 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int p = start + i;
+    if (p < 0) p = -p;
+    if (p >= T) p = 2 * (T - 1) - p;
+    const float v = (x[p] - sub) * mul;
+    a[i] = make_float2(v * hann_from_tw(tw, i, n), 0.f);
+  }
+  __syncthreads();
+  const float2* X = block_fft<false>(a, b, tw, n, logn);
+
+  float* o = out + (size_t)row * ld_out;
+  if (mode == F2G_SPEC_PACKED) {
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      const float2 v = X[k];
+      o[k] = round_tf32 ? tf32_rna(v.x) : v.x;
+      o[nb + k] = round_tf32 ? tf32_rna(v.y) : v.y;
+    }
+    for (int k = 2 * nb + threadIdx.x; k < ld_out; k += blockDim.x) o[k] = 0.f;
+    return;
+  }
+  // magnitude / power, optionally contracted with a filterbank
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    const float2 v = X[k];
+    const float p2 = v.x * v.x + v.y * v.y;
+    const float m = mode == F2G_SPEC_POWER ? p2 : sqrtf(p2);
+    if (fb) spec[k] = m;
+    else o[k] = round_tf32 ? tf32_rna(m) : m;
+  }
+  if (!fb) return;
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_filt; m += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < nb; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
+    if (log_clip > 0.f) acc = logf(fmaxf(acc, log_clip));
+    o[m] = round_tf32 ? tf32_rna(acc) : acc;
+  }
+}
+
+__global__ void irfft_frames_kernel(const float* __restrict__ packed, int ld, int n, int logn,
+                                    float* __restrict__ frames_out) {
+  extern __shared__ float2 sm[];
+  float2* a = sm;
+  float2* b = sm + n;
+  float2* tw = sm + 2 * n;
+  const int row = blockIdx.x;
+  const int nb = (n >> 1) + 1;
+  const float* p = packed + (size_t)row * ld;
+
+  fill_twiddles(tw, n);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    float re, im;
+    if (k < nb) {
+      re = p[k];
+      im = (k == 0 || k == (n >> 1)) ? 0.f : p[nb + k];   // C2R ignores Im(DC), Im(Nyquist)
+    } else {
+      const int kk = n - k;
+      re = p[kk];
+      im = -p[nb + kk];
+    }
+    a[k] = make_float2(re, im);
+  }
+  __syncthreads();
+  const float2* y = block_fft<true>(a, b, tw, n, logn);
+  const float inv_n = 1.0f / (float)n;
+  float* o = frames_out + (size_t)row * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    o[i] = y[i].x * inv_n * hann_from_tw(tw, i, n);
+}
+
+struct OlaArgs {
+  const float* fr[4];
+  int n[4], hop[4], frames[4];
+  int nb;
+};
+
+__global__ void ola_combine_kernel(OlaArgs a, const float* __restrict__ weight,
+                                   const float* __restrict__ x, float* __restrict__ out, int T,
+                                   int euler, float t, float dt, int clamp) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bi = blockIdx.y;
+  if (s >= T) return;
+  float pred = 0.f;
+  for (int j = 0; j < a.nb; ++j) {
+    const int n = a.n[j], hop = a.hop[j], F = a.frames[j];
+    float v = 0.f;
+    if (s < hop * (F - 1)) {
+      const int p = s + (n >> 1);
+      const int f_hi = min(p / hop, F - 1);
+      const int f_lo = p >= n ? (p - n) / hop + 1 : 0;
+      float acc = 0.f, env = 0.f;
+      for (int f = f_lo; f <= f_hi; ++f) {
+        const int i = p - f * hop;
+        acc += a.fr[j][((size_t)bi * F + f) * n + i];
+        const float w = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)n);
+        env += w * w;
+      }
+      v = acc / env;
+    }
+    const float wgt = weight ? weight[bi * a.nb + j] : 1.0f / (float)a.nb;
+    pred += v * wgt;
+  }
+  float r = pred;
+  if (euler) {
+    const float xv = x[(size_t)bi * T + s];
+    r = xv + ((pred - xv) / (1.0f - t)) * dt;
+  }
+  if (clamp) r = fminf(fmaxf(r, -1.0f), 1.0f);
+  out[(size_t)bi * T + s] = r;
+}
+
+__global__ void dc_peak_kernel(const float* __restrict__ audio, int T, int ld, float* __restrict__ pre) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  const float* x = audio + (size_t)blockIdx.x * ld;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) bc = v / (float)T;
+  }
+  __syncthreads();
+  const float mean = bc;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) m = fmaxf(m, fabsf(x[i] - mean));
+  m = warp_max(m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0) {
+      pre[2 * blockIdx.x] = mean;
+      pre[2 * blockIdx.x + 1] = 0.8f / (v + 1e-9f);
+    }
+  }
+}
+
+static int ilog2_exact(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return (1 << l) == n ? l : -1;
+}
+
+}  // namespace f2g
+
+using namespace f2g;
+
+extern "C" int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
+                        const float* pre, const float* fb, int n_filt, float log_clip, float* out,
+                        int ld_out, int round_tf32, void* stream) {
+  const int logn = ilog2_exact(n_fft);
+  if (logn < 5 || n_fft > 2048) {
+    set_error("f2g_stft: n_fft=%d must be a power of two in [32, 2048]", n_fft);
+    return F2G_EINVAL;
+  }
+  if (n_fft / 2 >= T) {
+    set_error("f2g_stft: reflect padding needs n_fft/2 (%d) < T (%d)", n_fft / 2, T);
+    return F2G_EINVAL;
+  }
+  if (mode != F2G_SPEC_PACKED && mode != F2G_SPEC_MAG && mode != F2G_SPEC_POWER) {
+    set_error("f2g_stft: bad mode %d", mode);
+    return F2G_EINVAL;
+  }
+  const int frames = 1 + T / hop;
+  const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
+  const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2) + (n_fft / 2 + 1) * sizeof(float);
+  stft_kernel<<<B * frames, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      audio, T, ld_audio, n_fft, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out,
+      round_tf32);
+  return check_launch("f2g_stft");
+}
+
+extern "C" int f2g_dc_peak(const float* audio, int B, int T, int ld_audio, float* pre, void* stream) {
+  dc_peak_kernel<<<B, 512, 0, static_cast<cudaStream_t>(stream)>>>(audio, T, ld_audio, pre);
+  return check_launch("f2g_dc_peak");
+}
+
+extern "C" int f2g_irfft_frames(const float* packed, int rows, int ld, int n_fft, float* frames_out,
+                                void* stream) {
+  const int logn = ilog2_exact(n_fft);
+  if (logn < 5 || n_fft > 2048) {
+    set_error("f2g_irfft_frames: n_fft=%d must be a power of two in [32, 2048]", n_fft);
+    return F2G_EINVAL;
+  }
+  const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
+  const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2);
+  irfft_frames_kernel<<<rows, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      packed, ld, n_fft, logn, frames_out);
+  return check_launch("f2g_irfft_frames");
+}
+
+extern "C" int f2g_ola_combine(const float* const* frames, const int* n_ffts, const int* hops,
+                               const int* n_frames, int nb, const float* weight, const float* x,
+                               float* out, int B, int T, int euler, float t, float dt, int clamp,
+                               void* stream) {
+  if (nb < 1 || nb > 4) {
+    set_error("f2g_ola_combine: nb=%d out of range", nb);
+    return F2G_EINVAL;
+  }
+  OlaArgs a;
+  a.nb = nb;
+  for (int j = 0; j < nb; ++j) {
+    a.fr[j] = frames[j];
+    a.n[j] = n_ffts[j];
+    a.hop[j] = hops[j];
+    a.frames[j] = n_frames[j];
+  }
+  dim3 grid((T + 255) / 256, B);
+  ola_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, weight, x, out, T,
+                                                                          euler, t, dt, clamp);
+  return check_launch("f2g_ola_combine");
+}

@@ -1,0 +1,320 @@
+"""Inference engine: runs MelAudioGenerator.infer / BaseAudioGenerator.infer
+(flow2gan/models/generator.py:236-271,327-366) as a fixed launch sequence of the CUDA library
+(csrc/*.cu) over pre-packed weights and pre-allocated channel-last workspaces, captured in a
+CUDA graph per (batch, frames, length, n_timesteps) shape.
+
+What is restructured relative to the reference (results stay equal):
+  * activations are channel-last rows (b*T + t, C) so 1x1 convs are K-major TF32 GEMMs;
+  * cond_mlp / cond_proj (step-invariant, and computed by the reference at the upsampled frame
+    rate every ODE step) run once per call at mel-frame rate -- they commute with the frame
+    repetition of upsample_cond (modules.py:668-680); the zero-padded tail frame is served by
+    one extra all-zero conditioning row;
+  * the three branches' same-stage GEMMs are one grouped persistent launch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _params_signature(model: torch.nn.Module) -> Tuple[int, int]:
+    v, p0 = 0, 0
+    for p in model.parameters():
+        v += p._version
+        p0 ^= p.data_ptr()
+    return v, p0
+
+
+def _pack(src: Tensor, rows: int, cols: int, rs: int, cs: int, ld: int, rnd: int = 1,
+          dst: Optional[Tensor] = None, dst_col: int = 0, dst_row: int = 0) -> Tensor:
+    """dst[dst_row + r, dst_col + c] = src.flat[r*rs + c*cs]  (TF32-rounded by default)."""
+    if dst is None:
+        dst = torch.zeros(rows, ld, device=src.device, dtype=torch.float32)
+    assert src.is_contiguous() and src.dtype == torch.float32
+    dptr = dst.data_ptr() + 4 * (dst_row * dst.stride(0) + dst_col)
+    L.pack2d(src.data_ptr(), rs, cs, rows, cols, dptr, dst.stride(0), cols, rnd)
+    return dst
+
+
+class _BlockW:
+    """Per-ConvNeXtBlock packed matrices + direct pointers to the small vectors."""
+
+    def __init__(self, blk):
+        C, H = blk.channels, blk.hidden_channels
+        self.C, self.H = C, H
+        self.blk = blk
+        self.dwT = _pack(blk.dwconv.weight.detach(), 7, C, 1, 7, C, rnd=0)          # (7, C)
+        self.W1 = _pack(blk.pwconv1.weight.detach(), H, C, C, 1, C)                  # (H, C)
+        self.W2 = _pack(blk.pwconv2.weight.detach(), C, H, H, 1, H)                  # (C, H)
+
+
+class PackedGenerator:
+    """GEMM-ready (TF32-rounded, 16B-aligned, concatenated) copies of the generator matrices.
+    Rebuilt automatically when the parameters change (signature over tensor versions)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.signature = None
+        self.refresh()
+
+    def stale(self) -> bool:
+        return _params_signature(self.model) != self.signature
+
+    def refresh(self) -> None:
+        m = self.model
+        with torch.no_grad():
+            ce = m.cond_encoder
+            nm = ce.cond_dim
+            self.ld_mel = _ceil(3 * nm, 4)
+            self.ce_Win = torch.zeros(ce.channels, self.ld_mel, device=ce.in_proj.weight.device)
+            for k in range(3):   # (Co, Ci, 3) -> column k*Ci + ci
+                w = ce.in_proj.weight.detach()
+                L.pack2d(w.data_ptr() + 4 * k, 3 * nm, 3, ce.channels, nm,
+                         self.ce_Win.data_ptr() + 4 * k * nm, self.ld_mel, nm, 1)
+            self.ce_blocks = [_BlockW(b) for b in ce.blocks]
+            self.branches = []
+            for est in m.estimators:
+                d = est.decoder
+                C, nin = d.channels, d.in_channels
+                ldp = _ceil(nin, 4)
+                br = type("BranchW", (), {})()
+                br.C, br.nin, br.ldp = C, nin, ldp
+                br.n_fft, br.hop = est.fft.n_fft, est.fft.hop_length
+                br.factor = est.cond_upsample_factor
+                br.dec = d
+                br.Win = _pack(d.in_proj.weight.detach(), C, nin, nin, 1, ldp)
+                br.Wout = _pack(d.out_proj.weight.detach(), nin, C, C, 1, C)
+                cc = d.cond_mlp[0].weight.shape[1]
+                ch = d.cond_mlp[0].weight.shape[0]
+                br.cc, br.ch = cc, ch
+                br.cmW0 = _pack(d.cond_mlp[0].weight.detach(), ch, cc, cc, 1, cc)
+                br.cmW2 = _pack(d.cond_mlp[2].weight.detach(), cc, ch, ch, 1, ch)
+                nl = len(d.blocks)
+                br.nl = nl
+                te = d.time_mlp[0].weight.shape[1]
+                br.te = te
+                br.Wcp = torch.zeros(nl * C, cc, device=br.Win.device)
+                br.bcp = torch.zeros(nl * C, device=br.Win.device)
+                br.Wte = torch.zeros(nl * C, te, device=br.Win.device)
+                br.bte = torch.zeros(nl * C, device=br.Win.device)
+                for i, blk in enumerate(d.blocks):
+                    _pack(blk.cond_proj.weight.detach(), C, cc, cc, 1, cc, dst=br.Wcp, dst_row=i * C)
+                    _pack(blk.time_embed_proj.weight.detach(), C, te, te, 1, te, rnd=0, dst=br.Wte,
+                          dst_row=i * C)
+                    br.bcp[i * C:(i + 1) * C].copy_(blk.cond_proj.bias.detach())
+                    br.bte[i * C:(i + 1) * C].copy_(blk.time_embed_proj.bias.detach())
+                br.blocks = [_BlockW(b) for b in d.blocks]
+                self.branches.append(br)
+        self.signature = _params_signature(m)
+
+
+def _g1(bw: _BlockW, a, h, M, bn=128):
+    b = bw.blk
+    return L.gemm_desc(a.data_ptr(), bw.W1.data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C, bw.H,
+                       bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
+                       act=L.ACT_PRELU, round_tf32=1)
+
+
+def _g2(bw: _BlockW, h, x, M, bn=128):
+    b = bw.blk
+    return L.gemm_desc(h.data_ptr(), bw.W2.data_ptr(), x.data_ptr(), M, bw.C, bw.H, bw.H, bw.H, bw.C,
+                       bn=bn, bias=b.pwconv2.bias.data_ptr(), res=x.data_ptr(), ld_res=bw.C,
+                       res_scale=b.residual_scale.scale.data_ptr())
+
+
+class InferencePlan:
+    """Workspaces + launch sequence for one (B, mel frames, T, masked?) shape."""
+
+    def __init__(self, model, packed: PackedGenerator, B: int, Fm: int, T: int, masked: bool):
+        self.m, self.pk = model, packed
+        self.B, self.Fm, self.T, self.masked = B, Fm, T, masked
+        dev = next(model.parameters()).device
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        ce = model.cond_encoder
+        self.n_mels = ce.cond_dim
+        self.Cc = ce.channels
+        self.Rc = B * Fm + 1                      # + one all-zero conditioning row
+        self.mel = z(B, self.n_mels, Fm)
+        self.mel_cl = z(B * Fm, packed.ld_mel)
+        self.c0 = z(self.Rc, self.Cc)
+        self.ce_a1 = z(self.Rc, self.Cc)
+        self.ce_h = z(self.Rc, ce.blocks[0].hidden_channels)
+        self.x_audio = z(B, T)
+        self.lens = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.freqs = model.estimators[0].decoder.time_embed.freqs(dev)
+        self.te_dim = model.estimators[0].decoder.time_embed.dim
+        self.emb = z(B, self.te_dim)
+        self.br = []
+        for bw in packed.branches:
+            w = type("BranchWS", (), {})()
+            w.F = 1 + T // bw.hop
+            w.R = B * w.F
+            w.pin = z(w.R, bw.ldp)
+            w.x = z(w.R, bw.C)
+            w.a1 = z(w.R, bw.C)
+            w.h = z(w.R, bw.blocks[0].H)
+            w.pout = z(w.R, bw.ldp)
+            w.fr = z(w.R, bw.n_fft)
+            w.te1 = z(B, bw.dec.time_mlp[0].weight.shape[0])
+            w.te2 = z(B, bw.te)
+            w.ts = z(B, bw.nl * bw.C)
+            w.cm_h = z(self.Rc, bw.ch)
+            w.c1 = z(self.Rc, bw.cc)
+            w.cp = z(self.Rc, bw.nl * bw.C)
+            w.mask = z(w.R) if masked else None
+            self.br.append(w)
+        self.t_all: Optional[Tensor] = None
+        self.graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
+
+    # ------------------------------------------------------------------ step-invariant part
+    def encode_cond(self) -> None:
+        m, pk, B, Fm = self.m, self.pk, self.B, self.Fm
+        ce = m.cond_encoder
+        M = B * Fm
+        L.im2col_cf(self.mel, B, self.n_mels, Fm, 3, self.mel_cl, pk.ld_mel, 1)
+        L.gemm_group([L.gemm_desc(self.mel_cl.data_ptr(), pk.ce_Win.data_ptr(), self.c0.data_ptr(),
+                                  M, self.Cc, 3 * self.n_mels, pk.ld_mel, pk.ld_mel, self.Cc,
+                                  bias=ce.in_proj.bias.data_ptr())])
+        L.biasnorm(self.c0, M, self.Cc, self.Cc, ce.in_norm.bias, ce.in_norm.log_scale, self.c0, self.Cc)
+        for bw in pk.ce_blocks:
+            b = bw.blk
+            L.block_pre(self.c0, B, Fm, bw.C, bw.C, bw.dwT, b.dwconv.bias, b.norm.bias,
+                        b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C)
+            L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M)])
+            L.gemm_group([_g2(bw, self.ce_h, self.c0, M)])
+        self.cond_paths()
+
+    def cond_paths(self) -> None:
+        """cond_mlp + all cond_proj of every branch at mel-frame rate (+ the zero row)."""
+        pk, Rc = self.pk, self.Rc
+        ds = []
+        for bw, w in zip(pk.branches, self.br):
+            cm = bw.dec.cond_mlp
+            ds.append(L.gemm_desc(self.c0.data_ptr(), bw.cmW0.data_ptr(), w.cm_h.data_ptr(), Rc, bw.ch,
+                                  bw.cc, bw.cc, bw.cc, bw.ch, bias=cm[0].bias.data_ptr(),
+                                  slope=cm[1].weight.data_ptr(), act=L.ACT_PRELU, round_tf32=1))
+        L.gemm_group(ds)
+        ds = []
+        for bw, w in zip(pk.branches, self.br):
+            cm = bw.dec.cond_mlp
+            ds.append(L.gemm_desc(w.cm_h.data_ptr(), bw.cmW2.data_ptr(), w.c1.data_ptr(), Rc, bw.cc,
+                                  bw.ch, bw.ch, bw.ch, bw.cc, bias=cm[2].bias.data_ptr(), round_tf32=1))
+        L.gemm_group(ds)
+        ds = []
+        for bw, w in zip(pk.branches, self.br):
+            N = bw.nl * bw.C
+            ds.append(L.gemm_desc(w.c1.data_ptr(), bw.Wcp.data_ptr(), w.cp.data_ptr(), Rc, N, bw.cc,
+                                  bw.cc, bw.cc, N, bias=bw.bcp.data_ptr()))
+        L.gemm_group(ds)
+
+    # ------------------------------------------------------------------ one model evaluation
+    def process_model(self, t_dev: Tensor) -> None:
+        """x_audio, cond (cp) -> per-branch windowed iSTFT frames (w.fr).  t_dev: (B,) device."""
+        pk, B, T, Fm = self.pk, self.B, self.T, self.Fm
+        for bw, w in zip(pk.branches, self.br):
+            L.stft(self.x_audio, B, T, T, bw.n_fft, bw.hop, L.SPEC_PACKED, w.pin, bw.ldp, round_tf32=1)
+        L.gemm_group([L.gemm_desc(w.pin.data_ptr(), bw.Win.data_ptr(), w.x.data_ptr(), w.R, bw.C,
+                                  bw.nin, bw.ldp, bw.ldp, bw.C, bias=bw.dec.in_proj.bias.data_ptr())
+                      for bw, w in zip(pk.branches, self.br)])
+        for bw, w in zip(pk.branches, self.br):
+            L.biasnorm(w.x, w.R, bw.C, bw.C, bw.dec.in_norm.bias, bw.dec.in_norm.log_scale, w.x, bw.C)
+        L.time_sinusoid(t_dev, B, self.te_dim, self.freqs, 1000.0, self.emb)
+        for bw, w in zip(pk.branches, self.br):
+            tm = bw.dec.time_mlp
+            H = tm[0].weight.shape[0]
+            L.linear_small(self.emb, B, bw.te, self.te_dim, tm[0].weight, bw.te, tm[0].bias, H,
+                           L.ACT_SILU, w.te1, H)
+            L.linear_small(w.te1, B, H, H, tm[2].weight, H, tm[2].bias, bw.te, L.ACT_NONE, w.te2, bw.te)
+            L.linear_small(w.te2, B, bw.te, bw.te, bw.Wte, bw.te, bw.bte, bw.nl * bw.C, L.ACT_NONE,
+                           w.ts, bw.nl * bw.C)
+        nl = pk.branches[0].nl
+        for i in range(nl):
+            for bw, w in zip(pk.branches, self.br):
+                k = bw.blocks[i]
+                b = k.blk
+                ldc = bw.nl * bw.C
+                L.block_pre(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
+                            b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm, bw.factor,
+                            B * Fm, w.ts[:, i * bw.C:], ldc, w.a1, bw.C)
+            L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
+            L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R) for bw, w in zip(pk.branches, self.br)])
+        L.gemm_group([L.gemm_desc(w.x.data_ptr(), bw.Wout.data_ptr(), w.pout.data_ptr(), w.R, bw.nin,
+                                  bw.C, bw.C, bw.C, bw.ldp, bias=bw.dec.out_proj.bias.data_ptr(),
+                                  row_scale=L.ptr(w.mask))
+                      for bw, w in zip(pk.branches, self.br)])
+        for bw, w in zip(pk.branches, self.br):
+            L.irfft_frames(w.pout, w.R, bw.ldp, bw.n_fft, w.fr)
+
+    def combine(self, out: Tensor, euler: bool, t: float, dt: float, clamp: bool,
+                weight: Optional[Tensor] = None) -> None:
+        pk = self.pk
+        L.ola_combine([w.fr for w in self.br], [bw.n_fft for bw in pk.branches],
+                      [bw.hop for bw in pk.branches], [w.F for w in self.br], weight, self.x_audio,
+                      out, self.B, self.T, euler, t, dt, clamp)
+
+    # ------------------------------------------------------------------ Euler sampler
+    def _prepare_steps(self, n: int):
+        t_span = torch.linspace(0, 1, n + 1)                       # generator.py:253
+        dt = float(t_span[1] - t_span[0])
+        ts = [float(t_span[k]) for k in range(n)]
+        self.t_all = t_span[:n].to(self.x_audio.device).unsqueeze(1).expand(n, self.B).contiguous()
+        return ts, dt
+
+    def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
+        if with_cond:
+            self.encode_cond()
+        ts, dt = self._steps
+        for k in range(n):
+            self.process_model(self.t_all[k])
+            self.combine(self.x_audio, True, ts[k], dt, clamp and k == n - 1)
+
+    def set_masks(self, lens: Tensor) -> None:
+        self.lens.copy_(lens.to(torch.int32))
+        for bw, w in zip(self.pk.branches, self.br):
+            L.frame_mask(self.lens, self.B, w.F, bw.hop, w.mask)
+
+    def infer(self, mel: Tensor, noise: Tensor, lens: Optional[Tensor], n: int, clamp: bool,
+              use_graph: bool = True) -> Tensor:
+        self.mel.copy_(mel)
+        self.x_audio.copy_(noise)
+        if self.masked:
+            self.set_masks(lens)
+        key = (n, bool(clamp))
+        if not use_graph:
+            self._steps = self._prepare_steps(n)
+            self._run(n, clamp)
+            return self.x_audio.clone()
+        g = self.graphs.get(key)
+        if g is None:
+            self._steps = self._prepare_steps(n)
+            self._run(n, clamp)                     # warm-up (also sets kernel attributes)
+            self.x_audio.copy_(noise)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(n, clamp)
+            self.graphs[key] = (g, self._steps, self.t_all)
+        else:
+            g, self._steps, self.t_all = g
+        g.replay()
+        return self.x_audio.clone()
+
+    def infer_from_cond(self, cond: Tensor, noise: Tensor, lens: Optional[Tensor], n: int,
+                        clamp: bool) -> Tensor:
+        """BaseAudioGenerator.infer entry: `cond` is an already-encoded (B, C, Fm) tensor."""
+        self.c0[: self.B * self.Fm].copy_(cond.transpose(1, 2).reshape(self.B * self.Fm, self.Cc))
+        self.x_audio.copy_(noise)
+        if self.masked:
+            self.set_masks(lens)
+        self._steps = self._prepare_steps(n)
+        self.cond_paths()
+        self._run(n, clamp, with_cond=False)
+        return self.x_audio.clone()

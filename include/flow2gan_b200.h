@@ -1,0 +1,151 @@
+/* flow2gan_b200 -- C ABI of the B200-native (sm_100a) Flow2GAN hot path.
+ *
+ * The reference (k2-fsa/Flow2GAN) has no FFI / plugin layer: its boundary is the Python
+ * nn.Module surface.  This header is therefore the NEW native boundary
+ * that the Python host layer (flow2gan_b200/*.py, mirroring flow2gan/models/*.py) binds through
+ * ctypes.  Every entry point:
+ *   - takes plain device pointers (fp32 unless noted), sizes and an explicit cudaStream_t
+ *     (passed as void*); the caller owns all memory (torch tensors on the Python side);
+ *   - launches asynchronously on that stream, spawns no threads, keeps no per-call state;
+ *   - returns 0 on success, a positive cudaError_t or a negative F2G_E* code otherwise;
+ *     f2g_last_error() returns the message (the Python layer raises RuntimeError with it).
+ *
+ * Activation layout: "token-major / channel-last" -- a (B, C, T) tensor of the reference is
+ * held as rows = b*T + t, columns = channel, leading dimension `ld` (multiple of 4 floats).
+ * Each function cites the reference code it replaces (paths relative to /root/reference).
+ */
+#ifndef FLOW2GAN_B200_H_
+#define FLOW2GAN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F2G_ABI_VERSION 1
+#define F2G_GEMM_MAX_PROBLEMS 8
+
+enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
+enum { F2G_SPEC_PACKED = 0, F2G_SPEC_MAG = 1, F2G_SPEC_POWER = 2, F2G_SPEC_COMPLEX_BANDS = 3 };
+
+int f2g_abi_version(void);
+const char* f2g_last_error(void);
+/* Fails (F2G_EARCH) unless the current device is compute capability 10.x. */
+int f2g_check_device(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Tensor-core contraction  C[M,N] = epi(alpha * A[M,K] . B[N,K]^T)   (tcgen05 kind::tf32)
+ * replaces: nn.Conv1d(kernel_size=1) / nn.Linear (flow2gan/models/modules.py:443-451,
+ * 563,570-579,593) and, via overlapping-row operands, nn.Conv2d of the discriminators
+ * (flow2gan/models/discriminators.py:65-76,171-184) plus their dgrad / wgrad.
+ *   a_mn = 0: A is K-major, element (m,k) at a[m*lda + k];  a_mn = 1: MN-major, a[k*lda + m].
+ *   b_mn = 0: B is K-major, element (n,k) at b[n*ldb + k];  b_mn = 1: MN-major, b[k*ldb + n].
+ *   epilogue, in this order: x = alpha*acc + bias[n]; act (PReLU slope[n] / leaky / SiLU);
+ *   x *= (gate[m,n] > 0 ? 1 : slope[n]) if gate; x += res_scale[n] * res[m,n] if res;
+ *   x *= row_scale[m] if row_scale; x += C[m,n] if accumulate; round-to-nearest TF32 if asked.
+ * Up to F2G_GEMM_MAX_PROBLEMS problems sharing (bn, a_mn, b_mn) run as ONE persistent launch.
+ * ------------------------------------------------------------------------------------- */
+typedef struct F2GGemm {
+  const float* a;
+  const float* b;
+  float* c;
+  int M, N, K;
+  int lda, ldb, ldc;
+  int a_mn, b_mn;
+  int bn; /* N tile: 64, 128 or 256 */
+  const float* bias;
+  const float* slope;
+  const float* res;
+  const float* res_scale;
+  const float* row_scale;
+  const float* gate;
+  int ld_res, ld_gate;
+  int act;
+  float leaky;
+  float alpha; /* 0 means 1 */
+  int round_tf32;
+  int accumulate;
+} F2GGemm;
+
+int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * STFT family.  replaces torch.stft(center=True, reflect, periodic hann, onesided) as used by
+ * STFT.forward + fft_to_real (modules.py:31-38,68-84), torchaudio MelSpectrogram /
+ * Spectrogram (modules.py:131-143,180-214; gan.py:47-54; discriminators.py:163,186-196).
+ * audio: (B, T) rows of stride ld_audio.  frames = 1 + T/hop.  One CTA per frame.
+ *   mode PACKED : out[(b*frames+f)*ld_out + c] = Re(bin c), c<=n/2 ; Im at c + n/2+1
+ *   mode MAG    : |S|   (n/2+1 columns)          mode POWER : |S|^2
+ * pre (optional, (B,2)): sample -> (x - pre[b][0]) * pre[b][1] before windowing (MRD).
+ * fb (optional, (n/2+1, n_filt) row-major): if given, the MAG/POWER spectrum is contracted
+ * with fb in fp32 inside the kernel and out gets n_filt columns; log_clip > 0 applies
+ * log(max(., log_clip)) (safe_log, utils.py:221-232).
+ * ------------------------------------------------------------------------------------- */
+int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
+             const float* pre, const float* fb, int n_filt, float log_clip, float* out,
+             int ld_out, int round_tf32, void* stream);
+
+/* per-row DC removal + peak normalisation constants (discriminators.py:187-190):
+ * pre[b] = (mean_t x, 0.8 / (max_t |x - mean| + 1e-9)). */
+int f2g_dc_peak(const float* audio, int B, int T, int ld_audio, float* pre, void* stream);
+
+/* iSTFT stage 1: packed rows -> windowed time frames  fr[(b*frames+f)*n + i] =
+ * w[i] * irfft(spec)[i]   (real_to_fft + torch.istft inner part, modules.py:41-49,105-116). */
+int f2g_irfft_frames(const float* packed, int rows, int ld, int n_fft, float* frames_out,
+                     void* stream);
+
+/* iSTFT stage 2 for up to 3 branches + branch fusion + Euler update
+ * (modules.py:717-719, generator.py:136-168,263-265):
+ *   pred[b,s] = sum_j weight[b,j] * OLA_j(s) / env_j(s)   (0 beyond hop_j*(frames_j-1))
+ *   out = euler ? x + ((pred - x) / (1 - t)) * dt : pred ; optional clamp to [-1,1].
+ * weight: (B, nb) or NULL (=> 1/nb each, "mean").  x may alias out. */
+int f2g_ola_combine(const float* const* frames, const int* n_ffts, const int* hops,
+                    const int* n_frames, int nb, const float* weight, const float* x, float* out,
+                    int B, int T, int euler, float t, float dt, int clamp, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ConvNeXt-block pieces (modules.py:286-416,456-495), channel-last rows.
+ * ------------------------------------------------------------------------------------- */
+/* BiasNorm over the channel dim of each row: y = x * mean((x-bias)^2)^-1/2 * exp(log_scale);
+ * log_scale is a device scalar.  y may alias x. */
+int f2g_biasnorm(const float* x, int rows, int C, int ld, const float* bias,
+                 const float* log_scale, float* y, int ld_y, void* stream);
+
+/* Fused block prologue: mask -> depthwise conv k=7 (zero pad 3, bias) -> BiasNorm ->
+ * + cond_proj row -> * (1 + time scale) -> TF32 round.  (ConvNeXtBlock.forward :473-485)
+ *   x: (B*T, ld_x) rows; dw_wT: (7, C) transposed depthwise weights; row_mask: (B*T) or NULL;
+ *   cond: rows of ld_cond (or NULL); cond row for (b,t) = t < cond_T*factor ? b*cond_T +
+ *   t/factor : zero_row;  tscale: (B, ld_ts) holds time_embed_proj(te) (the "1 +" is added
+ *   here) or NULL.  Optionally also writes the pre-norm conv output (needed by backward). */
+int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, const float* dw_wT,
+                  const float* dw_b, const float* bn_bias, const float* bn_log_scale,
+                  const float* row_mask, const float* cond, int ld_cond, int cond_T, int factor,
+                  int zero_row, const float* tscale, int ld_ts, float* out, int ld_out,
+                  float* conv_out, float* inv_rms_out, void* stream);
+
+/* Small dense layer for (B <= 64)-row inputs, fp32 SIMT: out[b,o] = act(bias[o] + in[b,:].W[o,:])
+ * (time_mlp / time_embed_proj, modules.py:569-573,451,485). */
+int f2g_linear_small(const float* in, int B, int K, int ld_in, const float* W, int ldw,
+                     const float* bias, int O, int act, float* out, int ld_out, void* stream);
+
+/* SinusoidalPosEmb (modules.py:223-232): emb[b] = [sin(scale t f_i) ; cos(scale t f_i)], f_i
+ * from the caller's table freqs[dim/2] = exp(-i ln(10000)/(dim/2-1)). */
+int f2g_time_sinusoid(const float* t, int B, int dim, const float* freqs, float scale, float* out,
+                      void* stream);
+
+/* Generic strided 2-D gather used for weight packing / layout changes:
+ * dst[r*ld + c] = src[r*src_rs + c*src_cs] for c < cols, 0 for cols <= c < ld_fill. */
+int f2g_pack2d(const float* src, long long src_rs, long long src_cs, int rows, int cols,
+               float* dst, int ld, int ld_fill, int round_tf32, void* stream);
+
+/* (B, C, T) channel-first -> rows (b*T+t) x [k*C + c] im2col for a k-tap 'same' conv, zero
+ * padded in time; columns K*C..ld zeroed (CondEncoder.in_proj, modules.py:511,536). */
+int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, float* out, int ld,
+                  int round_tf32, void* stream);
+
+/* frame mask from lengths: m[b*frames+f] = f < 1 + lens[b]/hop (modules.py:79-82,706-707). */
+int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOW2GAN_B200_H_ */

@@ -1,0 +1,287 @@
+"""Unit parity tests of the CUDA kernels (through the C ABI / ctypes) against the CPU oracle.
+Tolerances: fp32 SIMT kernels 1e-5 rel-RMS; TF32 tensor-core GEMM with TF32-exact inputs 2e-6."""
+import math
+
+import pytest
+import torch
+
+from _cases import audio_input, rel_rms
+from oracle import flow2gan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32 on CPU: round-to-nearest (ties away) to 10 mantissa bits."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF)
+    return r.view(torch.float32)
+
+
+@pytest.fixture(scope="module")
+def L():
+    from flow2gan_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def _gemm_case(L, M, N, K, bn, a_mn=0, b_mn=0, epi="plain", lda_pad=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = tf32_round(torch.randn(M, K, generator=g))
+    Bm = tf32_round(torch.randn(N, K, generator=g))
+    lda = (K if not a_mn else M) + lda_pad
+    ldb = (K if not b_mn else N) + lda_pad
+    lda, ldb = (lda + 3) // 4 * 4, (ldb + 3) // 4 * 4
+    if a_mn:
+        Ad = torch.zeros(K, lda); Ad[:, :M] = A.t()
+    else:
+        Ad = torch.zeros(M, lda); Ad[:, :K] = A
+    if b_mn:
+        Bd = torch.zeros(K, ldb); Bd[:, :N] = Bm.t()
+    else:
+        Bd = torch.zeros(N, ldb); Bd[:, :K] = Bm
+    ldc = (N + 3) // 4 * 4 + 4
+    ref = (A.double() @ Bm.double().t())
+    bias = torch.randn(N, generator=g)
+    slope = torch.rand(N, generator=g) * 0.5
+    res = torch.randn(M, N, generator=g)
+    rsc = torch.rand(N, generator=g) + 0.5
+    rows = (torch.rand(M, generator=g) > 0.3).float()
+    gate = torch.randn(M, N, generator=g)
+    C0 = torch.randn(M, ldc, generator=g)
+    kw = {}
+    dev = "cuda"
+    keep = []
+
+    def d(t):
+        t = t.to(dev).contiguous(); keep.append(t); return t.data_ptr()
+
+    if epi == "plain":
+        exp = ref
+    elif epi == "bias_prelu_round":
+        z = ref + bias.double()
+        exp = tf32_round(torch.where(z > 0, z, z * slope.double()).float()).double()
+        kw = dict(bias=d(bias), slope=d(slope), act=L.ACT_PRELU, round_tf32=1)
+    elif epi == "res":
+        exp = ref + bias.double() + rsc.double() * res.double()
+        kw = dict(bias=d(bias), res=d(res), ld_res=N, res_scale=d(rsc))
+    elif epi == "rowscale_leaky":
+        z = ref * 0.5 + bias.double()
+        exp = torch.where(z > 0, z, z * 0.1) * rows.double()[:, None]
+        kw = dict(bias=d(bias), act=L.ACT_LEAKY, leaky=0.1, alpha=0.5, row_scale=d(rows))
+    elif epi == "gate_acc":
+        exp = ref * torch.where(gate > 0, 1.0, slope.double()[None].expand(M, N)) + C0[:, :N].double()
+        kw = dict(slope=d(slope), gate=d(gate), ld_gate=N, accumulate=1)
+    elif epi == "silu":
+        z = ref + bias.double()
+        exp = z * torch.sigmoid(z)
+        kw = dict(bias=d(bias), act=L.ACT_SILU)
+    Cd = C0.clone().to(dev)
+    Ag, Bg = Ad.to(dev), Bd.to(dev)
+    L.gemm_group([L.gemm_desc(Ag.data_ptr(), Bg.data_ptr(), Cd.data_ptr(), M, N, K, lda, ldb, ldc,
+                              bn=bn, a_mn=a_mn, b_mn=b_mn, **kw)])
+    torch.cuda.synchronize()
+    got = Cd.cpu()
+    assert torch.equal(got[:, N:], C0[:, N:]), "GEMM wrote outside its N columns"
+    tol = 3e-4 if epi in ("bias_prelu_round",) else 3e-6
+    err = rel_rms(got[:, :N], exp)
+    assert err < tol, (M, N, K, bn, a_mn, b_mn, epi, err)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 32, 128), (128, 64, 64, 64), (300, 256, 96, 128), (300, 256, 96, 256),
+    (1520, 2304, 768, 128), (1520, 768, 2304, 64), (333, 130, 130, 128), (97, 514, 768, 128),
+    (6032, 1152, 384, 256),
+])
+def test_gemm_tn_shapes(L, M, N, K, bn):
+    _gemm_case(L, M, N, K, bn)
+
+
+@pytest.mark.parametrize("epi", ["bias_prelu_round", "res", "rowscale_leaky", "gate_acc", "silu"])
+def test_gemm_epilogues(L, epi):
+    _gemm_case(L, 421, 384, 160, 128, epi=epi)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 128, 64, 128), (300, 200, 100, 128), (768, 2304, 1520, 256),
+                                      (200, 96, 333, 64)])
+def test_gemm_mn_major(L, a_mn, b_mn, M, N, K, bn):
+    _gemm_case(L, M, N, K, bn, a_mn=a_mn, b_mn=b_mn)
+
+
+def test_gemm_grouped(L):
+    g = torch.Generator().manual_seed(3)
+    descs, checks = [], []
+    for (M, N, K) in ((1520, 768, 514), (3024, 512, 258), (6032, 384, 130), (17, 384, 40)):
+        ld = (K + 3) // 4 * 4
+        A = torch.zeros(M, ld); A[:, :K] = tf32_round(torch.randn(M, K, generator=g))
+        Bm = torch.zeros(N, ld); Bm[:, :K] = tf32_round(torch.randn(N, K, generator=g))
+        Ag, Bg, Cg = A.cuda(), Bm.cuda(), torch.zeros(M, N).cuda()
+        descs.append(L.gemm_desc(Ag.data_ptr(), Bg.data_ptr(), Cg.data_ptr(), M, N, K, ld, ld, N))
+        checks.append((Ag, Bg, Cg, A[:, :K].double() @ Bm[:, :K].double().t()))
+    L.gemm_group(descs)
+    torch.cuda.synchronize()
+    for Ag, Bg, Cg, ref in checks:
+        assert rel_rms(Cg.cpu(), ref) < 3e-6
+
+
+@pytest.mark.parametrize("n_fft,hop", [(128, 64), (256, 128), (512, 256), (1024, 512), (32, 8), (2048, 512)])
+def test_stft_packed(L, n_fft, hop):
+    B, T = 3, 6144
+    x = audio_input(B, T, seed=n_fft)
+    ref = O.stft_packed(x, n_fft, hop)                 # (B, n+2, F)
+    F = ref.shape[-1]
+    ld = n_fft + 8
+    out = torch.full((B * F, ld), 7.0, device="cuda")
+    L.stft(x.cuda(), B, T, T, n_fft, hop, L.SPEC_PACKED, out, ld)
+    got = out.cpu().view(B, F, ld)[:, :, : n_fft + 2].transpose(1, 2)
+    assert rel_rms(got, ref) < 2e-6
+    assert float(out[:, n_fft + 2:].abs().max()) == 0.0
+
+
+def test_logmel_fused_vs_oracle_and_fixture():
+    import os
+    from _cases import GOLDEN
+    from flow2gan_b200.modules import LogMelSpectrogram
+    g = torch.load(os.path.join(GOLDEN, "mel_24k_short.pt"), weights_only=False)
+    wav = (g["pcm_int16"].float()[None] / 32768.0).cuda()
+    m = LogMelSpectrogram(24000, 1024, 256, 100).cuda()
+    got = m(wav).cpu()
+    assert got.shape == g["mel"].shape
+    assert rel_rms(got, g["mel"]) < 1e-5                       # the reference's own fixture
+    x = audio_input(2, 12000, seed=9)
+    assert rel_rms(m(x.cuda()).cpu(), O.log_mel(x)) < 1e-5
+    m44 = LogMelSpectrogram(44100, 2048, 512, 128).cuda()
+    assert rel_rms(m44(x.cuda()).cpu(), O.log_mel(x, 44100, 2048, 512, 128)) < 1e-5
+
+
+@pytest.mark.parametrize("n_fft", [128, 256, 512, 1024])
+def test_istft_roundtrip_and_oracle(L, n_fft):
+    hop = n_fft // 2
+    B, T = 2, 5000
+    g = torch.Generator().manual_seed(n_fft)
+    F = 1 + T // hop
+    p = torch.randn(B, n_fft + 2, F, generator=g)
+    ref = O.convert_length(O.istft_packed(p, n_fft, hop), T)
+    ld = n_fft + 4
+    rows = torch.zeros(B * F, ld)
+    rows[:, : n_fft + 2] = p.transpose(1, 2).reshape(B * F, n_fft + 2)
+    fr = torch.empty(B * F, n_fft, device="cuda")
+    L.irfft_frames(rows.cuda(), B * F, ld, n_fft, fr)
+    out = torch.empty(B, T, device="cuda")
+    L.ola_combine([fr], [n_fft], [hop], [F], None, None, out, B, T, False, 0.0, 0.0, False)
+    assert rel_rms(out.cpu(), ref) < 3e-6
+    # STFT -> iSTFT reconstructs the signal (size-independent property)
+    x = audio_input(B, T, seed=1)
+    pk = torch.empty(B * F, ld, device="cuda")
+    L.stft(x.cuda(), B, T, T, n_fft, hop, L.SPEC_PACKED, pk, ld)
+    L.irfft_frames(pk, B * F, ld, n_fft, fr)
+    L.ola_combine([fr], [n_fft], [hop], [F], None, None, out, B, T, False, 0.0, 0.0, False)
+    valid = hop * (F - 1)
+    assert rel_rms(out.cpu()[:, :valid], x[:, :valid]) < 3e-6
+    assert float(out[:, valid:].abs().max()) == 0.0
+
+
+def test_ola_combine_mean_euler_clamp(L):
+    B, T = 2, 4096
+    g = torch.Generator().manual_seed(5)
+    cfgs = [(512, 256), (256, 128), (128, 64)]
+    frs, outs = [], []
+    for n, h in cfgs:
+        F = 1 + T // h
+        p = torch.randn(B, n + 2, F, generator=g) * 3
+        outs.append(O.convert_length(O.istft_packed(p, n, h), T))
+        rows = p.transpose(1, 2).reshape(B * F, n + 2).contiguous()
+        fr = torch.empty(B * F, n, device="cuda")
+        L.irfft_frames(rows.cuda(), B * F, n + 2, n, fr)
+        frs.append(fr)
+    x = torch.randn(B, T, generator=g)
+    pred = torch.stack(outs, 1).mean(1)
+    t, dt = 0.25, 0.25
+    ref = (x + (pred - x) / (1 - torch.tensor(t)) * torch.tensor(dt)).clamp(-1, 1)
+    xg = x.cuda()
+    L.ola_combine(frs, [c[0] for c in cfgs], [c[1] for c in cfgs], [1 + T // c[1] for c in cfgs],
+                  None, xg, xg, B, T, True, t, dt, True)
+    assert rel_rms(xg.cpu(), ref) < 3e-6
+    w = torch.rand(B, 3, generator=g)
+    out = torch.empty(B, T, device="cuda")
+    L.ola_combine(frs, [c[0] for c in cfgs], [c[1] for c in cfgs], [1 + T // c[1] for c in cfgs],
+                  w.cuda(), None, out, B, T, False, 0.0, 0.0, False)
+    assert rel_rms(out.cpu(), (torch.stack(outs, 1) * w[:, :, None]).sum(1)) < 3e-6
+
+
+@pytest.mark.parametrize("C", [384, 512, 768])
+def test_biasnorm_and_block_pre(L, C):
+    B, T, Tc, factor = 2, 37, 9, 4
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, C, T, generator=g)
+    bias = torch.randn(C, generator=g) * 0.1
+    ls = torch.tensor(0.7)
+    ref = O.bias_norm(x, bias, ls)
+    xr = x.transpose(1, 2).reshape(B * T, C).contiguous().cuda()
+    y = torch.empty_like(xr)
+    L.biasnorm(xr, B * T, C, C, bias.cuda(), ls.cuda(), y, C)
+    assert rel_rms(y.cpu().view(B, T, C).transpose(1, 2), ref) < 2e-6
+    # fused prologue
+    dw = torch.randn(C, 1, 7, generator=g) * 0.3
+    dwb = torch.randn(C, generator=g) * 0.1
+    cond = torch.randn(B, C, Tc, generator=g)
+    zero_vec = torch.randn(C, generator=g)
+    ts = torch.randn(B, C, generator=g) * 0.3
+    lens = torch.tensor([T, T - 11])
+    mask = (torch.arange(T)[None] < lens[:, None]).float()
+    conv = torch.nn.functional.conv1d(x * mask[:, None], dw, dwb, padding=3, groups=C)
+    z = O.bias_norm(conv, bias, ls)
+    cup = torch.cat([cond.repeat_interleave(factor, 2),
+                     zero_vec[None, :, None].expand(B, C, T - Tc * factor)], 2)
+    ref = tf32_round(((z + cup) * (1 + ts[:, :, None])).contiguous())
+    crow = torch.cat([cond.transpose(1, 2).reshape(B * Tc, C), zero_vec[None]], 0).contiguous().cuda()
+    dwT = dw[:, 0, :].t().contiguous().cuda()
+    out = torch.empty(B * T, C, device="cuda")
+    conv_out = torch.empty(B * T, C, device="cuda")
+    L.block_pre(xr, B, T, C, C, dwT, dwb.cuda(), bias.cuda(), ls.cuda(), mask.reshape(-1).cuda(), crow, C,
+                Tc, factor, B * Tc, ts.cuda(), C, out, C, conv_out, None)
+    assert rel_rms(out.cpu().view(B, T, C).transpose(1, 2), ref) < 3e-4   # tf32 rounding ties
+    assert rel_rms(conv_out.cpu().view(B, T, C).transpose(1, 2), conv) < 2e-6
+
+
+def test_time_embedding_path(L):
+    B, dim = 5, 512
+    g = torch.Generator().manual_seed(0)
+    t = torch.rand(B, generator=g)
+    ref = O.sinusoidal_pos_emb(t, dim)
+    half = dim // 2
+    freqs = torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1)))
+    emb = torch.empty(B, dim, device="cuda")
+    L.time_sinusoid(t.cuda(), B, dim, freqs.cuda(), 1000.0, emb)
+    assert float((emb.cpu() - ref).abs().max()) < 2e-4        # sin/cos of arguments up to 1000
+    W = torch.randn(700, dim, generator=g) / math.sqrt(dim)
+    bb = torch.randn(700, generator=g)
+    out = torch.empty(B, 700, device="cuda")
+    L.linear_small(emb, B, dim, dim, W.cuda(), dim, bb.cuda(), 700, L.ACT_SILU, out, 700)
+    assert rel_rms(out.cpu(), torch.nn.functional.silu(emb.cpu() @ W.t() + bb)) < 2e-6
+
+
+def test_im2col_and_masks(L):
+    B, C, T = 2, 100, 13
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, C, T, generator=g)
+    ld = 304
+    out = torch.empty(B * T, ld, device="cuda")
+    L.im2col_cf(x.cuda(), B, C, T, 3, out, ld, 0)
+    xp = torch.nn.functional.pad(x, (1, 1))
+    ref = torch.zeros(B, T, ld)
+    for k in range(3):
+        ref[:, :, k * C:(k + 1) * C] = xp[:, :, k:k + T].transpose(1, 2)
+    assert torch.equal(out.cpu().view(B, T, ld), ref)
+    lens = torch.tensor([1000, 777], dtype=torch.int32)
+    m = torch.empty(2 * 9, device="cuda")
+    L.frame_mask(lens.cuda(), 2, 9, 128, m)
+    ref = (torch.arange(9)[None] < (1 + lens // 128)[:, None]).float()
+    assert torch.equal(m.cpu().view(2, 9), ref)
+    a = audio_input(3, 3000, seed=3) + 0.1
+    pre = torch.empty(3, 2, device="cuda")
+    L.dc_peak(a.cuda(), 3, 3000, 3000, pre)
+    mean = a.mean(-1)
+    sc = 0.8 / ((a - mean[:, None]).abs().max(-1)[0] + 1e-9)
+    assert rel_rms(pre.cpu(), torch.stack([mean, sc], 1)) < 1e-5
