@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark of the Flow2GAN hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-timesteps 1]
+
+A "step" = one `model.infer` of mel_24k_base on a synthetic (16, 100, 94) mel batch (bs=16 x
+~1 s of 24 kHz audio, 16 x 24064 samples), n_timesteps ODE steps (default 1 = the metric's
+configuration).  Prints ONE JSON line (rank 0).
+
+  value      : audio samples/s, inputs resident in HBM, K CUDA-graph replays timed with CUDA
+               events (max over ranks; N>1 = N independent replicas, weak scaling).
+  e2e        : the same through the public API with HOST buffers: pinned mel -> H2D ->
+               model.infer (draws its noise like the reference) -> D2H pinned audio, per step.
+  roofline   : tcgen05 TF32 GEMM launches: sum(2*M*N*K) / sum(CUDA-event launch time), measured
+               in an eager (non-graph) pass of the same step, against the measured tensor peak.
+  cpu_baseline / --impl reference : the oracle port (oracle/flow2gan_oracle.py, a functional
+               restatement of the reference's PyTorch path; the reference itself is Python and
+               cannot travel to the GPU box) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODEL = "mel_24k_base"
+B, N_MELS, FRAMES, HOP = 16, 100, 94, 256
+T = FRAMES * HOP
+SAMPLES_PER_STEP = B * T
+REF_FLOPS = {1: 347.6e9, 2: 675.8e9, 4: 1332.2e9}   # SURVEY.md section 8(d), conv/matmul FLOPs
+
+
+def synth_inputs():
+    from _cases import mel_input, noise_input
+    return mel_input(B, N_MELS, FRAMES, seed=0), noise_input(B, T, seed=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device):
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from oracle.synth import synth_state_dict
+    torch.manual_seed(0)
+    m = MelAudioGenerator(**get_generator_config(MODEL))
+    spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    m.load_state_dict(synth_state_dict(spec, 99), strict=False)
+    return m.to(device).eval()
+
+
+def cpu_oracle_rate(n_timesteps: int, iters: int, warmup: int = 1):
+    from oracle import flow2gan_oracle as O
+    from oracle.synth import synth_state_dict
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = MelAudioGenerator(**get_generator_config(MODEL))
+    spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    sd = synth_state_dict(spec, 99)
+    cfg = O.generator_config(MODEL)
+    mel, noise = synth_inputs()
+    times = []
+    with torch.inference_mode():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            O.generator_infer(sd, cfg, mel, noise, None, n_timesteps, False)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    tot = sum(times)
+    return SAMPLES_PER_STEP * len(times) / tot, tot / len(times) * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    rate, ms, cores = cpu_oracle_rate(args.n_timesteps, steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "audio samples/sec (bs=16, 1s, 24 kHz) %d-step infer" % args.n_timesteps,
+        "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL} {args.n_timesteps}-step inference, synthetic mel (16,100,94) -> (16,24064)",
+                   "global_batch": B, "note": "CPU oracle port of the reference PyTorch path (reference is "
+                   "Python and cannot travel to the GPU box); bounded sample of %d steps" % steps},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} x (bs=16, 1 s) {args.n_timesteps}-step calls"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from flow2gan_b200 import _lib as L
+    L.lib()
+    model = build_model(dev)
+    mel_h, noise_h = synth_inputs()
+    mel, noise = mel_h.to(dev), noise_h.to(dev)
+    n = args.n_timesteps
+    W = max(3, args.warmup)
+    K = args.steps
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        plan = model.plan(B, FRAMES, T, False)
+        plan.infer(mel, noise, None, n, False)          # builds + captures the CUDA graph
+        graph = plan.graphs[(n, False)][0]
+        # launches per replay: count C-ABI calls of one eager pass
+        L.COUNT = 0
+        plan._steps = plan._prepare_steps(n)
+        plan._run(n, False)
+        launches_per_step = L.COUNT
+        torch.cuda.synchronize()
+
+        # ---------------- kernel-only (HBM-resident inputs), K graph replays ----------------
+        for _ in range(W):
+            plan.x_audio.copy_(noise)
+            graph.replay()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            graph.replay()      # x_audio keeps evolving; the work per replay is data independent
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms_total = e0.elapsed_time(e1)
+        t_dev = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        ms_total = float(t_dev.item())
+        value = world * SAMPLES_PER_STEP * K / (ms_total * 1e-3)
+
+        # ---------------- end to end through the public API with host buffers ---------------
+        mel_pin = mel_h.pin_memory()
+        out_pin = torch.empty(B, T).pin_memory()
+        for _ in range(W):
+            out_pin.copy_(model.infer(mel_pin.to(dev, non_blocking=True), n_timesteps=n), non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e2.record()
+        for _ in range(K):
+            a = model.infer(mel_pin.to(dev, non_blocking=True), n_timesteps=n)
+            out_pin.copy_(a, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the caller consumes the audio
+        e3.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_e2e = max(e2.elapsed_time(e3), wall * 1e3)
+        t_dev = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        e2e_value = world * SAMPLES_PER_STEP * K / (float(t_dev.item()) * 1e-3)
+
+        # ---------------- roofline of the dominant kernel (tcgen05 TF32 GEMM) ---------------
+        roof = None
+        if rank == 0:
+            L.PROFILE = []
+            for _ in range(3):
+                plan.x_audio.copy_(noise)
+                plan._run(n, False)
+            torch.cuda.synchronize()
+            flops = sum(f for (_, _, f) in L.PROFILE)
+            ms = sum(a.elapsed_time(b) for (a, b, _) in L.PROFILE)
+            nl = len(L.PROFILE)
+            L.PROFILE = None
+            pk, how = peaks()
+            peak = pk["bf16_tflops_sustained"] / 2.0
+            ach = flops / (ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "launches_timed": nl, "flops_per_launch_avg": flops / nl, "us_per_launch_avg": ms * 1e3 / nl,
+                    "peak_source": f"{how}: bf16_tflops_sustained/2 (TF32 issues at half the bf16 rate)",
+                    "step_ref_equiv_tflops": REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12 / 1.0}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu_rate, cpu_ms, cores = cpu_oracle_rate(n, iters=3 if n == 1 else 1) if world == 1 else (None, None, None)
+    line = {
+        "metric": "audio samples/sec (bs=16, 1s, 24 kHz) %d-step infer" % n,
+        "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": f"{MODEL} {n}-step inference, synthetic mel (16,100,94) -> (16,24064) per GPU",
+                   "global_batch": B * world, "parallelism": f"replicas x{world} (no data-path collective)",
+                   "weights": "synthetic (seeded), reference state_dict layout",
+                   "l2": "no explicit flush: every step streams 316 MB of weights (> 126 MB L2)",
+                   "timed": "K CUDA-graph replays between two CUDA events"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * N_MELS * FRAMES * 4,
+                "d2h_bytes_per_step": B * T * 4},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if cpu_rate is not None:
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": f"{3 if n == 1 else 1} x (bs=16, 1 s) {n}-step calls, {cpu_ms:.0f} ms each"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-timesteps", type=int, default=1, choices=[1, 2, 4])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

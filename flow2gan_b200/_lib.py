@@ -61,6 +61,8 @@ _SIGS = {
 
 _lib: Optional[C.CDLL] = None
 _device_ok = False
+COUNT = 0            # native launches issued through this module (bench.py's gpu_launches)
+PROFILE = None       # when a list: gemm_group appends (start_event, end_event, flops)
 
 
 def exported_symbols() -> Sequence[str]:
@@ -99,6 +101,8 @@ def lib() -> C.CDLL:
 
 
 def _check(rc: int) -> None:
+    global COUNT
+    COUNT += 1
     if rc != 0:
         msg = load().f2g_last_error().decode(errors="replace")
         raise RuntimeError(f"flow2gan_b200 native call failed (rc={rc}): {msg}")
@@ -137,6 +141,13 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
 def gemm_group(descs: Sequence[F2GGemm]) -> None:
     n = len(descs)
     arr = (F2GGemm * n)(*descs)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(lib().f2g_gemm_tf32(arr, n, stream()))
+        e1.record()
+        PROFILE.append((e0, e1, sum(2.0 * d.M * d.N * d.K for d in descs)))
+        return
     _check(lib().f2g_gemm_tf32(arr, n, stream()))
 
 

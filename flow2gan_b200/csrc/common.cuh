@@ -171,6 +171,18 @@ F2G_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
 //   [46,48) version = 1 on sm_100, [49,52) base offset = 0, [61,64) layout type (2 = SWIZZLE_128B).
+//   layout type 1 = SWIZZLE_128B_BASE32B: the only layout legal for MN-major TF32 operands
+//   (32-byte chunks swizzled over 4-row groups; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+F2G_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
 F2G_DEVINL uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);

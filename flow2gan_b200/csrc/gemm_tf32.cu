@@ -17,6 +17,7 @@
 #include "gemm_tf32.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace f2g {
 
@@ -58,6 +59,9 @@ struct alignas(64) DevGroup {
   DevProblem p[F2G_GEMM_MAX_PROBLEMS];
   int n_problems;
   int total_tiles;
+  // MN-major operand descriptor geometry (bytes); defaults in gemm_tf32_group(), overridable
+  // through F2G_MN_* environment variables for bring-up experiments.
+  int mn_lbo, mn_sbo, mn_layout, mn_kstep;
 };
 
 struct TileCoord {
@@ -180,12 +184,15 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
           const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: the 4 k-steps live inside one 128B swizzle row -> +32 bytes each.
-            // MN-major: each k-step is one 8-row (1024 B) swizzle atom; MN blocks 4096 B apart.
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 1024, 4096, 1024)
-                                        : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 1024, 4096, 1024)
-                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            // K-major (SWIZZLE_128B): the 4 k-steps live inside one 128B swizzle row -> +32 B.
+            // MN-major (SWIZZLE_128B_BASE32B): a k-step is 8 rows = two 4-row (512 B) swizzle
+            // atoms -> +1024 B; 32-wide MN blocks (one TMA box each) are 4096 B apart.
+            const uint64_t adesc =
+                A_MN ? make_smem_desc(a_addr + k * g.mn_kstep, g.mn_lbo, g.mn_sbo, g.mn_layout)
+                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc =
+                B_MN ? make_smem_desc(b_addr + k * g.mn_kstep, g.mn_lbo, g.mn_sbo, g.mn_layout)
+                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -290,9 +297,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D fp32 tensor map, 128B swizzle.  dims/strides innermost first; box = {32, box_rows}.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
-                     uint64_t outer_stride_elems, uint32_t box_rows) {
+                     uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
+  static const int mn_swz = env_int("F2G_MN_TMA_SWIZZLE", (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (!fn) return F2G_EDRIVER;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems % 4) != 0) {
     set_error("gemm operand must be 16B aligned with a leading dimension multiple of 4 floats "
@@ -304,7 +317,8 @@ static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? (CUtensorMapSwizzle)mn_swz : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
@@ -362,9 +376,11 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     }
     DevProblem& p = g.p[i];
     int rc;
-    rc = a_mn ? encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32) : encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, BM);
+    rc = a_mn ? encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32, true)
+              : encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, BM, false);
     if (rc) return rc;
-    rc = b_mn ? encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32) : encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn);
+    rc = b_mn ? encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
+              : encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn, false);
     if (rc) return rc;
     p.c = d.c; p.ldc = d.ldc;
     p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
@@ -380,6 +396,9 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   }
   g.n_problems = n;
   g.total_tiles = tiles;
+  static const int mn_lbo = env_int("F2G_MN_LBO", 4096), mn_sbo = env_int("F2G_MN_SBO", 512),
+                   mn_layout = env_int("F2G_MN_LAYOUT", 1), mn_kstep = env_int("F2G_MN_KSTEP", 1024);
+  g.mn_lbo = mn_lbo; g.mn_sbo = mn_sbo; g.mn_layout = mn_layout; g.mn_kstep = mn_kstep;
 
 #define F2G_DISPATCH(BN_)                                                        \
   if (bn == BN_) {                                                               \

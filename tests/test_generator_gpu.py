@@ -14,6 +14,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    # inference parity: the README / test_from_mel.py usage is under torch.inference_mode()
+    with torch.no_grad():
+        yield
+
+
 def _model(name, spec, seed):
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator

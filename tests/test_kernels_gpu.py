@@ -83,7 +83,7 @@ def _gemm_case(L, M, N, K, bn, a_mn=0, b_mn=0, epi="plain", lda_pad=0, seed=0):
     torch.cuda.synchronize()
     got = Cd.cpu()
     assert torch.equal(got[:, N:], C0[:, N:]), "GEMM wrote outside its N columns"
-    tol = 3e-4 if epi in ("bias_prelu_round",) else 3e-6
+    tol = 3e-4 if epi in ("bias_prelu_round",) else 1e-5   # fp32 accumulation over K<=2304
     err = rel_rms(got[:, :N], exp)
     assert err < tol, (M, N, K, bn, a_mn, b_mn, epi, err)
 
