@@ -62,6 +62,7 @@ struct alignas(64) DevGroup {
   // MN-major operand descriptor geometry (bytes); defaults in gemm_tf32_group(), overridable
   // through F2G_MN_* environment variables for bring-up experiments.
   int mn_lbo, mn_sbo, mn_layout, mn_kstep;
+  int dbg;  // bring-up only: bit0 = skip MMA issue, bit1 = skip TMA loads, bit2 = skip epilogue stores
 };
 
 struct TileCoord {
@@ -84,7 +85,7 @@ F2G_DEVINL TileCoord decode_tile(const DevGroup& g, int tile) {
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
+gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict__ gmaps) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -140,20 +141,27 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
+          if (g.dbg & 2) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const CUtensorMap* ma = gmaps ? &gmaps->p[tc.prob].map_a : &pr.map_a;
+          const CUtensorMap* mb = gmaps ? &gmaps->p[tc.prob].map_b : &pr.map_b;
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j)
-              tma_load_2d(sa + j * 4096, &pr.map_a, &full_bar[stage], tc.m0 + 32 * j, kb * BK);
+              tma_load_2d(sa + j * 4096, ma, &full_bar[stage], tc.m0 + 32 * j, kb * BK);
           } else {
-            tma_load_2d(sa, &pr.map_a, &full_bar[stage], kb * BK, tc.m0);
+            tma_load_2d(sa, ma, &full_bar[stage], kb * BK, tc.m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d(sb + j * 4096, &pr.map_b, &full_bar[stage], n0 + 32 * j, kb * BK);
+              tma_load_2d(sb + j * 4096, mb, &full_bar[stage], n0 + 32 * j, kb * BK);
           } else {
-            tma_load_2d(sb, &pr.map_b, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(sb, mb, &full_bar[stage], kb * BK, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -166,6 +174,13 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
     // ------------------------------- MMA issuer ---------------------------------------
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+      const uint32_t a_addr0 = smem_u32(smem), b_addr0 = a_addr0 + A_TILE_BYTES;
+      const uint64_t adesc0 = A_MN ? make_smem_desc(a_addr0, g.mn_lbo, g.mn_sbo, g.mn_layout)
+                                   : make_smem_desc_sw128(a_addr0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr0, g.mn_lbo, g.mn_sbo, g.mn_layout)
+                                   : make_smem_desc_sw128(b_addr0, 16, 1024);
+      const int a_kstep = A_MN ? g.mn_kstep : 32, b_kstep = B_MN ? g.mn_kstep : 32;
+      const bool dbg_no_mma = (g.dbg & 1) != 0;
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -180,20 +195,17 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+          // Descriptors differ only in the 14-bit (address >> 4) field: add the stage / k-step
+          // byte offset (>> 4) to the stage-0 descriptor (no carry: smem addresses < 2^18).
+          // K-major (SWIZZLE_128B): the 4 k-steps live inside one 128B swizzle row -> +32 B.
+          // MN-major (SWIZZLE_128B_BASE32B): a k-step is 8 rows = two 4-row (512 B) swizzle
+          // atoms -> +1024 B; 32-wide MN blocks (one TMA box each) are 4096 B apart.
+          const uint32_t soff = (uint32_t)(stage * Cfg::STAGE_BYTES) >> 4;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major (SWIZZLE_128B): the 4 k-steps live inside one 128B swizzle row -> +32 B.
-            // MN-major (SWIZZLE_128B_BASE32B): a k-step is 8 rows = two 4-row (512 B) swizzle
-            // atoms -> +1024 B; 32-wide MN blocks (one TMA box each) are 4096 B apart.
-            const uint64_t adesc =
-                A_MN ? make_smem_desc(a_addr + k * g.mn_kstep, g.mn_lbo, g.mn_sbo, g.mn_layout)
-                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc =
-                B_MN ? make_smem_desc(b_addr + k * g.mn_kstep, g.mn_lbo, g.mn_sbo, g.mn_layout)
-                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t adesc = adesc0 + soff + (uint32_t)((k * a_kstep) >> 4);
+            const uint64_t bdesc = bdesc0 + soff + (uint32_t)((k * b_kstep) >> 4);
+            if (!dbg_no_mma) umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -208,6 +220,9 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------------
+    // TMEM lane = output row.  Each warp drains its 32 rows in 32-column chunks, transposes the
+    // chunk through a padded smem scratch so that lane == column (coalesced 128 B row segments,
+    // per-column parameters in registers), applies the fused epilogue and stores.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     float* scratch = scratch_all + (warp - 2) * (32 * 33);
     int ab = 0;
@@ -215,45 +230,86 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g) {
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
       const DevProblem& pr = g.p[tc.prob];
+      // hoist every epilogue parameter out of the constant bank once per tile
       const int n0 = tc.n0 * BN;
       const int row_base = tc.m0 + q * 32;
+      const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate;
+      const int rows = min(32, pr.M - row_base);
+      float* const cbase = pr.c;
+      const float* const bias_p = pr.bias;
+      const float* const slope_p = pr.slope;
+      const float* const res_p = pr.res;
+      const float* const rsc_p = pr.res_scale;
+      const float* const rowsc_p = pr.row_scale;
+      const float* const gate_p = pr.gate;
+      const int act = pr.act;
+      const bool do_round = pr.round_tf32 != 0, do_acc = pr.accumulate != 0;
+      const float alpha = pr.alpha, leaky = pr.leaky;
+      const bool skip = (g.dbg & 4) != 0;
+
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= pr.N) break;
+        if (n0 + c0 >= N || skip) break;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN + c0, v);
         tmem_ld_wait();
+        if (rows <= 0) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int col = n0 + c0 + lane;
-        const bool col_ok = col < pr.N;
-        const float bias = (pr.bias && col_ok) ? __ldg(pr.bias + col) : 0.f;
-        const float slope = (pr.slope && col_ok) ? __ldg(pr.slope + col) : pr.leaky;
-        const float rsc = (pr.res_scale && col_ok) ? __ldg(pr.res_scale + col) : 1.f;
-        const int rows = min(32, pr.M - row_base);
-#pragma unroll 4
-        for (int i = 0; i < rows; ++i) {
-          const int row = row_base + i;
-          float x = scratch[i * 33 + lane] * pr.alpha + bias;
-          if (pr.act == F2G_ACT_PRELU || pr.act == F2G_ACT_LEAKY) {
-            x = x > 0.f ? x : x * slope;
-          } else if (pr.act == F2G_ACT_SILU) {
-            x = x / (1.f + __expf(-x));
+        const bool col_ok = col < N;
+        const float bias = (bias_p && col_ok) ? __ldg(bias_p + col) : 0.f;
+        const float slope = (slope_p && col_ok) ? __ldg(slope_p + col) : leaky;
+        const float rsc = (rsc_p && col_ok) ? __ldg(rsc_p + col) : 1.f;
+#pragma unroll 1
+        for (int i0 = 0; i0 < rows; i0 += 8) {
+          float x[8];
+          bool ok[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            ok[u] = col_ok && (i0 + u < rows);
+            x[u] = fmaf(scratch[(i0 + u) * 33 + lane], alpha, bias);
           }
-          if (col_ok) {
-            if (pr.gate) {  // multiply by d(act)/dz evaluated at a saved pre-activation
-              const float z = __ldg(pr.gate + (size_t)row * pr.ld_gate + col);
-              x *= (z > 0.f ? 1.f : slope);
-            }
-            if (pr.res) x += rsc * __ldg(pr.res + (size_t)row * pr.ld_res + col);
-            if (pr.row_scale) x *= __ldg(pr.row_scale + row);
-            float* dst = pr.c + (size_t)row * pr.ldc + col;
-            if (pr.accumulate) x += *dst;
-            *dst = pr.round_tf32 ? tf32_rna(x) : x;
+          if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = x[u] > 0.f ? x[u] : x[u] * slope;
+          } else if (act == F2G_ACT_SILU) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = x[u] / (1.f + __expf(-x[u]));
           }
+          if (gate_p) {  // multiply by d(act)/dz evaluated at a saved pre-activation
+            float z[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              z[u] = ok[u] ? __ldg(gate_p + (size_t)(row_base + i0 + u) * ld_gate + col) : 1.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] *= (z[u] > 0.f ? 1.f : slope);
+          }
+          if (res_p) {
+            float r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              r[u] = ok[u] ? __ldg(res_p + (size_t)(row_base + i0 + u) * ld_res + col) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = fmaf(rsc, r[u], x[u]);
+          }
+          if (rowsc_p) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u < rows) x[u] *= __ldg(rowsc_p + row_base + i0 + u);
+          }
+          float* dst = cbase + (size_t)(row_base + i0) * ldc + col;
+          if (do_acc) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (ok[u]) x[u] += dst[(size_t)u * ldc];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (ok[u]) dst[(size_t)u * ldc] = do_round ? tf32_rna(x[u]) : x[u];
         }
         __syncwarp();
       }
@@ -302,9 +358,11 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+static int env_int(const char* name, int dflt);
 static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
                      uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
+  static const int l2promo = env_int("F2G_TMA_L2PROMO", (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   static const int mn_swz = env_int("F2G_MN_TMA_SWIZZLE", (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (!fn) return F2G_EDRIVER;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems % 4) != 0) {
@@ -319,7 +377,7 @@ static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? (CUtensorMapSwizzle)mn_swz : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  (CUtensorMapL2promotion)l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
               (unsigned long long)inner, (unsigned long long)outer,
@@ -344,7 +402,15 @@ static int launch(const DevGroup& g, int num_sms, cudaStream_t stream) {
     configured = true;
   }
   const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g);
+  const DevGroup* gmaps = nullptr;
+  static const int desc_global = env_int("F2G_DESC_GLOBAL", 0);
+  if (desc_global) {   // bring-up experiment: tensor maps fetched from global instead of param space
+    static DevGroup* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, sizeof(DevGroup));
+    cudaMemcpyAsync(dbuf, &g, sizeof(DevGroup), cudaMemcpyHostToDevice, stream);
+    gmaps = dbuf;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g, gmaps);
   return check_launch("gemm_tf32");
 }
 
@@ -399,6 +465,7 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   static const int mn_lbo = env_int("F2G_MN_LBO", 4096), mn_sbo = env_int("F2G_MN_SBO", 512),
                    mn_layout = env_int("F2G_MN_LAYOUT", 1), mn_kstep = env_int("F2G_MN_KSTEP", 1024);
   g.mn_lbo = mn_lbo; g.mn_sbo = mn_sbo; g.mn_layout = mn_layout; g.mn_kstep = mn_kstep;
+  g.dbg = env_int("F2G_GEMM_DBG", 0);
 
 #define F2G_DISPATCH(BN_)                                                        \
   if (bn == BN_) {                                                               \

@@ -21,6 +21,12 @@ from torch import Tensor
 from . import _lib as L
 
 
+import os
+
+BN_G1 = int(os.environ.get("F2G_BN1", "256"))   # N tile of pwconv1-like GEMMs (wide N)
+BN_G2 = int(os.environ.get("F2G_BN2", "128"))   # N tile of pwconv2-like GEMMs (N = channels)
+
+
 def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -116,18 +122,20 @@ class PackedGenerator:
         self.signature = _params_signature(m)
 
 
-def _g1(bw: _BlockW, a, h, M, bn=128):
+def _g1(bw: _BlockW, a, h, M, bn=None):
+    bn = bn or BN_G1
     b = bw.blk
     return L.gemm_desc(a.data_ptr(), bw.W1.data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C, bw.H,
                        bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
                        act=L.ACT_PRELU, round_tf32=1)
 
 
-def _g2(bw: _BlockW, h, x, M, bn=128):
+def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0):
+    bn = bn or BN_G2
     b = bw.blk
     return L.gemm_desc(h.data_ptr(), bw.W2.data_ptr(), x.data_ptr(), M, bw.C, bw.H, bw.H, bw.H, bw.C,
                        bn=bn, bias=b.pwconv2.bias.data_ptr(), res=x.data_ptr(), ld_res=bw.C,
-                       res_scale=b.residual_scale.scale.data_ptr())
+                       res_scale=b.residual_scale.scale.data_ptr(), round_tf32=round_out)
 
 
 class InferencePlan:
@@ -184,12 +192,13 @@ class InferencePlan:
                                   M, self.Cc, 3 * self.n_mels, pk.ld_mel, pk.ld_mel, self.Cc,
                                   bias=ce.in_proj.bias.data_ptr())])
         L.biasnorm(self.c0, M, self.Cc, self.Cc, ce.in_norm.bias, ce.in_norm.log_scale, self.c0, self.Cc)
-        for bw in pk.ce_blocks:
+        for li, bw in enumerate(pk.ce_blocks):
             b = bw.blk
+            last = li == len(pk.ce_blocks) - 1      # c0 is then only a GEMM operand: RN-round it
             L.block_pre(self.c0, B, Fm, bw.C, bw.C, bw.dwT, b.dwconv.bias, b.norm.bias,
                         b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C)
             L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M)])
-            L.gemm_group([_g2(bw, self.ce_h, self.c0, M)])
+            L.gemm_group([_g2(bw, self.ce_h, self.c0, M, round_out=int(last))])
         self.cond_paths()
 
     def cond_paths(self) -> None:
@@ -245,7 +254,8 @@ class InferencePlan:
                             b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm, bw.factor,
                             B * Fm, w.ts[:, i * bw.C:], ldc, w.a1, bw.C)
             L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
-            L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R) for bw, w in zip(pk.branches, self.br)])
+            L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1))
+                          for bw, w in zip(pk.branches, self.br)])
         L.gemm_group([L.gemm_desc(w.x.data_ptr(), bw.Wout.data_ptr(), w.pout.data_ptr(), w.R, bw.nin,
                                   bw.C, bw.C, bw.C, bw.ldp, bias=bw.dec.out_proj.bias.data_ptr(),
                                   row_scale=L.ptr(w.mask))

@@ -21,11 +21,11 @@ def _no_grad():
         yield
 
 
-def _model(name, spec, seed):
+def _model(name, spec, seed, style="ref_init"):
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator
     m = MelAudioGenerator(**get_generator_config(name))
-    sd = synth_state_dict(spec, seed)
+    sd = synth_state_dict(spec, seed, style=style)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.endswith("window") or k.endswith(".fb") for k in missing)
     return m.cuda().eval(), sd
@@ -90,3 +90,18 @@ def test_infer_bench_shape_vs_oracle_and_rng_semantics():
         m.estimators[0].decoder.out_proj.bias.add_(0.5)
     c = m.infer(mel.cuda(), n_timesteps=1, noise=nz)
     assert not torch.equal(b, c)
+
+
+def test_infer_harsh_weights_stress():
+    """Stress (not the parity gate): every matrix ~ N(0, 0.81/fan_in), i.e. strong branches and
+    little residual dilution, maximises accumulated TF32 operand rounding over the 17 serial
+    GEMMs.  Single-pass TF32 stays within 3e-3 here (1.1e-3 measured); the parity gate at 1e-3
+    above uses the reference's own initialisation scale."""
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    m, sd = _model(g["model_name"], g["sd_spec"], 4242, style="harsh")
+    mel, noise = g["mel"], g["noise"]
+    out = m.infer(mel.cuda(), n_timesteps=2, noise=noise.cuda())
+    ref = O.generator_infer(sd, O.generator_config(g["model_name"]), mel, noise, None, 2, False)
+    err = rel_rms(out.cpu(), ref)
+    print("harsh-weights rel-RMS:", err)
+    assert err < 3e-3
