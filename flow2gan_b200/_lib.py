@@ -39,6 +39,11 @@ class F2GGemm(C.Structure):
     ]
 
 
+class F2GLinear(C.Structure):
+    _fields_ = [("inp", _fp), ("W", _fp), ("bias", _fp), ("out", _fp),
+                ("K", _i), ("O", _i), ("ld_in", _i), ("ldw", _i), ("ld_out", _i)]
+
+
 _SIGS = {
     "f2g_abi_version": ([], _i),
     "f2g_last_error": ([], C.c_char_p),
@@ -52,7 +57,7 @@ _SIGS = {
     "f2g_biasnorm": ([_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp], _i),
     "f2g_block_pre": ([_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i,
                        _fp, _i, _fp, _fp, _fp], _i),
-    "f2g_linear_small": ([_fp, _i, _i, _i, _fp, _i, _fp, _i, _i, _fp, _i, _fp], _i),
+    "f2g_linear_small": ([C.POINTER(F2GLinear), _i, _i, _i, _fp], _i),
     "f2g_time_sinusoid": ([_fp, _i, _i, _fp, _f, _fp, _fp], _i),
     "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
     "f2g_im2col_cf": ([_fp, _i, _i, _i, _i, _fp, _i, _i, _fp], _i),
@@ -187,9 +192,18 @@ def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, c
                                ptr(inv_out), stream()))
 
 
+def linear_small_group(problems, B, act):
+    """problems: sequence of (inp, K, ld_in, W, ldw, bias, O, out, ld_out) tensors/ints."""
+    n = len(problems)
+    arr = (F2GLinear * n)()
+    for d, (inp, K, ld_in, W, ldw, bias, O, out, ld_out) in zip(arr, problems):
+        d.inp, d.W, d.bias, d.out = ptr(inp), ptr(W), ptr(bias), ptr(out)
+        d.K, d.O, d.ld_in, d.ldw, d.ld_out = K, O, ld_in, ldw, ld_out
+    _check(lib().f2g_linear_small(arr, n, B, act, stream()))
+
+
 def linear_small(inp, B, K, ld_in, W, ldw, bias, O, act, out, ld_out):
-    _check(lib().f2g_linear_small(ptr(inp), B, K, ld_in, ptr(W), ldw, ptr(bias), O, act, ptr(out),
-                                  ld_out, stream()))
+    linear_small_group([(inp, K, ld_in, W, ldw, bias, O, out, ld_out)], B, act)
 
 
 def time_sinusoid(t, B, dim, freqs, scale, out):

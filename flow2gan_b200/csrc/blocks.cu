@@ -121,33 +121,52 @@ __global__ void block_pre_kernel(const float* __restrict__ x, int B, int T, int 
   }
 }
 
-// out[b,o] = act(bias[o] + sum_k in[b,k] W[o,k]); one warp per output column o, 8 rows a pass.
-__global__ void linear_small_kernel(const float* __restrict__ in, int B, int K, int ld_in,
-                                    const float* __restrict__ W, int ldw,
-                                    const float* __restrict__ bias, int O, int act,
-                                    float* __restrict__ out, int ld_out) {
+// Batched small dense layers (up to 4 independent problems per launch, blockIdx.y = problem):
+// out[b,o] = act(bias[o] + sum_k in[b,k] W[o,k]).  One warp per output column o: the W row is
+// held in registers (float4 per lane per 128 columns), every batch row is then one float4 dot +
+// warp reduction, so the weight matrix is streamed exactly once.
+struct LinSmallArgs {
+  const float* in[4];
+  const float* W[4];
+  const float* bias[4];
+  float* out[4];
+  int K[4], O[4], ld_in[4], ldw[4], ld_out[4];
+  int n, B, act;
+};
+constexpr int LIN_MAX_K4 = 12;  // K <= 12 * 128 = 1536
+
+__global__ void linear_small_kernel(const LinSmallArgs a) {
+  const int p = blockIdx.y;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (o >= O) return;
-  const float* w = W + (size_t)o * ldw;
-  for (int b0 = 0; b0 < B; b0 += 8) {
-    float acc[8];
+  if (o >= a.O[p]) return;
+  const int K = a.K[p];
+  const int chunks = K >> 7;
+  const float* __restrict__ w = a.W[p] + (size_t)o * a.ldw[p];
+  const float* __restrict__ in = a.in[p];
+  const int ld_in = a.ld_in[p];
+  float4 wr[LIN_MAX_K4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(w + k);
+  for (int j = 0; j < LIN_MAX_K4; ++j)
+    if (j < chunks) wr[j] = __ldg(reinterpret_cast<const float4*>(w + j * 128 + lane * 4));
+  const float bias = a.bias[p] ? a.bias[p][o] : 0.f;
+  for (int b = 0; b < a.B; ++b) {
+    float acc = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (b0 + r < B) acc[r] = fmaf(in[(size_t)(b0 + r) * ld_in + k], wv, acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float s = warp_sum(acc[r]);
-      if (lane == 0 && b0 + r < B) {
-        float v = s + (bias ? bias[o] : 0.f);
-        if (act == F2G_ACT_SILU) v = v / (1.f + expf(-v));
-        out[(size_t)(b0 + r) * ld_out + o] = v;
+    for (int j = 0; j < LIN_MAX_K4; ++j) {
+      if (j < chunks) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(in + (size_t)b * ld_in + j * 128 + lane * 4));
+        acc = fmaf(x.x, wr[j].x, acc);
+        acc = fmaf(x.y, wr[j].y, acc);
+        acc = fmaf(x.z, wr[j].z, acc);
+        acc = fmaf(x.w, wr[j].w, acc);
       }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + bias;
+      if (a.act == F2G_ACT_SILU) v = v / (1.f + expf(-v));
+      a.out[p][(size_t)b * a.ld_out[p] + o] = v;
     }
   }
 }
@@ -240,12 +259,28 @@ extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, cons
   return check_launch("f2g_block_pre");
 }
 
-extern "C" int f2g_linear_small(const float* in, int B, int K, int ld_in, const float* W, int ldw,
-                                const float* bias, int O, int act, float* out, int ld_out,
-                                void* stream) {
-  const int wpb = 8;
-  linear_small_kernel<<<(O + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, B, K, ld_in, W, ldw, bias, O, act, out, ld_out);
+extern "C" int f2g_linear_small(const F2GLinear* probs, int n, int B, int act, void* stream) {
+  if (n < 1 || n > 4) {
+    set_error("f2g_linear_small: n=%d out of range (1..4)", n);
+    return F2G_EINVAL;
+  }
+  LinSmallArgs a;
+  a.n = n; a.B = B; a.act = act;
+  int max_o = 0;
+  for (int i = 0; i < n; ++i) {
+    const F2GLinear& p = probs[i];
+    if (p.K % 128 != 0 || p.K > LIN_MAX_K4 * 128 || p.ld_in % 4 != 0 || p.ldw % 4 != 0) {
+      set_error("f2g_linear_small: K=%d must be a multiple of 128 (<= %d), ld_in/ldw multiples of 4",
+                p.K, LIN_MAX_K4 * 128);
+      return F2G_EINVAL;
+    }
+    a.in[i] = p.in; a.W[i] = p.W; a.bias[i] = p.bias; a.out[i] = p.out;
+    a.K[i] = p.K; a.O[i] = p.O; a.ld_in[i] = p.ld_in; a.ldw[i] = p.ldw; a.ld_out[i] = p.ld_out;
+    if (p.O > max_o) max_o = p.O;
+  }
+  const int wpb = 4;
+  dim3 grid((max_o + wpb - 1) / wpb, n);
+  linear_small_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("f2g_linear_small");
 }
 

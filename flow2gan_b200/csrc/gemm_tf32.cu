@@ -34,7 +34,7 @@ struct TileCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = (SMEM_LIMIT - EPI_SCRATCH_BYTES - 2048) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -89,10 +89,14 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  float* scratch_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  // 128B-swizzled operand tiles need 1024 B alignment; keep every access in the shared state
+  // space (a uintptr_t round-up would turn them into generic LD/ST -- measured 10x slower).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t scratch_all = smem_u32(smem) + STAGES * Cfg::STAGE_BYTES;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("f2g gemm: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
 
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -224,7 +228,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
     // chunk through a padded smem scratch so that lane == column (coalesced 128 B row segments,
     // per-column parameters in registers), applies the fused epilogue and stores.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    float* scratch = scratch_all + (warp - 2) * (32 * 33);
+    const uint32_t scratch = scratch_all + (warp - 2) * (32 * 33 * 4);
     int ab = 0;
     uint32_t ab_phase = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -257,7 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
         tmem_ld_wait();
         if (rows <= 0) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) sts_f32(scratch + (lane * 33 + j) * 4, __uint_as_float(v[j]));
         __syncwarp();
         const int col = n0 + c0 + lane;
         const bool col_ok = col < N;
@@ -271,7 +275,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             ok[u] = col_ok && (i0 + u < rows);
-            x[u] = fmaf(scratch[(i0 + u) * 33 + lane], alpha, bias);
+            x[u] = fmaf(lds_f32(scratch + ((i0 + u) * 33 + lane) * 4), alpha, bias);
           }
           if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
 #pragma unroll

@@ -236,14 +236,16 @@ class InferencePlan:
         for bw, w in zip(pk.branches, self.br):
             L.biasnorm(w.x, w.R, bw.C, bw.C, bw.dec.in_norm.bias, bw.dec.in_norm.log_scale, w.x, bw.C)
         L.time_sinusoid(t_dev, B, self.te_dim, self.freqs, 1000.0, self.emb)
+        prob1, prob2, prob3 = [], [], []
         for bw, w in zip(pk.branches, self.br):
             tm = bw.dec.time_mlp
             H = tm[0].weight.shape[0]
-            L.linear_small(self.emb, B, bw.te, self.te_dim, tm[0].weight, bw.te, tm[0].bias, H,
-                           L.ACT_SILU, w.te1, H)
-            L.linear_small(w.te1, B, H, H, tm[2].weight, H, tm[2].bias, bw.te, L.ACT_NONE, w.te2, bw.te)
-            L.linear_small(w.te2, B, bw.te, bw.te, bw.Wte, bw.te, bw.bte, bw.nl * bw.C, L.ACT_NONE,
-                           w.ts, bw.nl * bw.C)
+            prob1.append((self.emb, bw.te, self.te_dim, tm[0].weight, bw.te, tm[0].bias, H, w.te1, H))
+            prob2.append((w.te1, H, H, tm[2].weight, H, tm[2].bias, bw.te, w.te2, bw.te))
+            prob3.append((w.te2, bw.te, bw.te, bw.Wte, bw.te, bw.bte, bw.nl * bw.C, w.ts, bw.nl * bw.C))
+        L.linear_small_group(prob1, B, L.ACT_SILU)
+        L.linear_small_group(prob2, B, L.ACT_NONE)
+        L.linear_small_group(prob3, B, L.ACT_NONE)
         nl = pk.branches[0].nl
         for i in range(nl):
             for bw, w in zip(pk.branches, self.br):

@@ -122,10 +122,17 @@ int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, const float* dw
                   int zero_row, const float* tscale, int ld_ts, float* out, int ld_out,
                   float* conv_out, float* inv_rms_out, void* stream);
 
-/* Small dense layer for (B <= 64)-row inputs, fp32 SIMT: out[b,o] = act(bias[o] + in[b,:].W[o,:])
- * (time_mlp / time_embed_proj, modules.py:569-573,451,485). */
-int f2g_linear_small(const float* in, int B, int K, int ld_in, const float* W, int ldw,
-                     const float* bias, int O, int act, float* out, int ld_out, void* stream);
+/* Small dense layers for few-row inputs, fp32 SIMT, up to 4 independent problems per launch:
+ * out[b,o] = act(bias[o] + in[b,:].W[o,:]), b < B (time_mlp / time_embed_proj of the three
+ * branches, modules.py:569-573,451,485).  K multiple of 128 and <= 1536. */
+typedef struct F2GLinear {
+  const float* in;
+  const float* W;
+  const float* bias;
+  float* out;
+  int K, O, ld_in, ldw, ld_out;
+} F2GLinear;
+int f2g_linear_small(const F2GLinear* problems, int n, int B, int act, void* stream);
 
 /* SinusoidalPosEmb (modules.py:223-232): emb[b] = [sin(scale t f_i) ; cos(scale t f_i)], f_i
  * from the caller's table freqs[dim/2] = exp(-i ln(10000)/(dim/2-1)). */
