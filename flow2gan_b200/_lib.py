@@ -44,6 +44,17 @@ class F2GLinear(C.Structure):
                 ("K", _i), ("O", _i), ("ld_in", _i), ("ldw", _i), ("ld_out", _i)]
 
 
+class F2GAdamTensor(C.Structure):
+    _fields_ = [("p", _fp), ("g", _fp), ("v", _fp), ("d", _fp), ("numel", _ll),
+                ("is_scalar", _i), ("reserved", _i)]
+
+
+class F2GAdamHyper(C.Structure):
+    _fields_ = [("lr", _f), ("scalar_lr_scale", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
+                ("param_min_rms", _f), ("param_max_rms", _f), ("scalar_max", _f),
+                ("size_update_period", _i), ("clipping_update_period", _i), ("use_clipping", _i)]
+
+
 _SIGS = {
     "f2g_abi_version": ([], _i),
     "f2g_last_error": ([], C.c_char_p),
@@ -62,6 +73,7 @@ _SIGS = {
     "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
     "f2g_im2col_cf": ([_fp, _i, _i, _i, _i, _fp, _i, _i, _fp], _i),
     "f2g_frame_mask": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -220,3 +232,9 @@ def im2col_cf(x, B, Cc, T, ktaps, out, ld, round_tf32):
 
 def frame_mask(lens, B, frames, hop, out):
     _check(lib().f2g_frame_mask(ptr(lens), B, frames, hop, ptr(out), stream()))
+
+
+def scaled_adam_step(tab, n_tensors, chunks, n_chunks, acc, tstate, gstate, norms, step, phase, hyper):
+    _check(lib().f2g_scaled_adam_step(tab.data_ptr(), n_tensors, chunks.data_ptr(), n_chunks, ptr(acc),
+                                      ptr(tstate), ptr(gstate), ptr(norms), step, phase,
+                                      C.byref(hyper), stream()))

@@ -152,6 +152,35 @@ int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, float* out, in
 /* frame mask from lengths: m[b*frames+f] = f < 1 + lens[b]/hop (modules.py:79-82,706-707). */
 int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-tensor ScaledAdam step (flow2gan/optim.py:125-255,451-619) for ONE param group.
+ * tab (device): one record per parameter tensor; chunks (device): int2 {tensor, chunk} covering
+ * every tensor in 4096-element pieces; acc: 3 floats per tensor (scratch); tensor_state: 8
+ * floats per tensor {param_rms, scale_exp_avg_sq, scale_grads[4], scale_step, -}; group_state:
+ * {grad_norm (out), clip (out), model_norm_threshold (in, < 0 = unset)}; model_norms: ring of
+ * clipping_update_period floats.  phase 0 = reductions + norm, phase 1 = clip + update; the
+ * host refreshes the threshold between the phases on the (rare) steps the reference does.
+ * ------------------------------------------------------------------------------------- */
+typedef struct F2GAdamTensor {
+  float* p;
+  const float* g; /* NULL = no gradient this step (treated as zeros, optim.py:107-109) */
+  float* v;       /* exp_avg_sq */
+  float* d;       /* delta (momentum) */
+  long long numel;
+  int is_scalar;  /* numel == 1: no rms scaling, lr * scalar_lr_scale, clamp to +-scalar_max */
+  int reserved;
+} F2GAdamTensor;
+
+typedef struct F2GAdamHyper {
+  float lr, scalar_lr_scale, beta1, beta2, eps, param_min_rms, param_max_rms, scalar_max;
+  int size_update_period, clipping_update_period, use_clipping;
+} F2GAdamHyper;
+
+int f2g_scaled_adam_step(const F2GAdamTensor* tab_dev, int n_tensors, const int* chunks_dev,
+                         int n_chunks, float* acc_dev, float* tensor_state_dev,
+                         float* group_state_dev, float* model_norms_dev, int step, int phase,
+                         const F2GAdamHyper* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
