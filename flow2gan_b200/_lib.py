@@ -35,13 +35,22 @@ class F2GGemm(C.Structure):
         ("row_scale", _fp), ("gate", _fp),
         ("ld_res", _i), ("ld_gate", _i),
         ("act", _i), ("leaky", _f), ("alpha", _f),
-        ("round_tf32", _i), ("accumulate", _i),
+        ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i),
     ]
 
 
 class F2GLinear(C.Structure):
     _fields_ = [("inp", _fp), ("W", _fp), ("bias", _fp), ("out", _fp),
                 ("K", _i), ("O", _i), ("ld_in", _i), ("ldw", _i), ("ld_out", _i)]
+
+
+class F2GBlockBwdC(C.Structure):
+    _fields_ = [("dy", _fp), ("x", _fp), ("ld_x", _i), ("row_mask", _fp), ("y", _fp),
+                ("coef", _fp), ("gs", _fp), ("bn_bias", _fp), ("da1", _fp), ("ld_da", _i),
+                ("inv", _fp), ("cond", _fp), ("ld_cond", _i), ("cond_T", _i), ("factor", _i),
+                ("zero_row", _i), ("dxo", _fp), ("ld_dxo", _i),
+                ("g_dww", _fp), ("g_dwb", _fp), ("g_beta", _fp), ("g_ls", _fp), ("g_ts", _fp),
+                ("ld_gts", _i), ("g_rs", _fp), ("g_b2", _fp), ("B", _i), ("T", _i), ("C", _i)]
 
 
 class F2GAdamTensor(C.Structure):
@@ -65,7 +74,7 @@ _SIGS = {
     "f2g_irfft_frames": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_ola_combine": ([C.POINTER(_fp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _fp, _fp,
                          _fp, _i, _i, _i, _f, _f, _i, _fp], _i),
-    "f2g_biasnorm": ([_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp], _i),
+    "f2g_biasnorm": ([_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp], _i),
     "f2g_block_pre": ([_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i,
                        _fp, _i, _fp, _fp, _fp], _i),
     "f2g_linear_small": ([C.POINTER(F2GLinear), _i, _i, _i, _fp], _i),
@@ -73,6 +82,17 @@ _SIGS = {
     "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
     "f2g_im2col_cf": ([_fp, _i, _i, _i, _i, _fp, _i, _i, _fp], _i),
     "f2g_frame_mask": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_block_bwd_a": ([_fp, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp], _i),
+    "f2g_block_bwd_c": ([C.POINTER(F2GBlockBwdC), _fp], _i),
+    "f2g_block_bwd_b": ([_fp, _fp, _fp, _fp, _i, _fp, _i, _i, _i, _fp, _i, _fp], _i),
+    "f2g_act_bwd": ([_fp, _i, _fp, _i, _fp, _f, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp], _i),
+    "f2g_cond_reduce": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
+    "f2g_istft_bwd_prep": ([_fp, _i, _i, _i, _i, _i, _f, _fp, _fp], _i),
+    "f2g_istft_bwd_spec": ([_fp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp], _i),
+    "f2g_stft_bwd_frames": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_stft_bwd_fold": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
+    "f2g_spec_loss_bwd": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _f, _fp, _i, _fp, _fp], _i),
+    "f2g_colsum": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
 }
 
@@ -141,7 +161,8 @@ def stream() -> int:
 # ---------------------------------------------------------------------------------------
 def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
-              act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0) -> F2GGemm:
+              act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
+              ld_pre=0) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -152,6 +173,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.ld_res, d.ld_gate = ld_res, ld_gate
     d.act, d.leaky, d.alpha = act, leaky, alpha
     d.round_tf32, d.accumulate = round_tf32, accumulate
+    d.c_pre, d.ld_pre = c_pre, ld_pre
     return d
 
 
@@ -192,8 +214,9 @@ def ola_combine(frames, n_ffts, hops, n_frames, weight, x, out, B, T, euler, t, 
                                  int(euler), float(t), float(dt), int(clamp), stream()))
 
 
-def biasnorm(x, rows, Cc, ld, bias, log_scale, y, ld_y):
-    _check(lib().f2g_biasnorm(ptr(x), rows, Cc, ld, ptr(bias), ptr(log_scale), ptr(y), ld_y, stream()))
+def biasnorm(x, rows, Cc, ld, bias, log_scale, y, ld_y, inv_out=None):
+    _check(lib().f2g_biasnorm(ptr(x), rows, Cc, ld, ptr(bias), ptr(log_scale), ptr(y), ld_y,
+                              ptr(inv_out), stream()))
 
 
 def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
@@ -238,3 +261,57 @@ def scaled_adam_step(tab, n_tensors, chunks, n_chunks, acc, tstate, gstate, norm
     _check(lib().f2g_scaled_adam_step(tab.data_ptr(), n_tensors, chunks.data_ptr(), n_chunks, ptr(acc),
                                       ptr(tstate), ptr(gstate), ptr(norms), step, phase,
                                       C.byref(hyper), stream()))
+
+
+def block_bwd_a(da1, ld_da, y, inv, bn_bias, log_scale, tscale, ld_ts, B, T, Cc, dy, du, coef, gs):
+    _check(lib().f2g_block_bwd_a(ptr(da1), ld_da, ptr(y), ptr(inv), ptr(bn_bias), ptr(log_scale),
+                                 ptr(tscale), ld_ts, B, T, Cc, ptr(dy), ptr(du), ptr(coef), ptr(gs),
+                                 stream()))
+
+
+def block_bwd_c(**kw):
+    a = F2GBlockBwdC()
+    for k, v in kw.items():
+        setattr(a, k, ptr(v) if isinstance(v, torch.Tensor) else v)
+    _check(lib().f2g_block_bwd_c(C.byref(a), stream()))
+
+
+def block_bwd_b(dy, dw_wT, row_mask, dxo, ld_dxo, rs, B, T, Cc, dx, ld_dx):
+    _check(lib().f2g_block_bwd_b(ptr(dy), ptr(dw_wT), ptr(row_mask), ptr(dxo), ld_dxo, ptr(rs), B, T, Cc,
+                                 ptr(dx), ld_dx, stream()))
+
+
+def act_bwd(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, dz, ld_dz, g_bias, g_slope, round_tf32=0):
+    _check(lib().f2g_act_bwd(ptr(dh), ld_dh, ptr(z), ld_z, ptr(slope), float(leaky), act, rows, cols,
+                             ptr(dz), ld_dz, ptr(g_bias), ptr(g_slope), round_tf32, stream()))
+
+
+def cond_reduce(du, B, T, Cc, cond_T, factor, zero_row, out, ld_out):
+    _check(lib().f2g_cond_reduce(ptr(du), B, T, Cc, cond_T, factor, zero_row, ptr(out), ld_out, stream()))
+
+
+def istft_bwd_prep(g, B, T, n_fft, hop, frames, scale, gs):
+    _check(lib().f2g_istft_bwd_prep(ptr(g), B, T, n_fft, hop, frames, float(scale), ptr(gs), stream()))
+
+
+def istft_bwd_spec(gs, B, Lp, n_fft, hop, row_mask, dpacked, ld, round_tf32=0):
+    _check(lib().f2g_istft_bwd_spec(ptr(gs), B, Lp, n_fft, hop, ptr(row_mask), ptr(dpacked), ld,
+                                    round_tf32, stream()))
+
+
+def stft_bwd_frames(dpacked, rows, ld, n_fft, frames_out):
+    _check(lib().f2g_stft_bwd_frames(ptr(dpacked), rows, ld, n_fft, ptr(frames_out), stream()))
+
+
+def stft_bwd_fold(frames_grad, B, T, n_fft, hop, frames, dx, accumulate):
+    _check(lib().f2g_stft_bwd_fold(ptr(frames_grad), B, T, n_fft, hop, frames, ptr(dx), int(accumulate),
+                                   stream()))
+
+
+def spec_loss_bwd(audio, B, T, ld_audio, n_fft, hop, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out):
+    _check(lib().f2g_spec_loss_bwd(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(fb), n_filt,
+                                   float(log_clip), ptr(dF), ld_dF, ptr(frames_out), stream()))
+
+
+def colsum(x, ld, rows, cols, out):
+    _check(lib().f2g_colsum(ptr(x), ld, rows, cols, ptr(out), stream()))

@@ -17,7 +17,7 @@ F2G_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, int ld,
                                 const float* __restrict__ bias,
                                 const float* __restrict__ log_scale, float* __restrict__ y,
-                                int ld_y) {
+                                int ld_y, float* __restrict__ inv_out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -36,6 +36,7 @@ __global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, in
   }
   ssq = warp_sum(ssq);
   const float scale = (1.0f / sqrtf(ssq / (float)C)) * expf(*log_scale);
+  if (inv_out && lane == 0) inv_out[row] = scale;
 #pragma unroll
   for (int j = 0; j < MAX_CHUNKS; ++j) {
     if (j < chunks) {
@@ -236,11 +237,11 @@ static int check_channels(const char* who, int C, int ld) {
 }
 
 extern "C" int f2g_biasnorm(const float* x, int rows, int C, int ld, const float* bias,
-                            const float* log_scale, float* y, int ld_y, void* stream) {
+                            const float* log_scale, float* y, int ld_y, float* inv_out, void* stream) {
   if (int rc = check_channels("f2g_biasnorm", C, ld | ld_y)) return rc;
   const int wpb = 4;
   biasnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, C, ld, bias, log_scale, y, ld_y);
+      x, rows, C, ld, bias, log_scale, y, ld_y, inv_out);
   return check_launch("f2g_biasnorm");
 }
 

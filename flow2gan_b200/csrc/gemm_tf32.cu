@@ -42,13 +42,14 @@ struct alignas(64) DevProblem {
   CUtensorMap map_a;
   CUtensorMap map_b;
   float* c;
+  float* c_pre;
   const float* bias;
   const float* slope;
   const float* res;
   const float* res_scale;
   const float* row_scale;
   const float* gate;
-  int ldc, ld_res, ld_gate;
+  int ldc, ld_res, ld_gate, ld_pre;
   int M, N, K;
   int m_tiles, n_tiles, tile_begin;
   int act, round_tf32, accumulate;
@@ -240,6 +241,8 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate;
       const int rows = min(32, pr.M - row_base);
       float* const cbase = pr.c;
+      float* const pre_p = pr.c_pre;
+      const int ld_pre = pr.ld_pre;
       const float* const bias_p = pr.bias;
       const float* const slope_p = pr.slope;
       const float* const res_p = pr.res;
@@ -276,6 +279,11 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           for (int u = 0; u < 8; ++u) {
             ok[u] = col_ok && (i0 + u < rows);
             x[u] = fmaf(lds_f32(scratch + ((i0 + u) * 33 + lane) * 4), alpha, bias);
+          }
+          if (pre_p) {   // keep the pre-activation for the backward pass
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (ok[u]) pre_p[(size_t)(row_base + i0 + u) * ld_pre + col] = x[u];
           }
           if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
 #pragma unroll
@@ -452,7 +460,7 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     rc = b_mn ? encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
               : encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn, false);
     if (rc) return rc;
-    p.c = d.c; p.ldc = d.ldc;
+    p.c = d.c; p.ldc = d.ldc; p.c_pre = d.c_pre; p.ld_pre = d.ld_pre;
     p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
     p.row_scale = d.row_scale; p.gate = d.gate;
     p.ld_res = d.ld_res; p.ld_gate = d.ld_gate;

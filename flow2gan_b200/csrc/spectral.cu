@@ -55,7 +55,8 @@ F2G_DEVINL float hann_from_tw(const float2* tw, int i, int n) {
 __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
                             int hop, int frames, int mode, const float* __restrict__ pre,
                             const float* __restrict__ fb, int n_filt, float log_clip,
-                            float* __restrict__ out, int ld_out, int round_tf32) {
+                            float* __restrict__ out, int ld_out, int round_tf32, int center,
+                            int adjoint_scale, const float* __restrict__ row_mask) {
   extern __shared__ float2 sm[];
   float2* a = sm;
   float2* b = sm + n;
@@ -76,7 +77,7 @@ __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio
     mul = pre[2 * bi + 1];
   }
   const float* x = audio + (size_t)bi * ld_audio;
-  const int start = f * hop - (n >> 1);
+  const int start = center ? f * hop - (n >> 1) : f * hop;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int p = start + i;
     if (p < 0) p = -p;
@@ -89,8 +90,16 @@ __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio
 
   float* o = out + (size_t)row * ld_out;
   if (mode == F2G_SPEC_PACKED) {
+    const float rm = row_mask ? row_mask[row] : 1.f;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-      const float2 v = X[k];
+      float2 v = X[k];
+      if (adjoint_scale) {   // adjoint of the C2R transform: c_k / n, Im(DC) = Im(Nyquist) = 0
+        const bool edge = (k == 0) || (k == (n >> 1));
+        const float c = (edge ? 1.f : 2.f) / (float)n;
+        v.x *= c;
+        v.y = edge ? 0.f : v.y * c;
+      }
+      v.x *= rm; v.y *= rm;
       o[k] = round_tf32 ? tf32_rna(v.x) : v.x;
       o[nb + k] = round_tf32 ? tf32_rna(v.y) : v.y;
     }
@@ -187,6 +196,91 @@ __global__ void ola_combine_kernel(OlaArgs a, const float* __restrict__ weight,
   out[(size_t)bi * T + s] = r;
 }
 
+// STFT adjoint, per frame: fr[i] = w[i] * Re( sum_{k<=n/2} (dRe_k + i dIm_k) e^{+2 pi i k i / n} )
+__global__ void stft_bwd_frames_kernel(const float* __restrict__ dpacked, int ld, int n, int logn,
+                                       float* __restrict__ frames_out) {
+  extern __shared__ float2 sm[];
+  float2* a = sm;
+  float2* b = sm + n;
+  float2* tw = sm + 2 * n;
+  const int row = blockIdx.x;
+  const int nb = (n >> 1) + 1;
+  const float* p = dpacked + (size_t)row * ld;
+  fill_twiddles(tw, n);
+  for (int k = threadIdx.x; k < n; k += blockDim.x)
+    a[k] = k < nb ? make_float2(p[k], p[nb + k]) : make_float2(0.f, 0.f);
+  __syncthreads();
+  const float2* y = block_fft<true>(a, b, tw, n, logn);
+  float* o = frames_out + (size_t)row * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = y[i].x * hann_from_tw(tw, i, n);
+}
+
+// Fused backward of a filterbank spectrogram loss term (MelSpectrogram / LinearFilterSpectrogram
+// + optional safe_log): recompute the frame spectrum, push dF (grad w.r.t. the [log-]filterbank
+// output) through log -> fb -> |.| or |.|^2 -> rFFT -> window, emit windowed frame gradients.
+__global__ void spec_loss_bwd_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
+                                     int hop, int frames, int mode, const float* __restrict__ fb,
+                                     int n_filt, float log_clip, const float* __restrict__ dF, int ld_dF,
+                                     float* __restrict__ frames_out) {
+  extern __shared__ float2 sm[];
+  float2* a = sm;
+  float2* b = sm + n;
+  float2* tw = sm + 2 * n;
+  float* spec = reinterpret_cast<float*>(sm + 2 * n + (n >> 1));   // nb
+  float* dfilt = spec + (n >> 1) + 1;                              // n_filt
+  const int row = blockIdx.x;
+  const int bi = row / frames, f = row - bi * frames;
+  const int nb = (n >> 1) + 1;
+  fill_twiddles(tw, n);
+  __syncthreads();
+  const float* x = audio + (size_t)bi * ld_audio;
+  const int start = f * hop - (n >> 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int p = start + i;
+    if (p < 0) p = -p;
+    if (p >= T) p = 2 * (T - 1) - p;
+    a[i] = make_float2(x[p] * hann_from_tw(tw, i, n), 0.f);
+  }
+  __syncthreads();
+  float2* X = block_fft<false>(a, b, tw, n, logn);
+  float2* other = (X == a) ? b : a;
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    const float2 v = X[k];
+    const float p2 = v.x * v.x + v.y * v.y;
+    spec[k] = mode == F2G_SPEC_POWER ? p2 : sqrtf(p2);
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_filt; m += blockDim.x) {
+    float g = dF[(size_t)row * ld_dF + m];
+    if (log_clip > 0.f) {
+      float acc = 0.f;
+      for (int k = 0; k < nb; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
+      g = acc > log_clip ? g / acc : 0.f;
+    }
+    dfilt[m] = g;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    float2 o = make_float2(0.f, 0.f);
+    if (k < nb) {
+      float ds = 0.f;
+      for (int m = 0; m < n_filt; ++m) ds = fmaf(__ldg(fb + (size_t)k * n_filt + m), dfilt[m], ds);
+      const float2 v = X[k];
+      if (mode == F2G_SPEC_POWER) {
+        o = make_float2(2.f * v.x * ds, 2.f * v.y * ds);
+      } else {
+        const float mag = spec[k];
+        if (mag > 0.f) o = make_float2(v.x / mag * ds, v.y / mag * ds);
+      }
+    }
+    other[k] = o;
+  }
+  __syncthreads();
+  const float2* y = block_fft<true>(other, X, tw, n, logn);
+  float* o = frames_out + (size_t)row * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = y[i].x * hann_from_tw(tw, i, n);
+}
+
 __global__ void dc_peak_kernel(const float* __restrict__ audio, int T, int ld, float* __restrict__ pre) {
   __shared__ float red[32];
   __shared__ float bc;
@@ -229,29 +323,80 @@ static int ilog2_exact(int n) {
 
 using namespace f2g;
 
-extern "C" int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
-                        const float* pre, const float* fb, int n_filt, float log_clip, float* out,
-                        int ld_out, int round_tf32, void* stream) {
+static int stft_launch(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
+                       const float* pre, const float* fb, int n_filt, float log_clip, float* out,
+                       int ld_out, int round_tf32, int center, int adjoint_scale, const float* row_mask,
+                       void* stream) {
   const int logn = ilog2_exact(n_fft);
   if (logn < 5 || n_fft > 2048) {
     set_error("f2g_stft: n_fft=%d must be a power of two in [32, 2048]", n_fft);
     return F2G_EINVAL;
   }
-  if (n_fft / 2 >= T) {
-    set_error("f2g_stft: reflect padding needs n_fft/2 (%d) < T (%d)", n_fft / 2, T);
+  if (center ? (n_fft / 2 >= T) : (n_fft > T)) {
+    set_error("f2g_stft: signal too short (n_fft=%d, T=%d, center=%d)", n_fft, T, center);
     return F2G_EINVAL;
   }
   if (mode != F2G_SPEC_PACKED && mode != F2G_SPEC_MAG && mode != F2G_SPEC_POWER) {
     set_error("f2g_stft: bad mode %d", mode);
     return F2G_EINVAL;
   }
-  const int frames = 1 + T / hop;
+  const int frames = center ? 1 + T / hop : 1 + (T - n_fft) / hop;
   const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2) + (n_fft / 2 + 1) * sizeof(float);
   stft_kernel<<<B * frames, threads, smem, static_cast<cudaStream_t>(stream)>>>(
       audio, T, ld_audio, n_fft, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out,
-      round_tf32);
+      round_tf32, center, adjoint_scale, row_mask);
   return check_launch("f2g_stft");
+}
+
+extern "C" int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
+                        const float* pre, const float* fb, int n_filt, float log_clip, float* out,
+                        int ld_out, int round_tf32, void* stream) {
+  return stft_launch(audio, B, T, ld_audio, n_fft, hop, mode, pre, fb, n_filt, log_clip, out, ld_out,
+                     round_tf32, 1, 0, nullptr, stream);
+}
+
+extern "C" int f2g_istft_bwd_spec(const float* gs, int B, int Lp, int n_fft, int hop,
+                                  const float* row_mask, float* dpacked, int ld, int round_tf32,
+                                  void* stream) {
+  return stft_launch(gs, B, Lp, Lp, n_fft, hop, F2G_SPEC_PACKED, nullptr, nullptr, 0, 0.f, dpacked, ld,
+                     round_tf32, 0, 1, row_mask, stream);
+}
+
+extern "C" int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n_fft, float* frames_out,
+                                   void* stream) {
+  const int logn = ilog2_exact(n_fft);
+  if (logn < 5 || n_fft > 2048) {
+    set_error("f2g_stft_bwd_frames: n_fft=%d must be a power of two in [32, 2048]", n_fft);
+    return F2G_EINVAL;
+  }
+  const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
+  const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2);
+  stft_bwd_frames_kernel<<<rows, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      dpacked, ld, n_fft, logn, frames_out);
+  return check_launch("f2g_stft_bwd_frames");
+}
+
+extern "C" int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft, int hop,
+                                 int mode, const float* fb, int n_filt, float log_clip, const float* dF,
+                                 int ld_dF, float* frames_out, void* stream) {
+  const int logn = ilog2_exact(n_fft);
+  if (logn < 5 || n_fft > 2048 || n_fft / 2 >= T || !fb) {
+    set_error("f2g_spec_loss_bwd: bad arguments (n_fft=%d, T=%d)", n_fft, T);
+    return F2G_EINVAL;
+  }
+  const int frames = 1 + T / hop;
+  const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
+  const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2) +
+                      (size_t)(n_fft / 2 + 1 + n_filt) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(spec_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  spec_loss_bwd_kernel<<<B * frames, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      audio, T, ld_audio, n_fft, logn, hop, frames, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out);
+  return check_launch("f2g_spec_loss_bwd");
 }
 
 extern "C" int f2g_dc_peak(const float* audio, int B, int T, int ld_audio, float* pre, void* stream) {

@@ -1,0 +1,413 @@
+// Backward-pass SIMT kernels of the generator path (channel-last rows): ConvNeXt block prologue
+// adjoints, PReLU/SiLU adjoints with fused parameter-gradient column reductions, column sums
+// (bias grads), conditioning scatter, iSTFT / STFT adjoints.  The contractions (dgrad / wgrad)
+// run on the tcgen05 GEMM (gemm_tf32.cu) with MN-major operands.
+// Reference forward definitions: flow2gan/models/modules.py:286-339 (BiasNormFunction),
+// :456-495 (ConvNeXtBlock.forward), :668-680 (upsample_cond), :69-116 (STFT/ISTFT).
+#include "common.cuh"
+#include "../../include/flow2gan_b200.h"
+
+namespace f2g {
+
+constexpr int MAXC4 = 8;
+F2G_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+F2G_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------
+// Block prologue backward, stage A (one warp per token):
+//   forward: u = y*inv + cond ; a1 = u * (1 + ts)      (y = dwconv output, inv = rsqrt(mean((y-beta)^2)) e^ls)
+//   in : da1 ; out: du = da1*(1+ts) (optional), dy = inv*du - coef*(y-beta), coef = G*inv/(C*m),
+//        G = sum_c du*y, m = e^(2 ls)/inv^2 ; per row: coef[r], gs[r] = G*inv (d log_scale terms)
+// ---------------------------------------------------------------------------------------
+__global__ void block_bwd_a_kernel(const float* __restrict__ da1, int ld_da, const float* __restrict__ y,
+                                   const float* __restrict__ inv, const float* __restrict__ bn_bias,
+                                   const float* __restrict__ log_scale, const float* __restrict__ tscale,
+                                   int ld_ts, int B, int T, int C, float* __restrict__ dy,
+                                   float* __restrict__ du, float* __restrict__ coef_out,
+                                   float* __restrict__ gs_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const int bi = row / T;
+  const int chunks = C >> 7;
+  const float s = inv[row];
+  float4 g[MAXC4], yv[MAXC4];
+  float G = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXC4; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      float4 d = ld4(da1 + (size_t)row * ld_da + c);
+      if (tscale) {
+        const float4 t = ld4(tscale + (size_t)bi * ld_ts + c);
+        d.x *= 1.f + t.x; d.y *= 1.f + t.y; d.z *= 1.f + t.z; d.w *= 1.f + t.w;
+      }
+      g[j] = d;
+      yv[j] = ld4(y + (size_t)row * C + c);
+      G += d.x * yv[j].x + d.y * yv[j].y + d.z * yv[j].z + d.w * yv[j].w;
+      if (du) st4(du + (size_t)row * C + c, d);
+    }
+  }
+  G = warp_sum(G);
+  const float e2 = expf(2.f * (*log_scale));
+  const float m = e2 / (s * s);
+  const float coef = G * s / ((float)C * m);
+  if (lane == 0) {
+    coef_out[row] = coef;
+    gs_out[row] = G * s;
+  }
+#pragma unroll
+  for (int j = 0; j < MAXC4; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      const float4 b = ld4(bn_bias + c);
+      float4 o;
+      o.x = s * g[j].x - coef * (yv[j].x - b.x);
+      o.y = s * g[j].y - coef * (yv[j].y - b.y);
+      o.z = s * g[j].z - coef * (yv[j].z - b.z);
+      o.w = s * g[j].w - coef * (yv[j].w - b.w);
+      st4(dy + (size_t)row * C + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage C: all per-channel parameter-gradient reductions of one block, thread = channel,
+// CTA = (128-channel slab) x (chunk of rows inside ONE batch element):
+//   d dw_w[k][c] += sum_t dy[t,c] * xm[t+k-3,c] ; d dw_b[c] += sum dy ; d beta[c] += sum coef*(y-beta)
+//   d ts[b,c] += sum_t da1 * (y*inv + cond) ; d rs[c] += sum dxo * x ; d b2[c] += sum dxo
+//   d log_scale += sum gs            (dxo = gradient w.r.t. the block output)
+// Any pointer may be NULL to skip its term.
+// ---------------------------------------------------------------------------------------
+struct BlockBwdC {
+  const float* dy; const float* x; int ld_x; const float* row_mask; const float* y;
+  const float* coef; const float* gs; const float* bn_bias; const float* da1; int ld_da;
+  const float* inv; const float* cond; int ld_cond; int cond_T; int factor; int zero_row;
+  const float* dxo; int ld_dxo;
+  float* g_dww; float* g_dwb; float* g_beta; float* g_ls; float* g_ts; int ld_gts; float* g_rs; float* g_b2;
+  int B, T, C, rows_per_cta;
+};
+
+__global__ void block_bwd_c_kernel(const BlockBwdC a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;     // channel
+  const int bi = blockIdx.z;
+  const int t0 = blockIdx.y * a.rows_per_cta;
+  const int t1 = min(t0 + a.rows_per_cta, a.T);
+  if (c >= a.C) return;
+  const size_t rb = (size_t)bi * a.T;
+  float w7[7] = {0, 0, 0, 0, 0, 0, 0};
+  float s_dy = 0.f, s_beta = 0.f, s_ts = 0.f, s_rs = 0.f, s_b2 = 0.f, s_ls = 0.f;
+  const float beta = a.bn_bias ? a.bn_bias[c] : 0.f;
+  // sliding window of masked inputs x[t-3 .. t+3]
+  float win[7];
+  if (a.g_dww) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t0 + k - 3;
+      float v = 0.f;
+      if (tt >= 0 && tt < a.T) {
+        v = a.x[(rb + tt) * a.ld_x + c];
+        if (a.row_mask) v *= a.row_mask[rb + tt];
+      }
+      win[k] = v;
+    }
+  }
+  for (int t = t0; t < t1; ++t) {
+    const size_t r = rb + t;
+    const float dyv = a.dy ? a.dy[r * a.C + c] : 0.f;
+    if (a.g_dww) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w7[k] = fmaf(dyv, win[k], w7[k]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+      const int tn = t + 4;
+      float v = 0.f;
+      if (tn < a.T) {
+        v = a.x[(rb + tn) * a.ld_x + c];
+        if (a.row_mask) v *= a.row_mask[rb + tn];
+      }
+      win[6] = v;
+    }
+    s_dy += dyv;
+    float yv = 0.f;
+    if (a.y) yv = a.y[r * a.C + c];
+    if (a.g_beta) s_beta = fmaf(a.coef[r], yv - beta, s_beta);
+    if (a.g_ts) {
+      float u = yv * a.inv[r];
+      if (a.cond) {
+        const int crow = t < a.cond_T * a.factor ? bi * a.cond_T + t / a.factor : a.zero_row;
+        u += a.cond[(size_t)crow * a.ld_cond + c];
+      }
+      s_ts = fmaf(a.da1[r * a.ld_da + c], u, s_ts);
+    }
+    if (a.g_rs || a.g_b2) {
+      const float d = a.dxo[r * a.ld_dxo + c];
+      s_b2 += d;
+      if (a.g_rs) s_rs = fmaf(d, a.x[r * a.ld_x + c], s_rs);
+    }
+    if (a.g_ls && c == 0) s_ls += a.gs[r];
+  }
+  if (a.g_dww) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) atomicAdd(a.g_dww + (size_t)k * a.C + c, w7[k]);
+  }
+  if (a.g_dwb) atomicAdd(a.g_dwb + c, s_dy);
+  if (a.g_beta) atomicAdd(a.g_beta + c, s_beta);
+  if (a.g_ts) atomicAdd(a.g_ts + (size_t)bi * a.ld_gts + c, s_ts);
+  if (a.g_rs) atomicAdd(a.g_rs + c, s_rs);
+  if (a.g_b2) atomicAdd(a.g_b2 + c, s_b2);
+  if (a.g_ls && c == 0) atomicAdd(a.g_ls, s_ls);
+}
+
+// Stage B (one warp per token): dx[t,c] = mask[t] * sum_k w[c,k] dy[t-k+3,c] + rs[c] * dxo[t,c]
+__global__ void block_bwd_b_kernel(const float* __restrict__ dy, const float* __restrict__ dw_wT,
+                                   const float* __restrict__ row_mask, const float* __restrict__ dxo,
+                                   int ld_dxo, const float* __restrict__ rs, int B, int T, int C,
+                                   float* __restrict__ dx, int ld_dx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const int bi = row / T;
+  const int t = row - bi * T;
+  const int chunks = C >> 7;
+  const float mk = row_mask ? row_mask[row] : 1.f;
+#pragma unroll
+  for (int j = 0; j < MAXC4; ++j) {
+    if (j < chunks) {
+      const int c = j * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int tt = t - k + 3;
+          if (tt >= 0 && tt < T) {
+            const float4 d = ld4(dy + (size_t)(bi * T + tt) * C + c);
+            const float4 w = ld4(dw_wT + k * C + c);
+            acc.x = fmaf(d.x, w.x, acc.x); acc.y = fmaf(d.y, w.y, acc.y);
+            acc.z = fmaf(d.z, w.z, acc.z); acc.w = fmaf(d.w, w.w, acc.w);
+          }
+        }
+        acc.x *= mk; acc.y *= mk; acc.z *= mk; acc.w *= mk;
+      }
+      if (dxo) {
+        const float4 d = ld4(dxo + (size_t)row * ld_dxo + c);
+        float4 r = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rs) r = ld4(rs + c);
+        acc.x = fmaf(d.x, r.x, acc.x); acc.y = fmaf(d.y, r.y, acc.y);
+        acc.z = fmaf(d.z, r.z, acc.z); acc.w = fmaf(d.w, r.w, acc.w);
+      }
+      st4(dx + (size_t)row * ld_dx + c, acc);
+    }
+  }
+}
+
+// PReLU / LeakyReLU / SiLU backward over rows with fused column reductions (thread = column):
+//   dz = dh * act'(z) (written, optionally TF32-rounded); g_bias[c] += sum dz ; g_slope[c] += sum dh*min(z,0)
+__global__ void act_bwd_kernel(const float* __restrict__ dh, int ld_dh, const float* __restrict__ z,
+                               int ld_z, const float* __restrict__ slope, float leaky, int act, int rows,
+                               int cols, int rows_per_cta, float* __restrict__ dz, int ld_dz,
+                               float* __restrict__ g_bias, float* __restrict__ g_slope, int round_tf32) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  const float sl = slope ? slope[c] : leaky;
+  float sb = 0.f, ss = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float d = dh[(size_t)r * ld_dh + c];
+    const float zv = z ? z[(size_t)r * ld_z + c] : 1.f;
+    float o;
+    if (act == F2G_ACT_SILU) {
+      const float sg = 1.f / (1.f + expf(-zv));
+      o = d * sg * (1.f + zv * (1.f - sg));
+    } else if (act == F2G_ACT_NONE) {
+      o = d;
+    } else {
+      o = zv > 0.f ? d : d * sl;
+      ss = fmaf(d, fminf(zv, 0.f), ss);
+    }
+    sb += o;
+    if (dz) dz[(size_t)r * ld_dz + c] = round_tf32 ? tf32_rna(o) : o;
+  }
+  if (g_bias) atomicAdd(g_bias + c, sb);
+  if (g_slope) atomicAdd(g_slope + c, ss);
+}
+
+// dcp[b*cond_T + tm, c] = sum_{f<factor} du[b, tm*factor+f, c]; zero row = all remaining frames
+__global__ void cond_reduce_kernel(const float* __restrict__ du, int B, int T, int C, int cond_T, int factor,
+                                   int zero_row, float* __restrict__ out, int ld_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;     // 0 .. B*cond_T (last = zero row)
+  if (c >= C) return;
+  float s = 0.f;
+  if (row < B * cond_T) {
+    const int bi = row / cond_T, tm = row - bi * cond_T;
+    for (int f = 0; f < factor; ++f) {
+      const int t = tm * factor + f;
+      if (t < T) s += du[((size_t)bi * T + t) * C + c];
+    }
+    out[(size_t)row * ld_out + c] = s;
+  } else {
+    for (int bi = 0; bi < B; ++bi)
+      for (int t = cond_T * factor; t < T; ++t) s += du[((size_t)bi * T + t) * C + c];
+    out[(size_t)zero_row * ld_out + c] = s;
+  }
+}
+
+// iSTFT adjoint, first half: gs[b, p] = g[b, s] * scale / env(p) at p = s + n/2 for s < hop*(F-1), else 0
+__global__ void istft_bwd_prep_kernel(const float* __restrict__ g, int T, int n, int hop, int frames,
+                                      float scale, float* __restrict__ gs, int Lp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bi = blockIdx.y;
+  if (p >= Lp) return;
+  const int s = p - (n >> 1);
+  float v = 0.f;
+  if (s >= 0 && s < hop * (frames - 1) && s < T) {
+    const int f_hi = min(p / hop, frames - 1);
+    const int f_lo = p >= n ? (p - n) / hop + 1 : 0;
+    float env = 0.f;
+    for (int f = f_lo; f <= f_hi; ++f) {
+      const float w = 0.5f - 0.5f * cospif(2.0f * (float)(p - f * hop) / (float)n);
+      env += w * w;
+    }
+    v = g[(size_t)bi * T + s] * scale / env;
+  }
+  gs[(size_t)bi * Lp + p] = v;
+}
+
+// STFT adjoint, second half: fold windowed frame gradients back onto the (reflect padded) signal:
+//   dx[s] = OLA(s + n/2) + [1 <= s <= n/2] OLA(n/2 - s) + [T-1-n/2 <= s <= T-2] OLA(n/2 + 2(T-1) - s)
+__global__ void stft_bwd_fold_kernel(const float* __restrict__ fr, int n, int hop, int frames, int T,
+                                     float* __restrict__ dx, int accumulate) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bi = blockIdx.y;
+  if (s >= T) return;
+  const int h = n >> 1;
+  int pos[3];
+  int np = 0;
+  pos[np++] = s + h;
+  if (s >= 1 && s <= h) pos[np++] = h - s;
+  if (s >= T - 1 - h && s <= T - 2) pos[np++] = h + 2 * (T - 1) - s;
+  float acc = 0.f;
+  for (int q = 0; q < np; ++q) {
+    const int p = pos[q];
+    const int f_hi = min(p / hop, frames - 1);
+    const int f_lo = p >= n ? (p - n) / hop + 1 : 0;
+    for (int f = f_lo; f <= f_hi; ++f) acc += fr[((size_t)bi * frames + f) * n + (p - f * hop)];
+  }
+  float* o = dx + (size_t)bi * T + s;
+  *o = accumulate ? *o + acc : acc;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, int rows_per_cta,
+                              float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += x[(size_t)r * ld + c];
+  atomicAdd(out + c, s);
+}
+
+}  // namespace f2g
+
+using namespace f2g;
+
+static int pick_rows_per_cta(int rows, int col_blocks) {
+  // aim for ~4 CTAs per SM overall
+  int want = (148 * 4 + col_blocks - 1) / col_blocks;
+  if (want < 1) want = 1;
+  int rpc = (rows + want - 1) / want;
+  return rpc < 8 ? 8 : rpc;
+}
+
+extern "C" int f2g_block_bwd_a(const float* da1, int ld_da, const float* y, const float* inv,
+                               const float* bn_bias, const float* log_scale, const float* tscale,
+                               int ld_ts, int B, int T, int C, float* dy, float* du, float* coef,
+                               float* gs, void* stream) {
+  if (C % 128 != 0 || C > MAXC4 * 128) {
+    set_error("f2g_block_bwd_a: channels=%d must be a multiple of 128 (<= %d)", C, MAXC4 * 128);
+    return F2G_EINVAL;
+  }
+  const int rows = B * T;
+  block_bwd_a_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      da1, ld_da, y, inv, bn_bias, log_scale, tscale, ld_ts, B, T, C, dy, du, coef, gs);
+  return check_launch("f2g_block_bwd_a");
+}
+
+extern "C" int f2g_block_bwd_c(const F2GBlockBwdC* p, void* stream) {
+  BlockBwdC a;
+  a.dy = p->dy; a.x = p->x; a.ld_x = p->ld_x; a.row_mask = p->row_mask; a.y = p->y;
+  a.coef = p->coef; a.gs = p->gs; a.bn_bias = p->bn_bias; a.da1 = p->da1; a.ld_da = p->ld_da;
+  a.inv = p->inv; a.cond = p->cond; a.ld_cond = p->ld_cond; a.cond_T = p->cond_T;
+  a.factor = p->factor < 1 ? 1 : p->factor; a.zero_row = p->zero_row;
+  a.dxo = p->dxo; a.ld_dxo = p->ld_dxo;
+  a.g_dww = p->g_dww; a.g_dwb = p->g_dwb; a.g_beta = p->g_beta; a.g_ls = p->g_ls; a.g_ts = p->g_ts;
+  a.ld_gts = p->ld_gts; a.g_rs = p->g_rs; a.g_b2 = p->g_b2;
+  a.B = p->B; a.T = p->T; a.C = p->C;
+  const int cb = (a.C + 127) / 128;
+  int want = (148 * 4) / (cb * a.B);
+  if (want < 1) want = 1;
+  a.rows_per_cta = (a.T + want - 1) / want;
+  if (a.rows_per_cta < 8) a.rows_per_cta = 8;
+  dim3 grid(cb, (a.T + a.rows_per_cta - 1) / a.rows_per_cta, a.B);
+  block_bwd_c_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("f2g_block_bwd_c");
+}
+
+extern "C" int f2g_block_bwd_b(const float* dy, const float* dw_wT, const float* row_mask,
+                               const float* dxo, int ld_dxo, const float* rs, int B, int T, int C,
+                               float* dx, int ld_dx, void* stream) {
+  if (C % 128 != 0 || C > MAXC4 * 128) {
+    set_error("f2g_block_bwd_b: channels=%d must be a multiple of 128 (<= %d)", C, MAXC4 * 128);
+    return F2G_EINVAL;
+  }
+  const int rows = B * T;
+  block_bwd_b_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, dw_wT, row_mask, dxo, ld_dxo, rs, B, T, C, dx, ld_dx);
+  return check_launch("f2g_block_bwd_b");
+}
+
+extern "C" int f2g_act_bwd(const float* dh, int ld_dh, const float* z, int ld_z, const float* slope,
+                           float leaky, int act, int rows, int cols, float* dz, int ld_dz,
+                           float* g_bias, float* g_slope, int round_tf32, void* stream) {
+  const int cb = (cols + 127) / 128;
+  const int rpc = pick_rows_per_cta(rows, cb);
+  dim3 grid(cb, (rows + rpc - 1) / rpc);
+  act_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
+  return check_launch("f2g_act_bwd");
+}
+
+extern "C" int f2g_cond_reduce(const float* du, int B, int T, int C, int cond_T, int factor, int zero_row,
+                               float* out, int ld_out, void* stream) {
+  dim3 grid((C + 127) / 128, B * cond_T + 1);
+  cond_reduce_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(du, B, T, C, cond_T,
+                                                                         factor < 1 ? 1 : factor,
+                                                                         zero_row, out, ld_out);
+  return check_launch("f2g_cond_reduce");
+}
+
+extern "C" int f2g_istft_bwd_prep(const float* g, int B, int T, int n_fft, int hop, int frames,
+                                  float scale, float* gs, void* stream) {
+  const int Lp = n_fft + hop * (frames - 1);
+  dim3 grid((Lp + 255) / 256, B);
+  istft_bwd_prep_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, T, n_fft, hop, frames,
+                                                                             scale, gs, Lp);
+  return check_launch("f2g_istft_bwd_prep");
+}
+
+extern "C" int f2g_stft_bwd_fold(const float* frames_grad, int B, int T, int n_fft, int hop, int frames,
+                                 float* dx, int accumulate, void* stream) {
+  dim3 grid((T + 255) / 256, B);
+  stft_bwd_fold_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames_grad, n_fft, hop,
+                                                                            frames, T, dx, accumulate);
+  return check_launch("f2g_stft_bwd_fold");
+}
+
+extern "C" int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream) {
+  const int cb = (cols + 127) / 128;
+  const int rpc = pick_rows_per_cta(rows, cb);
+  dim3 grid(cb, (rows + rpc - 1) / rpc);
+  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, rpc, out);
+  return check_launch("f2g_colsum");
+}

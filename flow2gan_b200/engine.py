@@ -181,6 +181,7 @@ class InferencePlan:
             self.br.append(w)
         self.t_all: Optional[Tensor] = None
         self.graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
+        self._seen: Dict[Tuple[int, bool], bool] = {}
 
     # ------------------------------------------------------------------ step-invariant part
     def encode_cond(self) -> None:
@@ -305,6 +306,13 @@ class InferencePlan:
             self._run(n, clamp)
             return self.x_audio.clone()
         g = self.graphs.get(key)
+        if g is None and not self._seen.get(key):
+            # first call for this (weights, shape): run eagerly; capture on the second call, so a
+            # training loop whose weights change every iteration never pays for graph capture
+            self._seen[key] = True
+            self._steps = self._prepare_steps(n)
+            self._run(n, clamp)
+            return self.x_audio.clone()
         if g is None:
             self._steps = self._prepare_steps(n)
             self._run(n, clamp)                     # warm-up (also sets kernel attributes)

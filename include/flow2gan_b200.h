@@ -64,6 +64,8 @@ typedef struct F2GGemm {
   float alpha; /* 0 means 1 */
   int round_tf32;
   int accumulate;
+  float* c_pre; /* optional: alpha*acc + bias before the activation, (M, ld_pre) */
+  int ld_pre;
 } F2GGemm;
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
@@ -106,9 +108,9 @@ int f2g_ola_combine(const float* const* frames, const int* n_ffts, const int* ho
  * ConvNeXt-block pieces (modules.py:286-416,456-495), channel-last rows.
  * ------------------------------------------------------------------------------------- */
 /* BiasNorm over the channel dim of each row: y = x * mean((x-bias)^2)^-1/2 * exp(log_scale);
- * log_scale is a device scalar.  y may alias x. */
+ * log_scale is a device scalar.  y may alias x.  inv_out (optional, rows) receives the row scale. */
 int f2g_biasnorm(const float* x, int rows, int C, int ld, const float* bias,
-                 const float* log_scale, float* y, int ld_y, void* stream);
+                 const float* log_scale, float* y, int ld_y, float* inv_out, void* stream);
 
 /* Fused block prologue: mask -> depthwise conv k=7 (zero pad 3, bias) -> BiasNorm ->
  * + cond_proj row -> * (1 + time scale) -> TF32 round.  (ConvNeXtBlock.forward :473-485)
@@ -151,6 +153,69 @@ int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, float* out, in
 
 /* frame mask from lengths: m[b*frames+f] = f < 1 + lens[b]/hop (modules.py:79-82,706-707). */
 int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Backward pieces of the generator path (adjoints of the kernels above; the contractions of
+ * the backward pass are f2g_gemm_tf32 calls with MN-major operands).
+ * ------------------------------------------------------------------------------------- */
+/* Block prologue backward, stage A (BiasNormFunction.backward, modules.py:321-339, fused with the
+ * time-scale / cond adjoints): du = da1*(1+ts), dy = inv*du - coef*(y-beta); per-row coef, gs. */
+int f2g_block_bwd_a(const float* da1, int ld_da, const float* y, const float* inv,
+                    const float* bn_bias, const float* log_scale, const float* tscale, int ld_ts,
+                    int B, int T, int C, float* dy, float* du, float* coef, float* gs, void* stream);
+
+/* Stage C: every per-channel parameter-gradient reduction of one block in one pass (atomicAdd
+ * into the g_* accumulators; NULL skips a term): depthwise weights (7,C) / bias, BiasNorm bias /
+ * log_scale, time-scale (B,C), residual ChannelScale, pwconv2 bias. */
+typedef struct F2GBlockBwdC {
+  const float* dy; const float* x; int ld_x; const float* row_mask; const float* y;
+  const float* coef; const float* gs; const float* bn_bias; const float* da1; int ld_da;
+  const float* inv; const float* cond; int ld_cond; int cond_T; int factor; int zero_row;
+  const float* dxo; int ld_dxo;
+  float* g_dww; float* g_dwb; float* g_beta; float* g_ls; float* g_ts; int ld_gts; float* g_rs;
+  float* g_b2;
+  int B, T, C;
+} F2GBlockBwdC;
+int f2g_block_bwd_c(const F2GBlockBwdC* args, void* stream);
+
+/* Stage B: dx = mask * dwconv^T(dy) + rs * dxo  (either term may be absent). */
+int f2g_block_bwd_b(const float* dy, const float* dw_wT, const float* row_mask, const float* dxo,
+                    int ld_dxo, const float* rs, int B, int T, int C, float* dx, int ld_dx,
+                    void* stream);
+
+/* Activation backward over rows with fused column reductions: dz = dh * act'(z);
+ * g_bias[c] += sum dz; g_slope[c] += sum dh*min(z,0) (PReLU).  act = F2G_ACT_*. */
+int f2g_act_bwd(const float* dh, int ld_dh, const float* z, int ld_z, const float* slope, float leaky,
+                int act, int rows, int cols, float* dz, int ld_dz, float* g_bias, float* g_slope,
+                int round_tf32, void* stream);
+
+/* Adjoint of upsample_cond (modules.py:668-680): frame-rate gradient rows -> mel-rate rows
+ * (+ the shared zero row). */
+int f2g_cond_reduce(const float* du, int B, int T, int C, int cond_T, int factor, int zero_row,
+                    float* out, int ld_out, void* stream);
+
+/* iSTFT adjoint: g (B,T) -> padded-domain gs (B, n + hop*(frames-1)) = g*scale/env, then
+ * f2g_istft_bwd_spec: framed rFFT * c_k/n (* row mask) -> packed (rows, ld) gradient. */
+int f2g_istft_bwd_prep(const float* g, int B, int T, int n_fft, int hop, int frames, float scale,
+                       float* gs, void* stream);
+int f2g_istft_bwd_spec(const float* gs, int B, int Lp, int n_fft, int hop, const float* row_mask,
+                       float* dpacked, int ld, int round_tf32, void* stream);
+
+/* STFT adjoint: packed spectrum gradient -> windowed frame gradients -> fold onto the signal
+ * (overlap-add + reflect-padding adjoint). */
+int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n_fft, float* frames_out,
+                        void* stream);
+int f2g_stft_bwd_fold(const float* frames_grad, int B, int T, int n_fft, int hop, int frames,
+                      float* dx, int accumulate, void* stream);
+
+/* Fused backward of a [log-]filterbank spectrogram (MelSpectrogram power=1 / LinearFilter-
+ * Spectrogram power=2): dF (rows, ld_dF) -> windowed frame gradients (rows, n_fft). */
+int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
+                      const float* fb, int n_filt, float log_clip, const float* dF, int ld_dF,
+                      float* frames_out, void* stream);
+
+/* out[c] += sum_r x[r*ld + c]  (bias gradients). */
+int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused multi-tensor ScaledAdam step (flow2gan/optim.py:125-255,451-619) for ONE param group.
