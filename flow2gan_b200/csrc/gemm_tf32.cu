@@ -26,7 +26,7 @@ constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 4;
-constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
+constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 36 * 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
@@ -93,7 +93,6 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
   // 128B-swizzled operand tiles need 1024 B alignment; keep every access in the shared state
   // space (a uintptr_t round-up would turn them into generic LD/ST -- measured 10x slower).
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t scratch_all = smem_u32(smem) + STAGES * Cfg::STAGE_BYTES;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("f2g gemm: dynamic smem base not 1024B aligned\n");
     __trap();
@@ -225,11 +224,13 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------------
-    // TMEM lane = output row.  Each warp drains its 32 rows in 32-column chunks, transposes the
-    // chunk through a padded smem scratch so that lane == column (coalesced 128 B row segments,
-    // per-column parameters in registers), applies the fused epilogue and stores.
+    // TMEM lane = output row.  Each warp drains its 32 rows in 32-column chunks: tcgen05.ld ->
+    // 8 x STS.128 into a padded (stride 36) smem scratch -> re-read as 4 rows x 8 column-quads
+    // per pass so that every LDG/STG is a 128-bit access and a warp instruction covers four
+    // full 128 B row segments; per-column parameters live in registers as float4.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    const uint32_t scratch = scratch_all + (warp - 2) * (32 * 33 * 4);
+    float* const scratch = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES) + (warp - 2) * (32 * 36);
+    const int cg = lane & 7, rsub = lane >> 3;
     int ab = 0;
     uint32_t ab_phase = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -238,11 +239,10 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       // hoist every epilogue parameter out of the constant bank once per tile
       const int n0 = tc.n0 * BN;
       const int row_base = tc.m0 + q * 32;
-      const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate;
+      const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate, ld_pre = pr.ld_pre;
       const int rows = min(32, pr.M - row_base);
       float* const cbase = pr.c;
       float* const pre_p = pr.c_pre;
-      const int ld_pre = pr.ld_pre;
       const float* const bias_p = pr.bias;
       const float* const slope_p = pr.slope;
       const float* const res_p = pr.res;
@@ -253,6 +253,12 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       const bool do_round = pr.round_tf32 != 0, do_acc = pr.accumulate != 0;
       const float alpha = pr.alpha, leaky = pr.leaky;
       const bool skip = (g.dbg & 4) != 0;
+      // 128-bit global accesses need 16 B aligned rows
+      const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
+      const bool vec_res = !res_p || (((ld_res & 3) == 0) && ((reinterpret_cast<uintptr_t>(res_p) & 15) == 0));
+      const bool vec_gate = !gate_p || (((ld_gate & 3) == 0) && ((reinterpret_cast<uintptr_t>(gate_p) & 15) == 0));
+      const bool vec_pre = !pre_p || (((ld_pre & 3) == 0) && ((reinterpret_cast<uintptr_t>(pre_p) & 15) == 0));
+      const bool vec_all = vec_c && vec_res && vec_gate && vec_pre;
 
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
@@ -264,64 +270,86 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
         tmem_ld_wait();
         if (rows <= 0) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sts_f32(scratch + (lane * 33 + j) * 4, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(scratch + lane * 36 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
         __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = col < N;
-        const float bias = (bias_p && col_ok) ? __ldg(bias_p + col) : 0.f;
-        const float slope = (slope_p && col_ok) ? __ldg(slope_p + col) : leaky;
-        const float rsc = (rsc_p && col_ok) ? __ldg(rsc_p + col) : 1.f;
+        const int col = n0 + c0 + 4 * cg;
+        const int ncol = min(4, N - col);          // valid columns of this lane's quad (<= 0: none)
+        float bias[4], slope[4], rsc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool okc = e < ncol;
+          bias[e] = (bias_p && okc) ? __ldg(bias_p + col + e) : 0.f;
+          slope[e] = (slope_p && okc) ? __ldg(slope_p + col + e) : leaky;
+          rsc[e] = (rsc_p && okc) ? __ldg(rsc_p + col + e) : 1.f;
+        }
+        const bool quad = vec_all && ncol == 4;
+        // Keep this loop COMPACT: a fully unrolled generic epilogue (3.8k SASS instructions) made
+        // the four epilogue warps instruction-fetch bound (ncu: stall_no_inst) -- 18-28 us/tile.
+        if (quad) {
+#pragma unroll 4
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+            const int row = row_base + i;
+            const float4 xv = *reinterpret_cast<const float4*>(scratch + i * 36 + 4 * cg);
+            float x[4] = {fmaf(xv.x, alpha, bias[0]), fmaf(xv.y, alpha, bias[1]), fmaf(xv.z, alpha, bias[2]),
+                          fmaf(xv.w, alpha, bias[3])};
+            if (pre_p)
+              *reinterpret_cast<float4*>(pre_p + (size_t)row * ld_pre + col) = make_float4(x[0], x[1], x[2], x[3]);
+            if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * slope[e];
+            } else if (act == F2G_ACT_SILU) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = x[e] / (1.f + __expf(-x[e]));
+            }
+            if (gate_p) {  // multiply by d(act)/dz evaluated at a saved pre-activation
+              const float4 t = __ldg(reinterpret_cast<const float4*>(gate_p + (size_t)row * ld_gate + col));
+              x[0] *= (t.x > 0.f ? 1.f : slope[0]); x[1] *= (t.y > 0.f ? 1.f : slope[1]);
+              x[2] *= (t.z > 0.f ? 1.f : slope[2]); x[3] *= (t.w > 0.f ? 1.f : slope[3]);
+            }
+            if (res_p) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(res_p + (size_t)row * ld_res + col));
+              x[0] = fmaf(rsc[0], t.x, x[0]); x[1] = fmaf(rsc[1], t.y, x[1]);
+              x[2] = fmaf(rsc[2], t.z, x[2]); x[3] = fmaf(rsc[3], t.w, x[3]);
+            }
+            if (rowsc_p) {
+              const float rs = __ldg(rowsc_p + row);
+              x[0] *= rs; x[1] *= rs; x[2] *= rs; x[3] *= rs;
+            }
+            float* dst = cbase + (size_t)row * ldc + col;
+            if (do_acc) {
+              const float4 t = *reinterpret_cast<const float4*>(dst);
+              x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+            }
+            if (do_round) {
+              x[0] = tf32_rna(x[0]); x[1] = tf32_rna(x[1]); x[2] = tf32_rna(x[2]); x[3] = tf32_rna(x[3]);
+            }
+            *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+        } else if (ncol > 0) {   // unaligned leading dimension or N tail: scalar path
 #pragma unroll 1
-        for (int i0 = 0; i0 < rows; i0 += 8) {
-          float x[8];
-          bool ok[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            ok[u] = col_ok && (i0 + u < rows);
-            x[u] = fmaf(lds_f32(scratch + ((i0 + u) * 33 + lane) * 4), alpha, bias);
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+            const int row = row_base + i;
+#pragma unroll 1
+            for (int e = 0; e < ncol; ++e) {
+              float x = fmaf(scratch[i * 36 + 4 * cg + e], alpha, bias[e]);
+              if (pre_p) pre_p[(size_t)row * ld_pre + col + e] = x;
+              if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) x = x > 0.f ? x : x * slope[e];
+              else if (act == F2G_ACT_SILU) x = x / (1.f + __expf(-x));
+              if (gate_p) x *= (__ldg(gate_p + (size_t)row * ld_gate + col + e) > 0.f ? 1.f : slope[e]);
+              if (res_p) x = fmaf(rsc[e], __ldg(res_p + (size_t)row * ld_res + col + e), x);
+              if (rowsc_p) x *= __ldg(rowsc_p + row);
+              float* dst = cbase + (size_t)row * ldc + col + e;
+              if (do_acc) x += *dst;
+              *dst = do_round ? tf32_rna(x) : x;
+            }
           }
-          if (pre_p) {   // keep the pre-activation for the backward pass
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (ok[u]) pre_p[(size_t)(row_base + i0 + u) * ld_pre + col] = x[u];
-          }
-          if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = x[u] > 0.f ? x[u] : x[u] * slope;
-          } else if (act == F2G_ACT_SILU) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = x[u] / (1.f + __expf(-x[u]));
-          }
-          if (gate_p) {  // multiply by d(act)/dz evaluated at a saved pre-activation
-            float z[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              z[u] = ok[u] ? __ldg(gate_p + (size_t)(row_base + i0 + u) * ld_gate + col) : 1.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] *= (z[u] > 0.f ? 1.f : slope);
-          }
-          if (res_p) {
-            float r[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              r[u] = ok[u] ? __ldg(res_p + (size_t)(row_base + i0 + u) * ld_res + col) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = fmaf(rsc, r[u], x[u]);
-          }
-          if (rowsc_p) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (i0 + u < rows) x[u] *= __ldg(rowsc_p + row_base + i0 + u);
-          }
-          float* dst = cbase + (size_t)(row_base + i0) * ldc + col;
-          if (do_acc) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (ok[u]) x[u] += dst[(size_t)u * ldc];
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (ok[u]) dst[(size_t)u * ldc] = do_round ? tf32_rna(x[u]) : x[u];
         }
         __syncwarp();
       }
