@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libflow2gan_b200.so")
 
 ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_SILU = 0, 1, 2, 3
-SPEC_PACKED, SPEC_MAG, SPEC_POWER = 0, 1, 2
+SPEC_PACKED, SPEC_MAG, SPEC_POWER, SPEC_COMPLEX = 0, 1, 2, 3
 GEMM_MAX_PROBLEMS = 8
 
 _fp = C.c_void_p
@@ -35,13 +35,18 @@ class F2GGemm(C.Structure):
         ("row_scale", _fp), ("gate", _fp),
         ("ld_res", _i), ("ld_gate", _i),
         ("act", _i), ("leaky", _f), ("alpha", _f),
-        ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i),
+        ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i), ("split_k", _i),
     ]
 
 
 class F2GLinear(C.Structure):
     _fields_ = [("inp", _fp), ("W", _fp), ("bias", _fp), ("out", _fp),
                 ("K", _i), ("O", _i), ("ld_in", _i), ("ldw", _i), ("ld_out", _i)]
+
+
+class F2GConv2d(C.Structure):
+    _fields_ = [("Nb", _i), ("H", _i), ("W", _i), ("C", _i), ("pitch_h", _ll), ("pitch_n", _ll),
+                ("kh", _i), ("kw", _i), ("sh", _i), ("sw", _i), ("ph", _i), ("pw", _i), ("ldk", _i)]
 
 
 class F2GBlockBwdC(C.Structure):
@@ -89,10 +94,13 @@ _SIGS = {
     "f2g_cond_reduce": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_istft_bwd_prep": ([_fp, _i, _i, _i, _i, _i, _f, _fp, _fp], _i),
     "f2g_istft_bwd_spec": ([_fp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp], _i),
-    "f2g_stft_bwd_frames": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_stft_bwd_frames": ([_fp, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_stft_bwd_fold": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_spec_loss_bwd": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _f, _fp, _i, _fp, _fp], _i),
     "f2g_colsum": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
+    "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
+    "f2g_conv_w_pack": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
 }
 
@@ -162,7 +170,7 @@ def stream() -> int:
 def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
               act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
-              ld_pre=0) -> F2GGemm:
+              ld_pre=0, split_k=1) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -174,6 +182,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.act, d.leaky, d.alpha = act, leaky, alpha
     d.round_tf32, d.accumulate = round_tf32, accumulate
     d.c_pre, d.ld_pre = c_pre, ld_pre
+    d.split_k = split_k
     return d
 
 
@@ -299,8 +308,9 @@ def istft_bwd_spec(gs, B, Lp, n_fft, hop, row_mask, dpacked, ld, round_tf32=0):
                                     round_tf32, stream()))
 
 
-def stft_bwd_frames(dpacked, rows, ld, n_fft, frames_out):
-    _check(lib().f2g_stft_bwd_frames(ptr(dpacked), rows, ld, n_fft, ptr(frames_out), stream()))
+def stft_bwd_frames(dpacked, rows, ld, n_fft, frames_out, interleaved=0):
+    _check(lib().f2g_stft_bwd_frames(ptr(dpacked), rows, ld, n_fft, ptr(frames_out), int(interleaved),
+                                     stream()))
 
 
 def stft_bwd_fold(frames_grad, B, T, n_fft, hop, frames, dx, accumulate):
@@ -315,3 +325,22 @@ def spec_loss_bwd(audio, B, T, ld_audio, n_fft, hop, mode, fb, n_filt, log_clip,
 
 def colsum(x, ld, rows, cols, out):
     _check(lib().f2g_colsum(ptr(x), ld, rows, cols, ptr(out), stream()))
+
+
+def conv_geom(Nb, H, W, Cc, pitch_h, pitch_n, kh, kw, sh, sw, ph, pw, ldk) -> F2GConv2d:
+    g = F2GConv2d()
+    g.Nb, g.H, g.W, g.C, g.pitch_h, g.pitch_n = Nb, H, W, Cc, pitch_h, pitch_n
+    g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.ldk = kh, kw, sh, sw, ph, pw, ldk
+    return g
+
+
+def im2col2d(x_ptr, geom, col, round_tf32=1):
+    _check(lib().f2g_im2col2d(x_ptr, C.byref(geom), ptr(col), round_tf32, stream()))
+
+
+def col2im2d(dcol, geom, dx_ptr, accumulate=0):
+    _check(lib().f2g_col2im2d(ptr(dcol), C.byref(geom), dx_ptr, accumulate, stream()))
+
+
+def conv_w_pack(src, Co, Ci, taps, Co_pad, ld, dst, direction):
+    _check(lib().f2g_conv_w_pack(ptr(src), Co, Ci, taps, Co_pad, ld, ptr(dst), direction, stream()))

@@ -1,0 +1,155 @@
+// Conv2d of the discriminators as gather + tensor-core GEMM on channel-last tensors:
+//   im2col2d : (Nb, H, W, C) [a W-band of a wider tensor allowed] -> (Nb*Ho*Wo, kh*kw*C [+pad])
+//   col2im2d : adjoint (gather form), accumulates every (ih, iw) tap that touches an input pixel
+//   conv weight pack / unpack between the parameter layout (Co, Ci, kh, kw) and the GEMM layout
+//   (Co_pad, (ih*kw + iw)*Ci + ci)
+// Reference: torch.nn.Conv2d call sites flow2gan/models/discriminators.py:65-76,95-104,171-184,
+// 203-217 ((5,1)/(3,1) strided convs of DiscriminatorP, (3,9)/(3,3) convs of DiscriminatorR).
+#include "common.cuh"
+#include "../../include/flow2gan_b200.h"
+
+namespace f2g {
+
+struct ConvGeom {
+  int Nb, H, W, C;        // logical input (band) dims
+  long long pitch_h;      // elements between consecutive h rows of the underlying buffer
+  long long pitch_n;      // elements between consecutive n images
+  int kh, kw, sh, sw, ph, pw, Ho, Wo;
+  int ldk;                // leading dim of the col matrix (>= kh*kw*C, multiple of 4)
+};
+
+__global__ void im2col2d_kernel(const float* __restrict__ x, ConvGeom g, float* __restrict__ col,
+                                int round_tf32) {
+  const long long total = (long long)g.Nb * g.Ho * g.Wo * g.ldk;
+  const int K = g.kh * g.kw * g.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % g.ldk);
+    const long long m = i / g.ldk;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % g.C;
+      const int tap = k / g.C;
+      const int iw = tap % g.kw, ih = tap / g.kw;
+      const int wo = (int)(m % g.Wo);
+      const long long t = m / g.Wo;
+      const int ho = (int)(t % g.Ho);
+      const int n = (int)(t / g.Ho);
+      const int h = ho * g.sh - g.ph + ih, w = wo * g.sw - g.pw + iw;
+      if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+        v = x[(long long)n * g.pitch_n + (long long)h * g.pitch_h + (long long)w * g.C + c];
+    }
+    col[i] = round_tf32 ? tf32_rna(v) : v;
+  }
+}
+
+__global__ void col2im2d_kernel(const float* __restrict__ dcol, ConvGeom g, float* __restrict__ dx,
+                                int accumulate) {
+  const long long total = (long long)g.Nb * g.H * g.W * g.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % g.C);
+    long long t = i / g.C;
+    const int w = (int)(t % g.W);
+    t /= g.W;
+    const int h = (int)(t % g.H);
+    const int n = (int)(t / g.H);
+    float acc = 0.f;
+    for (int ih = 0; ih < g.kh; ++ih) {
+      const int hn = h + g.ph - ih;
+      if (hn < 0 || hn % g.sh != 0) continue;
+      const int ho = hn / g.sh;
+      if (ho >= g.Ho) continue;
+      for (int iw = 0; iw < g.kw; ++iw) {
+        const int wn = w + g.pw - iw;
+        if (wn < 0 || wn % g.sw != 0) continue;
+        const int wo = wn / g.sw;
+        if (wo >= g.Wo) continue;
+        const long long m = ((long long)n * g.Ho + ho) * g.Wo + wo;
+        acc += dcol[m * g.ldk + (ih * g.kw + iw) * g.C + c];
+      }
+    }
+    float* o = dx + (long long)n * g.pitch_n + (long long)h * g.pitch_h + (long long)w * g.C + c;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// dir 0: param (Co, Ci, kh*kw) -> packed (Co_pad rows, ld), TF32 rounded, padding zeroed
+// dir 1: packed gradient -> param layout (no rounding)
+__global__ void conv_w_pack_kernel(const float* __restrict__ src, int Co, int Ci, int taps, int Co_pad,
+                                   int ld, float* __restrict__ dst, int dir) {
+  if (dir == 0) {
+    const long long total = (long long)Co_pad * ld;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int k = (int)(i % ld), co = (int)(i / ld);
+      float v = 0.f;
+      if (co < Co && k < taps * Ci) {
+        const int ci = k % Ci, tap = k / Ci;
+        v = src[((long long)co * Ci + ci) * taps + tap];
+      }
+      dst[i] = tf32_rna(v);
+    }
+  } else {
+    const long long total = (long long)Co * Ci * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int tap = (int)(i % taps);
+      const long long t = i / taps;
+      const int ci = (int)(t % Ci), co = (int)(t / Ci);
+      dst[i] = src[(long long)co * ld + tap * Ci + ci];
+    }
+  }
+}
+
+}  // namespace f2g
+
+using namespace f2g;
+
+static int fill_geom(ConvGeom& g, const F2GConv2d* p) {
+  g.Nb = p->Nb; g.H = p->H; g.W = p->W; g.C = p->C;
+  g.pitch_h = p->pitch_h; g.pitch_n = p->pitch_n;
+  g.kh = p->kh; g.kw = p->kw; g.sh = p->sh; g.sw = p->sw; g.ph = p->ph; g.pw = p->pw;
+  g.Ho = (p->H + 2 * p->ph - p->kh) / p->sh + 1;
+  g.Wo = (p->W + 2 * p->pw - p->kw) / p->sw + 1;
+  g.ldk = p->ldk;
+  if (g.Ho < 1 || g.Wo < 1 || g.ldk < g.kh * g.kw * g.C || (g.ldk & 3)) {
+    set_error("conv2d geometry invalid (Ho=%d Wo=%d ldk=%d K=%d)", g.Ho, g.Wo, g.ldk, g.kh * g.kw * g.C);
+    return F2G_EINVAL;
+  }
+  return 0;
+}
+
+static int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = 148LL * 32;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+extern "C" int f2g_im2col2d(const float* x, const F2GConv2d* p, float* col, int round_tf32, void* stream) {
+  ConvGeom g;
+  if (int rc = fill_geom(g, p)) return rc;
+  const long long total = (long long)g.Nb * g.Ho * g.Wo * g.ldk;
+  im2col2d_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
+  return check_launch("f2g_im2col2d");
+}
+
+extern "C" int f2g_col2im2d(const float* dcol, const F2GConv2d* p, float* dx, int accumulate, void* stream) {
+  ConvGeom g;
+  if (int rc = fill_geom(g, p)) return rc;
+  const long long total = (long long)g.Nb * g.H * g.W * g.C;
+  col2im2d_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
+  return check_launch("f2g_col2im2d");
+}
+
+extern "C" int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int Co_pad, int ld, float* dst,
+                               int dir, void* stream) {
+  if (ld < taps * Ci || (ld & 3) || Co_pad < Co) {
+    set_error("f2g_conv_w_pack: bad ld=%d (need >= %d, multiple of 4)", ld, taps * Ci);
+    return F2G_EINVAL;
+  }
+  const long long total = dir == 0 ? (long long)Co_pad * ld : (long long)Co * Ci * taps;
+  conv_w_pack_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, Co, Ci, taps,
+                                                                                    Co_pad, ld, dst, dir);
+  return check_launch("f2g_conv_w_pack");
+}

@@ -52,6 +52,7 @@ struct alignas(64) DevProblem {
   int ldc, ld_res, ld_gate, ld_pre;
   int M, N, K;
   int m_tiles, n_tiles, tile_begin;
+  int split_k, kb_total, kb_per;
   int act, round_tf32, accumulate;
   float leaky, alpha;
 };
@@ -67,7 +68,7 @@ struct alignas(64) DevGroup {
 };
 
 struct TileCoord {
-  int prob, m0, n0;
+  int prob, m0, n0, kb0, kb1;
 };
 
 F2G_DEVINL TileCoord decode_tile(const DevGroup& g, int tile) {
@@ -75,12 +76,17 @@ F2G_DEVINL TileCoord decode_tile(const DevGroup& g, int tile) {
 #pragma unroll 1
   for (int i = 1; i < g.n_problems; ++i)
     if (tile >= g.p[i].tile_begin) pi = i;
-  const int local = tile - g.p[pi].tile_begin;
+  int local = tile - g.p[pi].tile_begin;
   const int nt = g.p[pi].n_tiles;
+  const int mn = nt * g.p[pi].m_tiles;
+  const int ks = local / mn;          // K-split index (0 when split_k == 1)
+  local -= ks * mn;
   TileCoord t;
   t.prob = pi;
   t.m0 = (local / nt) * BM;
   t.n0 = (local % nt);
+  t.kb0 = ks * g.p[pi].kb_per;
+  t.kb1 = min(t.kb0 + g.p[pi].kb_per, g.p[pi].kb_total);
   return t;
 }
 
@@ -140,8 +146,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
         const TileCoord tc = decode_tile(g, tile);
         const DevProblem& pr = g.p[tc.prob];
         const int n0 = tc.n0 * BN;
-        const int kblocks = (pr.K + BK - 1) / BK;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
@@ -191,12 +196,10 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       uint32_t ab_phase = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
-        const DevProblem& pr = g.p[tc.prob];
-        const int kblocks = (pr.K + BK - 1) / BK;
         mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + ab * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           // Descriptors differ only in the 14-bit (address >> 4) field: add the stage / k-step
@@ -209,7 +212,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = adesc0 + soff + (uint32_t)((k * a_kstep) >> 4);
             const uint64_t bdesc = bdesc0 + soff + (uint32_t)((k * b_kstep) >> 4);
-            if (!dbg_no_mma) umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (!dbg_no_mma) umma_tf32(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -284,6 +287,17 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           bias[e] = (bias_p && okc) ? __ldg(bias_p + col + e) : 0.f;
           slope[e] = (slope_p && okc) ? __ldg(slope_p + col + e) : leaky;
           rsc[e] = (rsc_p && okc) ? __ldg(rsc_p + col + e) : 1.f;
+        }
+        if (pr.split_k > 1) {   // partial-K tile: atomically accumulate into the pre-zeroed C
+#pragma unroll 1
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+            for (int e = 0; e < ncol; ++e)
+              atomicAdd(cbase + (size_t)(row_base + i) * ldc + col + e, scratch[i * 36 + 4 * cg + e] * alpha);
+          }
+          __syncwarp();
+          continue;
         }
         const bool quad = vec_all && ncol == 4;
         // Keep this loop COMPACT: a fully unrolled generic epilogue (3.8k SASS instructions) made
@@ -498,7 +512,16 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     p.tile_begin = tiles;
     p.act = d.act; p.round_tf32 = d.round_tf32; p.accumulate = d.accumulate;
     p.leaky = d.leaky; p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
-    tiles += p.m_tiles * p.n_tiles;
+    p.kb_total = (d.K + BK - 1) / BK;
+    int sk = d.split_k < 1 ? 1 : d.split_k;
+    if (sk > p.kb_total) sk = p.kb_total;
+    p.kb_per = (p.kb_total + sk - 1) / sk;
+    p.split_k = (p.kb_total + p.kb_per - 1) / p.kb_per;      // every split owns >= 1 k-block
+    if (p.split_k > 1 && (d.bias || d.act || d.res || d.gate || d.row_scale || d.c_pre || d.round_tf32)) {
+      set_error("split-K gemm supports the plain (alpha) epilogue only");
+      return F2G_EINVAL;
+    }
+    tiles += p.m_tiles * p.n_tiles * p.split_k;
   }
   g.n_problems = n;
   g.total_tiles = tiles;

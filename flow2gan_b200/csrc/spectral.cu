@@ -106,6 +106,14 @@ __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio
     for (int k = 2 * nb + threadIdx.x; k < ld_out; k += blockDim.x) o[k] = 0.f;
     return;
   }
+  if (mode == F2G_SPEC_COMPLEX_BANDS) {   // interleaved (re, im) per bin: (rows, freq, 2) channel-last
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      const float2 v = X[k];
+      o[2 * k] = v.x;
+      o[2 * k + 1] = v.y;
+    }
+    return;
+  }
   // magnitude / power, optionally contracted with a filterbank
   for (int k = threadIdx.x; k < nb; k += blockDim.x) {
     const float2 v = X[k];
@@ -198,7 +206,7 @@ __global__ void ola_combine_kernel(OlaArgs a, const float* __restrict__ weight,
 
 // STFT adjoint, per frame: fr[i] = w[i] * Re( sum_{k<=n/2} (dRe_k + i dIm_k) e^{+2 pi i k i / n} )
 __global__ void stft_bwd_frames_kernel(const float* __restrict__ dpacked, int ld, int n, int logn,
-                                       float* __restrict__ frames_out) {
+                                       float* __restrict__ frames_out, int interleaved) {
   extern __shared__ float2 sm[];
   float2* a = sm;
   float2* b = sm + n;
@@ -207,8 +215,11 @@ __global__ void stft_bwd_frames_kernel(const float* __restrict__ dpacked, int ld
   const int nb = (n >> 1) + 1;
   const float* p = dpacked + (size_t)row * ld;
   fill_twiddles(tw, n);
-  for (int k = threadIdx.x; k < n; k += blockDim.x)
-    a[k] = k < nb ? make_float2(p[k], p[nb + k]) : make_float2(0.f, 0.f);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    float2 v = make_float2(0.f, 0.f);
+    if (k < nb) v = interleaved ? make_float2(p[2 * k], p[2 * k + 1]) : make_float2(p[k], p[nb + k]);
+    a[k] = v;
+  }
   __syncthreads();
   const float2* y = block_fft<true>(a, b, tw, n, logn);
   float* o = frames_out + (size_t)row * n;
@@ -336,7 +347,8 @@ static int stft_launch(const float* audio, int B, int T, int ld_audio, int n_fft
     set_error("f2g_stft: signal too short (n_fft=%d, T=%d, center=%d)", n_fft, T, center);
     return F2G_EINVAL;
   }
-  if (mode != F2G_SPEC_PACKED && mode != F2G_SPEC_MAG && mode != F2G_SPEC_POWER) {
+  if (mode != F2G_SPEC_PACKED && mode != F2G_SPEC_MAG && mode != F2G_SPEC_POWER &&
+      mode != F2G_SPEC_COMPLEX_BANDS) {
     set_error("f2g_stft: bad mode %d", mode);
     return F2G_EINVAL;
   }
@@ -364,7 +376,7 @@ extern "C" int f2g_istft_bwd_spec(const float* gs, int B, int Lp, int n_fft, int
 }
 
 extern "C" int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n_fft, float* frames_out,
-                                   void* stream) {
+                                   int interleaved, void* stream) {
   const int logn = ilog2_exact(n_fft);
   if (logn < 5 || n_fft > 2048) {
     set_error("f2g_stft_bwd_frames: n_fft=%d must be a power of two in [32, 2048]", n_fft);
@@ -373,7 +385,7 @@ extern "C" int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n
   const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2);
   stft_bwd_frames_kernel<<<rows, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dpacked, ld, n_fft, logn, frames_out);
+      dpacked, ld, n_fft, logn, frames_out, interleaved);
   return check_launch("f2g_stft_bwd_frames");
 }
 

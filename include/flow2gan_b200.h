@@ -66,6 +66,8 @@ typedef struct F2GGemm {
   int accumulate;
   float* c_pre; /* optional: alpha*acc + bias before the activation, (M, ld_pre) */
   int ld_pre;
+  int split_k;  /* > 1: K is split over that many CTAs per tile, results atomically added into a
+                   pre-zeroed C (plain epilogue only) -- used by weight-gradient GEMMs with huge K */
 } F2GGemm;
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
@@ -77,6 +79,7 @@ int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
  * audio: (B, T) rows of stride ld_audio.  frames = 1 + T/hop.  One CTA per frame.
  *   mode PACKED : out[(b*frames+f)*ld_out + c] = Re(bin c), c<=n/2 ; Im at c + n/2+1
  *   mode MAG    : |S|   (n/2+1 columns)          mode POWER : |S|^2
+ *   mode COMPLEX_BANDS : interleaved (re, im) per bin = channel-last (rows, freq, 2) for the MRD
  * pre (optional, (B,2)): sample -> (x - pre[b][0]) * pre[b][1] before windowing (MRD).
  * fb (optional, (n/2+1, n_filt) row-major): if given, the MAG/POWER spectrum is contracted
  * with fb in fp32 inside the kernel and out gets n_filt columns; log_clip > 0 applies
@@ -204,7 +207,7 @@ int f2g_istft_bwd_spec(const float* gs, int B, int Lp, int n_fft, int hop, const
 /* STFT adjoint: packed spectrum gradient -> windowed frame gradients -> fold onto the signal
  * (overlap-add + reflect-padding adjoint). */
 int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n_fft, float* frames_out,
-                        void* stream);
+                        int interleaved, void* stream);
 int f2g_stft_bwd_fold(const float* frames_grad, int B, int T, int n_fft, int hop, int frames,
                       float* dx, int accumulate, void* stream);
 
@@ -216,6 +219,26 @@ int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft,
 
 /* out[c] += sum_r x[r*ld + c]  (bias gradients). */
 int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Conv2d of the discriminators (discriminators.py:65-76,171-184) = gather + f2g_gemm_tf32 on
+ * channel-last tensors.  The input may be a W-band [w0, w0+W) of a wider (Nb, H, Wfull, C)
+ * buffer: pass the band base pointer and the buffer pitches (elements).
+ * ------------------------------------------------------------------------------------- */
+typedef struct F2GConv2d {
+  int Nb, H, W, C;
+  long long pitch_h, pitch_n;
+  int kh, kw, sh, sw, ph, pw;
+  int ldk; /* leading dimension of the column matrix: >= kh*kw*C, multiple of 4 */
+} F2GConv2d;
+/* col[(n,ho,wo), (ih,iw,c)] = x[n, ho*sh-ph+ih, wo*sw-pw+iw, c] (0 outside), padding columns 0 */
+int f2g_im2col2d(const float* x, const F2GConv2d* geom, float* col, int round_tf32, void* stream);
+/* adjoint of im2col2d: dx (+)= sum of the taps that read each input element */
+int f2g_col2im2d(const float* dcol, const F2GConv2d* geom, float* dx, int accumulate, void* stream);
+/* dir 0: (Co, Ci, taps) parameter -> (Co_pad, ld) GEMM operand [co][tap*Ci + ci], TF32-rounded;
+ * dir 1: packed gradient -> parameter layout. */
+int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int Co_pad, int ld, float* dst, int dir,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused multi-tensor ScaledAdam step (flow2gan/optim.py:125-255,451-619) for ONE param group.

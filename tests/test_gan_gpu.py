@@ -1,0 +1,92 @@
+"""GAN stage parity against golden outputs of the reference itself (tests/golden/ref_gan_24k.pt):
+D-phase / G-phase loss tuples (gan.py:101-166) and the gradients of the stepped half after the
+finetune.py loss weighting, plus conv2d building-block checks against torch on CPU.
+Loss values: 2e-3 relative (TF32 discriminators + generator); gradients: see test_train_gpu.py."""
+import os
+import random
+
+import pytest
+import torch
+
+from _cases import GOLDEN, rel_rms
+from oracle.synth import synth_state_dict
+from test_train_gpu import _assert_grads, _grad_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape,k,s,p,leaky", [
+    ((2, 40, 3, 32), (5, 1), (3, 1), (2, 0), 0.1),
+    ((2, 9, 37, 2), (3, 9), (1, 1), (1, 4), 0.1),
+    ((2, 9, 37, 32), (3, 9), (1, 2), (1, 4), 0.1),
+    ((2, 7, 11, 32), (3, 3), (1, 1), (1, 1), None),
+    ((3, 50, 2, 1), (5, 1), (3, 1), (2, 0), 0.1),
+    ((2, 12, 5, 1024), (3, 1), (1, 1), (1, 0), None),
+])
+def test_conv2d_cl_forward_backward(shape, k, s, p, leaky):
+    from flow2gan_b200.discriminators import conv2d_cl
+    gen = torch.Generator().manual_seed(sum(shape))
+    Nb, H, W, C = shape
+    Co = 1 if leaky is None else 48
+    conv = torch.nn.Conv2d(C, Co, k, s, padding=p)
+    x = torch.randn(Nb, H, W + 6, C, generator=gen)            # a band [3, 3+W) of a wider tensor
+    xg = x.cuda().requires_grad_(True)
+    conv_g = torch.nn.Conv2d(C, Co, k, s, padding=p).cuda()
+    conv_g.load_state_dict(conv.state_dict())
+    y = conv2d_cl(xg[:, :, 3:3 + W, :], conv_g, leaky)
+    xr = x.clone().requires_grad_(True)
+    yr = conv(xr[:, :, 3:3 + W, :].permute(0, 3, 1, 2))
+    if leaky is not None:
+        yr = torch.nn.functional.leaky_relu(yr, leaky)
+    yr = yr.permute(0, 2, 3, 1)
+    assert y.shape == yr.shape
+    assert rel_rms(y.detach().cpu(), yr.detach()) < 1e-3
+    w = torch.randn(yr.shape, generator=gen)
+    (y * w.cuda()).sum().backward()
+    (yr * w).sum().backward()
+    assert rel_rms(xg.grad.cpu(), xr.grad) < 2e-3
+    assert rel_rms(conv_g.weight.grad.cpu(), conv.weight.grad) < 2e-3
+    assert rel_rms(conv_g.bias.grad.cpu(), conv.bias.grad) < 2e-3
+
+
+def _gan(g):
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.gan import GAN
+    from flow2gan_b200.generator import MelAudioGenerator
+    gen = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    gen.branch_dropout = 0.0                                   # finetune.py:414
+    gan = GAN(gen, **get_gan_config("gan_multi_scale_mel_recon"))
+    missing, unexpected = gan.load_state_dict(synth_state_dict(g["sd_spec"], g["sd_seed"]), strict=False)
+    assert not unexpected
+    return gan.cuda()
+
+
+@pytest.mark.parametrize("tag,draw", [("limit_on", 0.0), ("limit_off", 0.99)])
+def test_gan_phases_match_reference(tag, draw):
+    g = torch.load(os.path.join(GOLDEN, "ref_gan_24k.pt"), weights_only=False)
+    gan = _gan(g)
+    from flow2gan_b200.modules import LogMelSpectrogram
+    audio, lens = g["audio"].cuda(), g["lens"].cuda()
+    mel = LogMelSpectrogram(24000, 1024, 256, 100).cuda()(audio)
+    assert rel_rms(mel.cpu(), g["mel"]) < 1e-5
+    noise = g["noise"].cuda()
+    rr = random.random
+    random.random = lambda: draw                                # pins limit_param_value (modules.py:267)
+    try:
+        for train_disc, ph, wts in ((True, "d", (1.0, 0.1)), (False, "g", (1.0, 0.1, 1.0, 0.1, 45.0))):
+            gan.zero_grad()
+            losses = gan(cond=mel, audio=audio, audio_lens=lens, n_timesteps=1, train_disc=train_disc,
+                         noise=noise)
+            got = torch.stack([l.detach() for l in losses]).cpu()
+            ref = g[f"{ph}_{tag}_losses"]
+            rel = ((got - ref).abs() / ref.abs()).max()
+            print(ph, tag, "losses", got.tolist(), "max rel", float(rel))
+            assert float(rel) < 2e-3
+            assert gan.discriminator.training == train_disc and gan.generator.training == (not train_disc)
+            sum(l * w for l, w in zip(losses, wts)).backward()
+            sub = gan.discriminator if train_disc else gan.generator
+            pre = "discriminator." if train_disc else "generator."
+            errs = _grad_errors([(pre + k, p) for k, p in sub.named_parameters()], g[f"{ph}_{tag}_grads"])
+            _assert_grads(errs)
+    finally:
+        random.random = rr
