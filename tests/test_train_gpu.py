@@ -6,7 +6,7 @@ Gradient tolerance: the forward pass is TF32 (5e-4 rel-RMS on activations, the p
 gradient through ~40 serial TF32 contractions accumulates that to ~1-2e-2 per tensor, and scalar
 parameters whose gradient is a cancelling sum (BiasNorm log_scale) reach ~6e-2.  Even the fp32
 reference vs the fp32 oracle differ by up to 1e-2 on such tensors (test_oracle_vs_golden.py).
-Gate: worst tensor < 2.5e-1, 90th percentile < 5e-2, median < 2e-2, loss value itself < 2e-3."""
+Gates: see _assert_grads; loss value itself < 2e-3."""
 import os
 
 import pytest
@@ -29,6 +29,7 @@ def _model(name, spec, seed):
 
 
 def _grad_errors(named_params, golden):
+    """per tensor: (relative error, reference l2)."""
     errs = {}
     for k, p in named_params:
         e = golden[k]
@@ -36,22 +37,33 @@ def _grad_errors(named_params, golden):
             continue
         assert p.grad is not None, k
         g = p.grad.detach().float().cpu()
+        if e["l2"] < 1e-6:      # exactly-cancelling gradient in the reference (e.g. hinge conv_post.bias)
+            assert float(g.double().norm()) < 1e-4, (k, float(g.double().norm()))
+            continue
         if "full" in e:
-            err = float((g - e["full"]).double().norm()) / max(e["l2"], 1e-12)
+            err = float((g - e["full"]).double().norm()) / e["l2"]
         else:
             head = g.flatten()[:256]
-            err = max(abs(float(g.double().norm()) - e["l2"]) / max(e["l2"], 1e-12),
+            err = max(abs(float(g.double().norm()) - e["l2"]) / e["l2"],
                       float((head - e["head"]).double().norm() / e["head"].double().norm().clamp_min(1e-12)))
-        errs[k] = err
+        errs[k] = (err, e["l2"])
     return errs
 
 
-def _assert_grads(errs, worst=2.5e-1, p90=5e-2, median=2e-2):
-    v = sorted(errs.values())
-    top = sorted(((e, k) for k, e in errs.items()), reverse=True)[:12]
-    print("grad rel-err: median %.2e  p90 %.2e  max %.2e" % (v[len(v) // 2], v[int(len(v) * 0.9)], v[-1]))
+def _assert_grads(errs, total=3e-2, p90=5e-2, median=2e-2, worst_big=1.5e-1):
+    """errs: name -> (rel err, ref l2).  Gates: the norm-weighted error of the whole gradient
+    vector, the median / 90th percentile over tensors, and the worst tensor among those that carry
+    >= 1 % of the largest tensor norm (tiny cancellation-dominated tensors -- e.g. a time_embed_proj
+    whose gradient is a near-zero sum over frames -- amplify TF32 noise arbitrarily)."""
+    v = sorted(e for e, _ in errs.values())
+    top = sorted(((e, k) for k, (e, _) in errs.items()), reverse=True)[:8]
+    l2max = max(l for _, l in errs.values())
+    tot = (sum((e * l) ** 2 for e, l in errs.values()) / sum(l ** 2 for _, l in errs.values())) ** 0.5
+    big = max(e for e, l in errs.values() if l >= 1e-2 * l2max)
+    print("grad rel-err: whole-vector %.2e  median %.2e  p90 %.2e  max %.2e  max(big tensors) %.2e"
+          % (tot, v[len(v) // 2], v[int(len(v) * 0.9)], v[-1], big))
     print("   worst tensors:", [(k, round(e, 4)) for e, k in top])
-    assert v[-1] < worst, top[:8]
+    assert tot < total and big < worst_big
     assert v[int(len(v) * 0.9)] < p90
     assert v[len(v) // 2] < median
 
@@ -99,8 +111,10 @@ def test_two_step_sampler_grads_vs_oracle_autograd():
     errs = {}
     for k, p in m.named_parameters():
         r = leaves[k].grad
-        errs[k] = float((p.grad.cpu() - r).double().norm() / r.double().norm().clamp_min(1e-12))
-    errs["<noise>"] = float((nz.grad.cpu() - nz_ref.grad).double().norm() / nz_ref.grad.double().norm())
+        errs[k] = (float((p.grad.cpu() - r).double().norm() / r.double().norm().clamp_min(1e-12)),
+                   float(r.double().norm()))
+    errs["<noise>"] = (float((nz.grad.cpu() - nz_ref.grad).double().norm() / nz_ref.grad.double().norm()),
+                       float(nz_ref.grad.double().norm()))
     _assert_grads(errs)
 
 
