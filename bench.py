@@ -153,6 +153,51 @@ def cpu_oracle_rate(n_timesteps: int, iters: int, warmup: int = 1):
     return SAMPLES_PER_STEP * len(times) / tot, tot / len(times) * 1e3, cores
 
 
+def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
+    """GAN fine-tune step pair (D-iteration + G-iteration on bs=16 x 24000 samples per GPU, incl.
+    ScaledAdam updates and, for world > 1, the NCCL gradient all-reduce of the stepped half) --
+    the second half of BASELINE.json's metric (finetune.py:590-626)."""
+    from _cases import audio_input
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.gan import GAN
+    from flow2gan_b200.generator import MelAudioGenerator
+    from flow2gan_b200.trainer import GANTrainer
+    from oracle.synth import synth_state_dict
+    torch.manual_seed(0)
+    gen = MelAudioGenerator(**get_generator_config(MODEL))
+    gen.branch_dropout = 0.0
+    gan = GAN(gen, **get_gan_config("gan_multi_scale_mel_recon"))
+    spec = [(k, tuple(v.shape)) for k, v in gan.state_dict().items()]
+    gan.load_state_dict(synth_state_dict(spec, 4321), strict=False)
+    gan = gan.to(dev)
+    tr = GANTrainer(gan, n_timesteps=n_timesteps)
+    Tt = 24000
+    audio = audio_input(B, Tt, seed=2 + int(os.environ.get("RANK", "0"))).to(dev)
+    lens = torch.full((B,), Tt, device=dev, dtype=torch.int64)
+    torch.manual_seed(1 + int(os.environ.get("RANK", "0")))
+    for _ in range(2):                    # warm-up pair
+        tr.step(audio, lens)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2 * pairs):
+        info = tr.step(audio, lens)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"value": world * 2 * B * Tt * pairs / (ms * 1e-3), "unit": "samples/s", "ms_per_pair": ms / pairs,
+            "pairs": pairs, "n_timesteps": n_timesteps, "global_batch": B * world,
+            "allreduce_bytes_per_pair": 0 if world == 1 else (78949542 + 42503752) * 4,
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "includes": "LogMel front-end, GAN.forward, backward, grad all-reduce (world>1), ScaledAdam.step, Eden2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -277,6 +322,12 @@ def run_ours(args):
                     "peak_source": f"{how}: bf16_tflops (burst; launches are timed one by one)/2 -- TF32 issues at half the bf16 rate",
                     "step_ref_equiv_tflops": REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12 / 1.0}
 
+    train = None
+    if not args.no_train:
+        try:
+            train = gan_train_bench(dev, dist, world, pairs=args.train_pairs, n_timesteps=n)
+        except Exception as e:                       # keep the headline line alive
+            train = {"error": repr(e)[:300]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -298,6 +349,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    if train is not None:
+        line["gan_train"] = train
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": f"{3 if n == 1 else 1} x (bs=16, 1 s) {n}-step calls, {cpu_ms:.0f} ms each"}
@@ -313,6 +366,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-timesteps", type=int, default=1, choices=[1, 2, 4])
+    ap.add_argument("--no-train", action="store_true", help="skip the GAN train-step measurement")
+    ap.add_argument("--train-pairs", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
