@@ -54,7 +54,10 @@ def grad_summary(named_grads, full_numel=4096):
         if g.numel() <= full_numel:
             e["full"] = g.clone()
         else:
-            e["head"] = g.flatten()[:256].clone()
+            # strided sample over the WHOLE tensor (a contiguous head would be one output channel)
+            stride = max(1, g.numel() // 2048)
+            e["stride"] = stride
+            e["sample"] = g.flatten()[::stride][:2048].clone()
         out[k] = e
     return out
 
