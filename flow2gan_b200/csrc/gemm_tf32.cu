@@ -27,14 +27,15 @@ constexpr int UMMA_K = 8;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 36 * 4;
+constexpr int EPI_PARAM_BYTES = 3 * 256 * 4;   // bias / slope / residual scale of one tile
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
 struct TileCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (SMEM_LIMIT - EPI_SCRATCH_BYTES - 2048) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - EPI_SCRATCH_BYTES - EPI_PARAM_BYTES - 2048) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + EPI_PARAM_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -90,7 +91,9 @@ F2G_DEVINL TileCoord decode_tile(const DevGroup& g, int tile) {
   return t;
 }
 
-template <int BN, int A_MN, int B_MN>
+enum { EPI_GENERIC = 0, EPI_BIAS_ACT = 1, EPI_BIAS_RES = 2, EPI_PLAIN = 3 };
+
+template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict__ gmaps) {
   using Cfg = TileCfg<BN>;
@@ -229,11 +232,17 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
     // ------------------------------- epilogue warps -----------------------------------
     // TMEM lane = output row.  Each warp drains its 32 rows in 32-column chunks: tcgen05.ld ->
     // 8 x STS.128 into a padded (stride 36) smem scratch -> re-read as 4 rows x 8 column-quads
-    // per pass so that every LDG/STG is a 128-bit access and a warp instruction covers four
-    // full 128 B row segments; per-column parameters live in registers as float4.
+    // per pass so that every LDG/STG is a 128-bit access and a warp instruction covers four full
+    // 128 B row segments.  Per-column parameters of the tile are staged in smem while the main
+    // loop still runs.  The common epilogues are compile-time specialisations (EPI): with ONE
+    // epilogue warp per SM sub-partition there is no thread-level parallelism to hide a long
+    // branchy dependent chain, so the fast paths are branch-free and issue their 8 LDS.128 /
+    // LDG.128 up front (ncu showed the generic path latency-bound at ~500 cycles per row group).
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     float* const scratch = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES) + (warp - 2) * (32 * 36);
+    float* const sparam = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_SCRATCH_BYTES);
     const int cg = lane & 7, rsub = lane >> 3;
+    const int et = (warp - 2) * 32 + lane;
     int ab = 0;
     uint32_t ab_phase = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -246,15 +255,12 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       const int rows = min(32, pr.M - row_base);
       float* const cbase = pr.c;
       float* const pre_p = pr.c_pre;
-      const float* const bias_p = pr.bias;
-      const float* const slope_p = pr.slope;
       const float* const res_p = pr.res;
-      const float* const rsc_p = pr.res_scale;
       const float* const rowsc_p = pr.row_scale;
       const float* const gate_p = pr.gate;
       const int act = pr.act;
       const bool do_round = pr.round_tf32 != 0, do_acc = pr.accumulate != 0;
-      const float alpha = pr.alpha, leaky = pr.leaky;
+      const float alpha = pr.alpha;
       const bool skip = (g.dbg & 4) != 0;
       // 128-bit global accesses need 16 B aligned rows
       const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
@@ -262,6 +268,22 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       const bool vec_gate = !gate_p || (((ld_gate & 3) == 0) && ((reinterpret_cast<uintptr_t>(gate_p) & 15) == 0));
       const bool vec_pre = !pre_p || (((ld_pre & 3) == 0) && ((reinterpret_cast<uintptr_t>(pre_p) & 15) == 0));
       const bool vec_all = vec_c && vec_res && vec_gate && vec_pre;
+
+      // stage bias / slope / residual-scale of this tile's BN columns (overlaps the main loop)
+      {
+        const float* const bias_p = pr.bias;
+        const float* const slope_p = pr.slope;
+        const float* const rsc_p = pr.res_scale;
+        const float leaky = pr.leaky;
+        for (int c = et; c < BN; c += 128) {
+          const int colc = n0 + c;
+          const bool okc = colc < N;
+          sparam[c] = (bias_p && okc) ? __ldg(bias_p + colc) : 0.f;
+          sparam[BN + c] = (slope_p && okc) ? __ldg(slope_p + colc) : leaky;
+          sparam[2 * BN + c] = (rsc_p && okc) ? __ldg(rsc_p + colc) : 1.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
@@ -280,30 +302,81 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
         __syncwarp();
         const int col = n0 + c0 + 4 * cg;
         const int ncol = min(4, N - col);          // valid columns of this lane's quad (<= 0: none)
-        float bias[4], slope[4], rsc[4];
+        const float4 bias4 = *reinterpret_cast<const float4*>(sparam + c0 + 4 * cg);
+        const float4 slope4 = *reinterpret_cast<const float4*>(sparam + BN + c0 + 4 * cg);
+        const float4 rsc4 = *reinterpret_cast<const float4*>(sparam + 2 * BN + c0 + 4 * cg);
+        const bool chunk_full = vec_all && (n0 + c0 + 32 <= N) && pr.split_k == 1;   // warp-uniform
+
+        if (EPI != EPI_GENERIC && chunk_full) {
+          // ---------------- specialised, branch-free fast paths -------------------------
+          float4 xv[8], rv[8];
+          bool okr[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool okc = e < ncol;
-          bias[e] = (bias_p && okc) ? __ldg(bias_p + col + e) : 0.f;
-          slope[e] = (slope_p && okc) ? __ldg(slope_p + col + e) : leaky;
-          rsc[e] = (rsc_p && okc) ? __ldg(rsc_p + col + e) : 1.f;
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            okr[rr] = i < rows;
+            xv[rr] = *reinterpret_cast<const float4*>(scratch + i * 36 + 4 * cg);
+          }
+          if (EPI == EPI_BIAS_RES) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr)
+              rv[rr] = okr[rr] ? __ldg(reinterpret_cast<const float4*>(
+                                     res_p + (size_t)(row_base + rr * 4 + rsub) * ld_res + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (EPI == EPI_PLAIN && do_acc) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr)
+              rv[rr] = okr[rr] ? *reinterpret_cast<const float4*>(
+                                     cbase + (size_t)(row_base + rr * 4 + rsub) * ldc + col)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            float4 x = xv[rr];
+            x.x = fmaf(x.x, alpha, bias4.x); x.y = fmaf(x.y, alpha, bias4.y);
+            x.z = fmaf(x.z, alpha, bias4.z); x.w = fmaf(x.w, alpha, bias4.w);
+            const size_t row = (size_t)(row_base + rr * 4 + rsub);
+            if (EPI == EPI_BIAS_ACT) {
+              if (pre_p && okr[rr]) *reinterpret_cast<float4*>(pre_p + row * ld_pre + col) = x;
+              x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;
+              x.z = x.z > 0.f ? x.z : x.z * slope4.z; x.w = x.w > 0.f ? x.w : x.w * slope4.w;
+            } else if (EPI == EPI_BIAS_RES) {
+              x.x = fmaf(rsc4.x, rv[rr].x, x.x); x.y = fmaf(rsc4.y, rv[rr].y, x.y);
+              x.z = fmaf(rsc4.z, rv[rr].z, x.z); x.w = fmaf(rsc4.w, rv[rr].w, x.w);
+            } else if (do_acc) {
+              x.x += rv[rr].x; x.y += rv[rr].y; x.z += rv[rr].z; x.w += rv[rr].w;
+            }
+            if (do_round) {
+              x.x = tf32_rna(x.x); x.y = tf32_rna(x.y); x.z = tf32_rna(x.z); x.w = tf32_rna(x.w);
+            }
+            if (okr[rr]) *reinterpret_cast<float4*>(cbase + row * ldc + col) = x;
+          }
+          __syncwarp();
+          continue;
         }
+
+        const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
+        const float slope[4] = {slope4.x, slope4.y, slope4.z, slope4.w};
+        const float rsc[4] = {rsc4.x, rsc4.y, rsc4.z, rsc4.w};
         if (pr.split_k > 1) {   // partial-K tile: atomically accumulate into the pre-zeroed C
 #pragma unroll 1
           for (int rr = 0; rr < 8; ++rr) {
             const int i = rr * 4 + rsub;
             if (i >= rows) continue;
-            for (int e = 0; e < ncol; ++e)
-              atomicAdd(cbase + (size_t)(row_base + i) * ldc + col + e, scratch[i * 36 + 4 * cg + e] * alpha);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < ncol)
+                atomicAdd(cbase + (size_t)(row_base + i) * ldc + col + e, scratch[i * 36 + 4 * cg + e] * alpha);
           }
           __syncwarp();
           continue;
         }
         const bool quad = vec_all && ncol == 4;
-        // Keep this loop COMPACT: a fully unrolled generic epilogue (3.8k SASS instructions) made
-        // the four epilogue warps instruction-fetch bound (ncu: stall_no_inst) -- 18-28 us/tile.
+        // generic path (any epilogue combination, N tails, unaligned leading dimensions); kept
+        // compact on purpose: fully unrolled it was instruction-fetch bound (ncu: stall_no_inst)
         if (quad) {
-#pragma unroll 4
+#pragma unroll 2
           for (int rr = 0; rr < 8; ++rr) {
             const int i = rr * 4 + rsub;
             if (i >= rows) continue;
@@ -350,8 +423,9 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
             const int i = rr * 4 + rsub;
             if (i >= rows) continue;
             const int row = row_base + i;
-#pragma unroll 1
-            for (int e = 0; e < ncol; ++e) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e >= ncol) continue;
               float x = fmaf(scratch[i * 36 + 4 * cg + e], alpha, bias[e]);
               if (pre_p) pre_p[(size_t)row * ld_pre + col + e] = x;
               if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) x = x > 0.f ? x : x * slope[e];
@@ -370,6 +444,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // all warps done with this tile's staged parameters
       ab ^= 1;
       if (ab == 0) ab_phase ^= 1;
     }
@@ -441,11 +516,11 @@ static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64
   return 0;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int EPI>
 static int launch(const DevGroup& g, int num_sms, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
@@ -530,17 +605,42 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   g.mn_lbo = mn_lbo; g.mn_sbo = mn_sbo; g.mn_layout = mn_layout; g.mn_kstep = mn_kstep;
   g.dbg = env_int("F2G_GEMM_DBG", 0);
 
-#define F2G_DISPATCH(BN_)                                                        \
-  if (bn == BN_) {                                                               \
-    if (!a_mn && !b_mn) return launch<BN_, 0, 0>(g, g_num_sms, stream);         \
-    if (!a_mn && b_mn) return launch<BN_, 0, 1>(g, g_num_sms, stream);          \
-    if (a_mn && b_mn) return launch<BN_, 1, 1>(g, g_num_sms, stream);           \
-    if (a_mn && !b_mn) return launch<BN_, 1, 0>(g, g_num_sms, stream);          \
+  // epilogue specialisation shared by the whole group (else the generic epilogue)
+  int epi = -1;
+  for (int i = 0; i < n; ++i) {
+    const F2GGemm& d = descs[i];
+    int e = EPI_GENERIC;
+    const bool odd = d.gate || d.row_scale || d.act == F2G_ACT_SILU;
+    if (!odd && d.bias && (d.act == F2G_ACT_PRELU || d.act == F2G_ACT_LEAKY) && !d.res && !d.accumulate)
+      e = EPI_BIAS_ACT;
+    else if (!odd && d.act == F2G_ACT_NONE && d.res && !d.accumulate && !d.c_pre)
+      e = EPI_BIAS_RES;
+    else if (!odd && d.act == F2G_ACT_NONE && !d.res && !d.bias && !d.c_pre)
+      e = EPI_PLAIN;
+    epi = (epi == -1 || epi == e) ? e : EPI_GENERIC;
+  }
+  static const int force_generic = env_int("F2G_GEMM_GENERIC_EPI", 0);
+  if (force_generic) epi = EPI_GENERIC;
+
+#define F2G_DISPATCH_E(BN_, AM_, BM_)                                                       \
+  {                                                                                         \
+    if (epi == EPI_BIAS_ACT) return launch<BN_, AM_, BM_, EPI_BIAS_ACT>(g, g_num_sms, stream); \
+    if (epi == EPI_BIAS_RES) return launch<BN_, AM_, BM_, EPI_BIAS_RES>(g, g_num_sms, stream); \
+    if (epi == EPI_PLAIN) return launch<BN_, AM_, BM_, EPI_PLAIN>(g, g_num_sms, stream);       \
+    return launch<BN_, AM_, BM_, EPI_GENERIC>(g, g_num_sms, stream);                         \
+  }
+#define F2G_DISPATCH(BN_)                                  \
+  if (bn == BN_) {                                         \
+    if (!a_mn && !b_mn) F2G_DISPATCH_E(BN_, 0, 0)          \
+    if (!a_mn && b_mn) F2G_DISPATCH_E(BN_, 0, 1)           \
+    if (a_mn && b_mn) F2G_DISPATCH_E(BN_, 1, 1)            \
+    if (a_mn && !b_mn) F2G_DISPATCH_E(BN_, 1, 0)           \
   }
   F2G_DISPATCH(64)
   F2G_DISPATCH(128)
   F2G_DISPATCH(256)
 #undef F2G_DISPATCH
+#undef F2G_DISPATCH_E
   set_error("unsupported gemm tile width bn=%d (64/128/256)", bn);
   return F2G_EINVAL;
 }
