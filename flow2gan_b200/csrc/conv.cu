@@ -18,43 +18,69 @@ struct ConvGeom {
   int ldk;                // leading dim of the col matrix (>= kh*kw*C, multiple of 4)
 };
 
+// One warp per output row m = (n, ho, wo): the (n, ho, wo) decomposition is done once per row,
+// lanes stride over K.  VEC: C % 4 == 0 -> 128-bit loads/stores of 4 channels.
+template <bool VEC>
 __global__ void im2col2d_kernel(const float* __restrict__ x, ConvGeom g, float* __restrict__ col,
                                 int round_tf32) {
-  const long long total = (long long)g.Nb * g.Ho * g.Wo * g.ldk;
+  const long long M = (long long)g.Nb * g.Ho * g.Wo;
+  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int wo = (int)(m % g.Wo);
+  const long long t = m / g.Wo;
+  const int ho = (int)(t % g.Ho);
+  const int n = (int)(t / g.Ho);
+  const int h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
+  const float* xb = x + (long long)n * g.pitch_n;
+  float* crow = col + m * g.ldk;
   const int K = g.kh * g.kw * g.C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % g.ldk);
-    const long long m = i / g.ldk;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % g.C;
-      const int tap = k / g.C;
-      const int iw = tap % g.kw, ih = tap / g.kw;
-      const int wo = (int)(m % g.Wo);
-      const long long t = m / g.Wo;
-      const int ho = (int)(t % g.Ho);
-      const int n = (int)(t / g.Ho);
-      const int h = ho * g.sh - g.ph + ih, w = wo * g.sw - g.pw + iw;
-      if (h >= 0 && h < g.H && w >= 0 && w < g.W)
-        v = x[(long long)n * g.pitch_n + (long long)h * g.pitch_h + (long long)w * g.C + c];
+  if (VEC) {
+    const int K4 = K >> 2, C4 = g.C >> 2;
+    for (int kq = lane; kq < (g.ldk >> 2); kq += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kq < K4) {
+        const int tap = kq / C4, c = (kq - tap * C4) << 2;
+        const int ih = tap / g.kw, iw = tap - ih * g.kw;
+        const int h = h0 + ih, w = w0 + iw;
+        if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+          v = *reinterpret_cast<const float4*>(xb + (long long)h * g.pitch_h + (long long)w * g.C + c);
+        if (round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+      }
+      *reinterpret_cast<float4*>(crow + (kq << 2)) = v;
     }
-    col[i] = round_tf32 ? tf32_rna(v) : v;
+  } else {
+    for (int k = lane; k < g.ldk; k += 32) {
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / g.C, c = k - tap * g.C;
+        const int ih = tap / g.kw, iw = tap - ih * g.kw;
+        const int h = h0 + ih, w = w0 + iw;
+        if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+          v = xb[(long long)h * g.pitch_h + (long long)w * g.C + c];
+        if (round_tf32) v = tf32_rna(v);
+      }
+      crow[k] = v;
+    }
   }
 }
 
+// adjoint: one thread per input element (VEC: per 4 channels) gathers every tap that read it
+template <bool VEC>
 __global__ void col2im2d_kernel(const float* __restrict__ dcol, ConvGeom g, float* __restrict__ dx,
                                 int accumulate) {
-  const long long total = (long long)g.Nb * g.H * g.W * g.C;
+  const int CV = VEC ? (g.C >> 2) : g.C;
+  const long long total = (long long)g.Nb * g.H * g.W * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % g.C);
-    long long t = i / g.C;
+    const int cv = (int)(i % CV);
+    long long t = i / CV;
     const int w = (int)(t % g.W);
     t /= g.W;
     const int h = (int)(t % g.H);
     const int n = (int)(t / g.H);
-    float acc = 0.f;
+    const int c = VEC ? (cv << 2) : cv;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ih = 0; ih < g.kh; ++ih) {
       const int hn = h + g.ph - ih;
       if (hn < 0 || hn % g.sh != 0) continue;
@@ -66,11 +92,23 @@ __global__ void col2im2d_kernel(const float* __restrict__ dcol, ConvGeom g, floa
         const int wo = wn / g.sw;
         if (wo >= g.Wo) continue;
         const long long m = ((long long)n * g.Ho + ho) * g.Wo + wo;
-        acc += dcol[m * g.ldk + (ih * g.kw + iw) * g.C + c];
+        const float* src = dcol + m * g.ldk + (ih * g.kw + iw) * g.C + c;
+        if (VEC) {
+          const float4 v = *reinterpret_cast<const float4*>(src);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        } else {
+          acc.x += *src;
+        }
       }
     }
     float* o = dx + (long long)n * g.pitch_n + (long long)h * g.pitch_h + (long long)w * g.C + c;
-    *o = accumulate ? *o + acc : acc;
+    if (VEC) {
+      float4 r = acc;
+      if (accumulate) { const float4 p = *reinterpret_cast<const float4*>(o); r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+      *reinterpret_cast<float4*>(o) = r;
+    } else {
+      *o = accumulate ? *o + acc.x : acc.x;
+    }
   }
 }
 
@@ -129,16 +167,23 @@ static int grid_for(long long total) {
 extern "C" int f2g_im2col2d(const float* x, const F2GConv2d* p, float* col, int round_tf32, void* stream) {
   ConvGeom g;
   if (int rc = fill_geom(g, p)) return rc;
-  const long long total = (long long)g.Nb * g.Ho * g.Wo * g.ldk;
-  im2col2d_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
+  const long long M = (long long)g.Nb * g.Ho * g.Wo;
+  const bool vec = (g.C % 4 == 0) && (g.pitch_h % 4 == 0) && (g.pitch_n % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
+  const unsigned blocks = (unsigned)((M + 7) / 8);
+  if (vec) im2col2d_kernel<true><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
+  else im2col2d_kernel<false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
   return check_launch("f2g_im2col2d");
 }
 
 extern "C" int f2g_col2im2d(const float* dcol, const F2GConv2d* p, float* dx, int accumulate, void* stream) {
   ConvGeom g;
   if (int rc = fill_geom(g, p)) return rc;
-  const long long total = (long long)g.Nb * g.H * g.W * g.C;
-  col2im2d_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
+  const bool vec = (g.C % 4 == 0) && (g.pitch_h % 4 == 0) && (g.pitch_n % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0);
+  const long long total = (long long)g.Nb * g.H * g.W * (vec ? g.C / 4 : g.C);
+  if (vec) col2im2d_kernel<true><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
+  else col2im2d_kernel<false><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
   return check_launch("f2g_col2im2d");
 }
 

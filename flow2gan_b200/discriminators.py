@@ -131,8 +131,20 @@ class MultiPeriodDiscriminator(nn.Module):
                                              for p in periods])
 
     def forward(self, y: Tensor, y_hat: Tensor, bandwidth_id=None, train_weights: bool = True):
-        outs = [d(torch.cat([y, y_hat], 0), train_weights) for d in self.discriminators]
+        return _run_real_fake(self.discriminators, y, y_hat, train_weights)
+
+
+def _run_real_fake(discs, y: Tensor, y_hat: Tensor, train_weights: bool):
+    """D-phase (weights trained): one pass over the concatenated real|fake batch.  G-phase
+    (weights frozen, gradient only w.r.t. y_hat): the real half runs without autograd so no
+    input-gradient work is spent on it (the reference runs d(y), d(y_hat) separately too)."""
+    if train_weights or not y_hat.requires_grad:
+        outs = [d(torch.cat([y, y_hat], 0), train_weights) for d in discs]
         return _split_real_fake(outs, y.shape[0])
+    with torch.no_grad():
+        real = [d(y, False) for d in discs]
+    fake = [d(y_hat, False) for d in discs]
+    return ([s for s, _ in real], [s for s, _ in fake], [f for _, f in real], [f for _, f in fake])
 
 
 def _split_real_fake(outs, B):
@@ -227,5 +239,4 @@ class MultiResolutionDiscriminator(nn.Module):
                                              for w in fft_sizes])
 
     def forward(self, y: Tensor, y_hat: Tensor, bandwidth_id=None, train_weights: bool = True):
-        outs = [d(torch.cat([y, y_hat], 0), train_weights) for d in self.discriminators]
-        return _split_real_fake(outs, y.shape[0])
+        return _run_real_fake(self.discriminators, y, y_hat, train_weights)
