@@ -47,8 +47,14 @@ __global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, in
   }
 }
 
-// Fused ConvNeXt-block prologue, one warp per token (b, t):
+// Fused ConvNeXt-block prologue.  One CTA = PRE_TOK consecutive tokens of one batch element
+// processed CONCURRENTLY (threadIdx.y = token, threadIdx.x = 4-channel group): the 7-row windows
+// of neighbouring tokens overlap and are served by that SM's L1, so L2 sees (PRE_TOK+6)/PRE_TOK
+// reads per row instead of 7 (the one-token-per-CTA version ran at L2 bandwidth, 10 us/launch),
+// while the thread count stays that of the per-token mapping (a serial strip was slower: 14 us).
 //   y = dwconv7(x * mask) + b ; z = BiasNorm(y) + cond_row ; z *= 1 + ts[b] ; out = tf32(z)
+constexpr int PRE_TOK = 4;
+
 __global__ void block_pre_kernel(const float* __restrict__ x, int B, int T, int C, int ld_x,
                                  const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
                                  const float* __restrict__ bn_bias,
@@ -58,68 +64,60 @@ __global__ void block_pre_kernel(const float* __restrict__ x, int B, int T, int 
                                  int factor, int zero_row, const float* __restrict__ tscale,
                                  int ld_ts, float* __restrict__ out, int ld_out,
                                  float* __restrict__ conv_out, float* __restrict__ inv_out) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B * T) return;
-  const int bi = row / T;
-  const int t = row - bi * T;
-  const int chunks = C >> 7;
+  __shared__ float red[PRE_TOK][8];
+  const int bi = blockIdx.y;
+  const int ty = threadIdx.y;
+  const int t = blockIdx.x * PRE_TOK + ty;
+  const bool live = t < T;
+  const int c = threadIdx.x * 4;
+  const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const size_t rb = (size_t)bi * T;
+  const size_t row = rb + t;
 
-  float mk[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int tt = t + k - 3;
-    mk[k] = (tt >= 0 && tt < T) ? (row_mask ? row_mask[bi * T + tt] : 1.f) : 0.f;
-  }
-
-  float4 y[MAX_CHUNKS];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float ssq = 0.f;
+  if (live) {
+    acc = ld4(dw_b + c);
 #pragma unroll
-  for (int j = 0; j < MAX_CHUNKS; ++j) {
-    if (j < chunks) {
-      const int c = j * 128 + lane * 4;
-      float4 acc = ld4(dw_b + c);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        if (mk[k] != 0.f) {
-          const float4 xv = ld4(x + (size_t)(row + k - 3) * ld_x + c);
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t + k - 3;
+      if (tt >= 0 && tt < T) {
+        const float mk = row_mask ? row_mask[rb + tt] : 1.f;
+        if (mk != 0.f) {
+          const float4 xv = ld4(x + (rb + tt) * ld_x + c);
           const float4 w = ld4(dw_wT + k * C + c);
-          acc.x = fmaf(xv.x * mk[k], w.x, acc.x);
-          acc.y = fmaf(xv.y * mk[k], w.y, acc.y);
-          acc.z = fmaf(xv.z * mk[k], w.z, acc.z);
-          acc.w = fmaf(xv.w * mk[k], w.w, acc.w);
+          acc.x = fmaf(xv.x * mk, w.x, acc.x);
+          acc.y = fmaf(xv.y * mk, w.y, acc.y);
+          acc.z = fmaf(xv.z * mk, w.z, acc.z);
+          acc.w = fmaf(xv.w * mk, w.w, acc.w);
         }
       }
-      y[j] = acc;
-      const float4 b = ld4(bn_bias + c);
-      const float d0 = acc.x - b.x, d1 = acc.y - b.y, d2 = acc.z - b.z, d3 = acc.w - b.w;
-      ssq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      if (conv_out) st4(conv_out + (size_t)row * C + c, acc);
     }
+    const float4 bb = ld4(bn_bias + c);
+    const float d0 = acc.x - bb.x, d1 = acc.y - bb.y, d2 = acc.z - bb.z, d3 = acc.w - bb.w;
+    ssq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    if (conv_out) st4(conv_out + row * C + c, acc);
   }
+  // blockDim.x (= C/4) is a multiple of 32, so each warp belongs to exactly one token
   ssq = warp_sum(ssq);
+  if ((threadIdx.x & 31) == 0) red[ty][wid] = ssq;
+  __syncthreads();
+  if (!live) return;
+  ssq = 0.f;
+  for (int j = 0; j < nw; ++j) ssq += red[ty][j];
   const float inv = (1.0f / sqrtf(ssq / (float)C)) * expf(*bn_log_scale);
-  if (inv_out && lane == 0) inv_out[row] = inv;
-
-  int crow = zero_row;
-  if (cond && t < cond_T * factor) crow = bi * cond_T + t / factor;
-#pragma unroll
-  for (int j = 0; j < MAX_CHUNKS; ++j) {
-    if (j < chunks) {
-      const int c = j * 128 + lane * 4;
-      float4 z = make_float4(y[j].x * inv, y[j].y * inv, y[j].z * inv, y[j].w * inv);
-      if (cond) {
-        const float4 cv = ld4(cond + (size_t)crow * ld_cond + c);
-        z.x += cv.x; z.y += cv.y; z.z += cv.z; z.w += cv.w;
-      }
-      if (tscale) {
-        const float4 s = ld4(tscale + (size_t)bi * ld_ts + c);
-        z.x *= 1.f + s.x; z.y *= 1.f + s.y; z.z *= 1.f + s.z; z.w *= 1.f + s.w;
-      }
-      st4(out + (size_t)row * ld_out + c,
-          make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
-    }
+  if (inv_out && threadIdx.x == 0) inv_out[row] = inv;
+  float4 z = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  if (cond) {
+    const int crow = t < cond_T * factor ? bi * cond_T + t / factor : zero_row;
+    const float4 cv = ld4(cond + (size_t)crow * ld_cond + c);
+    z.x += cv.x; z.y += cv.y; z.z += cv.z; z.w += cv.w;
   }
+  if (tscale) {
+    const float4 sc = ld4(tscale + (size_t)bi * ld_ts + c);
+    z.x *= 1.f + sc.x; z.y *= 1.f + sc.y; z.z *= 1.f + sc.z; z.w *= 1.f + sc.w;
+  }
+  st4(out + row * ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
 }
 
 // Batched small dense layers (up to 4 independent problems per launch, blockIdx.y = problem):
@@ -252,9 +250,9 @@ extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, cons
                              int ld_out, float* conv_out, float* inv_rms_out, void* stream) {
   if (int rc = check_channels("f2g_block_pre", C, ld_x | ld_out | (cond ? ld_cond : 0) | (tscale ? ld_ts : 0)))
     return rc;
-  const int wpb = 4;
-  const int rows = B * T;
-  block_pre_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  dim3 grid((T + PRE_TOK - 1) / PRE_TOK, B);
+  dim3 block(C / 4, PRE_TOK);
+  block_pre_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       x, B, T, C, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
       factor < 1 ? 1 : factor, zero_row, tscale, ld_ts, out, ld_out, conv_out, inv_rms_out);
   return check_launch("f2g_block_pre");

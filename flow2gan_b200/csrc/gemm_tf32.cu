@@ -30,10 +30,15 @@ constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 36 * 4;
 constexpr int EPI_PARAM_BYTES = 3 * 256 * 4;   // bias / slope / residual scale of one tile
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// A pipeline stage holds KATOMS 32-wide K slices (one 128B-swizzle atom each).  With BN <= 128 the
+// four MMAs of one slice (256 tensor cycles) are shorter than the issue + barrier round trip
+// (~375 cycles measured), so two slices share a stage / barrier; BN = 256 keeps one (smem).
 template <int BN>
 struct TileCfg {
+  static constexpr int KATOMS = BN <= 128 ? 2 : 1;
+  static constexpr int BK_STAGE = BK * KATOMS;
   static constexpr int B_TILE_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGE_BYTES = KATOMS * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int STAGES = (SMEM_LIMIT - EPI_SCRATCH_BYTES - EPI_PARAM_BYTES - 2048) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SCRATCH_BYTES + EPI_PARAM_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -151,8 +156,8 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
         const int n0 = tc.n0 * BN;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + A_TILE_BYTES;
+          uint8_t* sa0 = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb0 = sa0 + Cfg::KATOMS * A_TILE_BYTES;
           if (g.dbg & 2) {
             mbar_arrive(&full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -161,19 +166,25 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const CUtensorMap* ma = gmaps ? &gmaps->p[tc.prob].map_a : &pr.map_a;
           const CUtensorMap* mb = gmaps ? &gmaps->p[tc.prob].map_b : &pr.map_b;
-          if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j)
-              tma_load_2d(sa + j * 4096, ma, &full_bar[stage], tc.m0 + 32 * j, kb * BK);
-          } else {
-            tma_load_2d(sa, ma, &full_bar[stage], kb * BK, tc.m0);
-          }
-          if (B_MN) {
+          for (int at = 0; at < Cfg::KATOMS; ++at) {
+            uint8_t* sa = sa0 + at * A_TILE_BYTES;
+            uint8_t* sb = sb0 + at * Cfg::B_TILE_BYTES;
+            const int kc = kb * Cfg::BK_STAGE + at * BK;      // beyond K: TMA zero-fills the slice
+            if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d(sb + j * 4096, mb, &full_bar[stage], n0 + 32 * j, kb * BK);
-          } else {
-            tma_load_2d(sb, mb, &full_bar[stage], kb * BK, n0);
+              for (int j = 0; j < BM / 32; ++j)
+                tma_load_2d(sa + j * 4096, ma, &full_bar[stage], tc.m0 + 32 * j, kc);
+            } else {
+              tma_load_2d(sa, ma, &full_bar[stage], kc, tc.m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j)
+                tma_load_2d(sb + j * 4096, mb, &full_bar[stage], n0 + 32 * j, kc);
+            } else {
+              tma_load_2d(sb, mb, &full_bar[stage], kc, n0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -186,7 +197,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
     // ------------------------------- MMA issuer ---------------------------------------
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
-      const uint32_t a_addr0 = smem_u32(smem), b_addr0 = a_addr0 + A_TILE_BYTES;
+      const uint32_t a_addr0 = smem_u32(smem), b_addr0 = a_addr0 + Cfg::KATOMS * A_TILE_BYTES;
       const uint64_t adesc0 = A_MN ? make_smem_desc(a_addr0, g.mn_lbo, g.mn_sbo, g.mn_layout)
                                    : make_smem_desc_sw128(a_addr0, 16, 1024);
       const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr0, g.mn_lbo, g.mn_sbo, g.mn_layout)
@@ -212,10 +223,13 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           // atoms -> +1024 B; 32-wide MN blocks (one TMA box each) are 4096 B apart.
           const uint32_t soff = (uint32_t)(stage * Cfg::STAGE_BYTES) >> 4;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = adesc0 + soff + (uint32_t)((k * a_kstep) >> 4);
-            const uint64_t bdesc = bdesc0 + soff + (uint32_t)((k * b_kstep) >> 4);
-            if (!dbg_no_mma) umma_tf32(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
+          for (int at = 0; at < Cfg::KATOMS; ++at) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = adesc0 + soff + (uint32_t)((at * A_TILE_BYTES + k * a_kstep) >> 4);
+              const uint64_t bdesc = bdesc0 + soff + (uint32_t)((at * Cfg::B_TILE_BYTES + k * b_kstep) >> 4);
+              if (!dbg_no_mma) umma_tf32(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || at || k) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -320,7 +334,7 @@ gemm_tf32_kernel(const __grid_constant__ DevGroup g, const DevGroup* __restrict_
           if (EPI == EPI_BIAS_RES) {
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr)
-              rv[rr] = okr[rr] ? __ldg(reinterpret_cast<const float4*>(
+              rv[rr] = (okr[rr] && res_p) ? __ldg(reinterpret_cast<const float4*>(
                                      res_p + (size_t)(row_base + rr * 4 + rsub) * ld_res + col))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -587,7 +601,8 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     p.tile_begin = tiles;
     p.act = d.act; p.round_tf32 = d.round_tf32; p.accumulate = d.accumulate;
     p.leaky = d.leaky; p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
-    p.kb_total = (d.K + BK - 1) / BK;
+    const int bk_stage = bn <= 128 ? 2 * BK : BK;
+    p.kb_total = (d.K + bk_stage - 1) / bk_stage;
     int sk = d.split_k < 1 ? 1 : d.split_k;
     if (sk > p.kb_total) sk = p.kb_total;
     p.kb_per = (p.kb_total + sk - 1) / sk;
@@ -613,8 +628,8 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     const bool odd = d.gate || d.row_scale || d.act == F2G_ACT_SILU;
     if (!odd && d.bias && (d.act == F2G_ACT_PRELU || d.act == F2G_ACT_LEAKY) && !d.res && !d.accumulate)
       e = EPI_BIAS_ACT;
-    else if (!odd && d.act == F2G_ACT_NONE && d.res && !d.accumulate && !d.c_pre)
-      e = EPI_BIAS_RES;
+    else if (!odd && d.act == F2G_ACT_NONE && (d.res || d.bias) && !d.accumulate && !d.c_pre)
+      e = EPI_BIAS_RES;            // bias [+ scaled residual]
     else if (!odd && d.act == F2G_ACT_NONE && !d.res && !d.bias && !d.c_pre)
       e = EPI_PLAIN;
     epi = (epi == -1 || epi == e) ? e : EPI_GENERIC;

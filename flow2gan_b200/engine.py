@@ -23,7 +23,7 @@ from . import _lib as L
 
 import os
 
-BN_G1 = int(os.environ.get("F2G_BN1", "256"))   # N tile of pwconv1-like GEMMs (wide N)
+BN_G1 = int(os.environ.get("F2G_BN1", "128"))   # N tile of pwconv1-like GEMMs (wide N)
 BN_G2 = int(os.environ.get("F2G_BN2", "128"))   # N tile of pwconv2-like GEMMs (N = channels)
 
 
@@ -31,12 +31,14 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
-def _params_signature(model: torch.nn.Module) -> Tuple[int, int]:
-    v, p0 = 0, 0
-    for p in model.parameters():
+def _params_signature(plist) -> Tuple[int, int]:
+    """Cheap change detector over a cached parameter list: in-place updates (optimizer steps,
+    load_state_dict) bump tensor versions; storage moves go through Module._apply, which drops
+    the packed weights altogether.  (Walking model.parameters() each call cost 0.5 ms.)"""
+    v = 0
+    for p in plist:
         v += p._version
-        p0 ^= p.data_ptr()
-    return v, p0
+    return v, plist[0].data_ptr()
 
 
 def _pack(src: Tensor, rows: int, cols: int, rs: int, cs: int, ld: int, rnd: int = 1,
@@ -72,10 +74,11 @@ class PackedGenerator:
         self.refresh()
 
     def stale(self) -> bool:
-        return _params_signature(self.model) != self.signature
+        return _params_signature(self._plist) != self.signature
 
     def refresh(self) -> None:
         m = self.model
+        self._plist = list(m.parameters())
         with torch.no_grad():
             ce = m.cond_encoder
             nm = ce.cond_dim
@@ -119,7 +122,7 @@ class PackedGenerator:
                     br.bte[i * C:(i + 1) * C].copy_(blk.time_embed_proj.bias.detach())
                 br.blocks = [_BlockW(b) for b in d.blocks]
                 self.branches.append(br)
-        self.signature = _params_signature(m)
+        self.signature = _params_signature(self._plist)
 
 
 def _g1(bw: _BlockW, a, h, M, bn=None):
@@ -159,7 +162,7 @@ class InferencePlan:
         self.lens = torch.zeros(B, device=dev, dtype=torch.int32)
         self.freqs = model.estimators[0].decoder.time_embed.freqs(dev)
         self.te_dim = model.estimators[0].decoder.time_embed.dim
-        self.emb = z(B, self.te_dim)
+        self.emb = z(1, self.te_dim)
         self.br = []
         for bw in packed.branches:
             w = type("BranchWS", (), {})()
@@ -171,9 +174,11 @@ class InferencePlan:
             w.h = z(w.R, bw.blocks[0].H)
             w.pout = z(w.R, bw.ldp)
             w.fr = z(w.R, bw.n_fft)
-            w.te1 = z(B, bw.dec.time_mlp[0].weight.shape[0])
-            w.te2 = z(B, bw.te)
-            w.ts = z(B, bw.nl * bw.C)
+            # the sampler evaluates every batch element at the same t (generator.py:260): the time
+            # path is computed for ONE row and broadcast (row stride 0) to the block prologue
+            w.te1 = z(1, bw.dec.time_mlp[0].weight.shape[0])
+            w.te2 = z(1, bw.te)
+            w.ts = z(1, bw.nl * bw.C)
             w.cm_h = z(self.Rc, bw.ch)
             w.c1 = z(self.Rc, bw.cc)
             w.cp = z(self.Rc, bw.nl * bw.C)
@@ -236,7 +241,7 @@ class InferencePlan:
                       for bw, w in zip(pk.branches, self.br)])
         for bw, w in zip(pk.branches, self.br):
             L.biasnorm(w.x, w.R, bw.C, bw.C, bw.dec.in_norm.bias, bw.dec.in_norm.log_scale, w.x, bw.C)
-        L.time_sinusoid(t_dev, B, self.te_dim, self.freqs, 1000.0, self.emb)
+        L.time_sinusoid(t_dev, 1, self.te_dim, self.freqs, 1000.0, self.emb)
         prob1, prob2, prob3 = [], [], []
         for bw, w in zip(pk.branches, self.br):
             tm = bw.dec.time_mlp
@@ -244,9 +249,9 @@ class InferencePlan:
             prob1.append((self.emb, bw.te, self.te_dim, tm[0].weight, bw.te, tm[0].bias, H, w.te1, H))
             prob2.append((w.te1, H, H, tm[2].weight, H, tm[2].bias, bw.te, w.te2, bw.te))
             prob3.append((w.te2, bw.te, bw.te, bw.Wte, bw.te, bw.bte, bw.nl * bw.C, w.ts, bw.nl * bw.C))
-        L.linear_small_group(prob1, B, L.ACT_SILU)
-        L.linear_small_group(prob2, B, L.ACT_NONE)
-        L.linear_small_group(prob3, B, L.ACT_NONE)
+        L.linear_small_group(prob1, 1, L.ACT_SILU)
+        L.linear_small_group(prob2, 1, L.ACT_NONE)
+        L.linear_small_group(prob3, 1, L.ACT_NONE)
         nl = pk.branches[0].nl
         for i in range(nl):
             for bw, w in zip(pk.branches, self.br):
@@ -255,7 +260,7 @@ class InferencePlan:
                 ldc = bw.nl * bw.C
                 L.block_pre(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
                             b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm, bw.factor,
-                            B * Fm, w.ts[:, i * bw.C:], ldc, w.a1, bw.C)
+                            B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C)
             L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
             L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1))
                           for bw, w in zip(pk.branches, self.br)])
