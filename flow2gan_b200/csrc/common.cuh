@@ -29,6 +29,13 @@ F2G_DEVINL float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// Same rounding (nearest, ties away from zero) for finite inputs in two integer instructions;
+// cvt.rna.tf32.f32 expands to a 4-5 instruction sequence with an Inf/NaN guard.  Inf/NaN inputs
+// are not preserved -- only used on GEMM epilogue outputs.
+F2G_DEVINL float tf32_rna_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 F2G_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

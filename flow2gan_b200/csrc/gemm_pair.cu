@@ -1,0 +1,731 @@
+// CTA-pair (cta_group::2) grouped, persistent TF32 GEMM: 256 x BN output tiles on two SMs.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )          fp32 in HBM, TF32 operands, fp32 accumulate
+//
+// Why a pair: with fp32-container operands a 128x128 single-CTA tile moves 128 B of operands per
+// tensor cycle through the L2->SM fabric (32 FLOP/B); measured on B200 the chip sustains about
+// 10 TB/s there, which capped the one-CTA kernel (gemm_tf32.cu) at ~300 TF/s.  A CTA pair shares
+// one 256-row MMA: each CTA stages its own 128 rows of A and only HALF of the B tile, so a
+// 256x256 tile needs 64 B per tensor cycle per SM (64 FLOP/B).
+//
+// Same call sites as gemm_tf32.cu (every 1x1 conv / Linear of flow2gan/models/modules.py:443-451,
+// 563-593 and the Conv2d contractions of flow2gan/models/discriminators.py:65-76,171-184).
+//
+// Roles per CTA (320 threads): warp 0 = TMA producer (both CTAs; all complete_tx land on the
+// LEADER's full barrier), warp 1 = MMA issuer (leader CTA only, tcgen05.mma.cta_group::2, commits
+// multicast to both CTAs), warps 2-9 = epilogue (two warps per TMEM lane quarter, alternating
+// 32-column chunks).  TMEM: two 256-column accumulator buffers per CTA, so the epilogue of tile i
+// overlaps the main loop of tile i+1.  BN is chosen per problem (32..256, multiple of 32).
+#include "common.cuh"
+#include "gemm_tf32.h"
+
+#include <stdlib.h>
+
+namespace f2g {
+
+constexpr int PBM = 128;                       // rows per CTA (pair tile = 256 rows)
+constexpr int PBK = 32;                        // 32 fp32 = one 128 B swizzle row
+constexpr int P_A_BYTES = PBM * PBK * 4;       // 16 KB
+constexpr int P_STAGE_BYTES = 2 * P_A_BYTES;   // A + up to 128 B-tile rows
+constexpr int P_STAGES = 5;
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 36 * 4;
+constexpr int P_PARAM_BYTES = 3 * 256 * 4;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + P_PARAM_BYTES;
+constexpr int P_TMEM_COLS = 512;
+
+struct alignas(64) PProblem {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  float* c;
+  float* c_pre;
+  const float* bias;
+  const float* slope;
+  const float* res;
+  const float* res_scale;
+  const float* row_scale;
+  const float* gate;
+  int ldc, ld_res, ld_gate, ld_pre;
+  int M, N, K, bn;
+  int m_tiles, n_tiles, tile_begin;
+  int split_k, kb_total, kb_per;
+  int act, round_tf32, accumulate;
+  float leaky, alpha;
+};
+
+struct alignas(64) PGroup {
+  PProblem p[F2G_GEMM_MAX_PROBLEMS];
+  int n_problems;
+  int total_tiles;
+  int dbg;   // bring-up (F2G_PAIR_DBG): bit0 = epilogue drains TMEM but stores nothing,
+             // bit1 = epilogue skips TMEM loads too
+};
+
+struct PTile {
+  int prob, m0, n0, kb0, kb1;
+};
+
+F2G_DEVINL PTile pdecode(const PGroup& g, int tile) {
+  int pi = 0;
+#pragma unroll 1
+  for (int i = 1; i < g.n_problems; ++i)
+    if (tile >= g.p[i].tile_begin) pi = i;
+  int local = tile - g.p[pi].tile_begin;
+  const int nt = g.p[pi].n_tiles;
+  const int mn = nt * g.p[pi].m_tiles;
+  const int ks = local / mn;
+  local -= ks * mn;
+  PTile t;
+  t.prob = pi;
+  t.m0 = (local / nt) * (2 * PBM);
+  t.n0 = (local % nt) * g.p[pi].bn;
+  t.kb0 = ks * g.p[pi].kb_per;
+  t.kb1 = min(t.kb0 + g.p[pi].kb_per, g.p[pi].kb_total);
+  return t;
+}
+
+// ------------------------------- cluster / cta_group::2 PTX ---------------------------------
+F2G_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+F2G_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+F2G_DEVINL uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Default (.release.cta) semantics on purpose: a cluster-scope release compiles to MEMBAR.ALL.GPU,
+// which made every epilogue warp wait for all of its global stores once per tile (ncu: 7 % of
+// the samples).  The only thing this arrive orders is the warp's tcgen05.ld traffic, which is
+// fenced by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+F2G_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are credited to an mbarrier of the pair's leader CTA
+F2G_DEVINL void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+F2G_DEVINL void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+F2G_DEVINL void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+F2G_DEVINL void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+F2G_DEVINL void umma_tf32_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs
+F2G_DEVINL void umma_commit_cg2(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+enum { PEPI_GENERIC = 0, PEPI_BIAS_ACT = 1, PEPI_BIAS_RES = 2, PEPI_PLAIN = 3 };
+
+// Fast epilogue of one 32x32 chunk, after the transpose through `scratch`: this lane owns the
+// column quad `col` of rows rsub, rsub+4, ..., rsub+28.  Straight-line on purpose (one epilogue
+// warp or two per SM sub-partition: nothing hides a dependent chain or a branch): all eight
+// LDS.128 / LDG.128 are issued up front, rounding is a mask instead of a branch, the optional
+// pre-activation store is its own pass.  FULL = all 32 rows valid (no predicates at all).
+//   x = alpha*acc + bias ; BIAS_ACT: [pre = x] x = prelu(x) ; BIAS_RES: x += rsc * res ;
+//   PLAIN: x += C (if rp) ; x = tf32(x) if asked ; C = x
+template <int EPI, bool FULL>
+F2G_DEVINL void epi_fast_chunk(const float* __restrict__ sl, float* __restrict__ cp, size_t cstep,
+                               const float* __restrict__ rp, size_t rstep, float* __restrict__ pp,
+                               size_t pstep, int rows_left, float alpha, float4 bias4, float4 slope4,
+                               float4 rsc4, uint32_t radd, uint32_t rmask) {
+  float4 xv[8], rv[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) xv[rr] = *reinterpret_cast<const float4*>(sl + rr * (4 * 36));
+  if (EPI != PEPI_BIAS_ACT) {
+    if (rp) {
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr)
+        rv[rr] = (FULL || rr * 4 < rows_left) ? *reinterpret_cast<const float4*>(rp + rr * rstep)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    xv[rr].x = fmaf(xv[rr].x, alpha, bias4.x); xv[rr].y = fmaf(xv[rr].y, alpha, bias4.y);
+    xv[rr].z = fmaf(xv[rr].z, alpha, bias4.z); xv[rr].w = fmaf(xv[rr].w, alpha, bias4.w);
+  }
+  if (EPI == PEPI_BIAS_ACT) {
+    if (pp) {
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr)
+        if (FULL || rr * 4 < rows_left) *reinterpret_cast<float4*>(pp + rr * pstep) = xv[rr];
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    float4 x = xv[rr];
+    if (EPI == PEPI_BIAS_ACT) {
+      x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;
+      x.z = x.z > 0.f ? x.z : x.z * slope4.z; x.w = x.w > 0.f ? x.w : x.w * slope4.w;
+    } else if (EPI == PEPI_BIAS_RES) {
+      x.x = fmaf(rsc4.x, rv[rr].x, x.x); x.y = fmaf(rsc4.y, rv[rr].y, x.y);
+      x.z = fmaf(rsc4.z, rv[rr].z, x.z); x.w = fmaf(rsc4.w, rv[rr].w, x.w);
+    } else {
+      x.x += rv[rr].x; x.y += rv[rr].y; x.z += rv[rr].z; x.w += rv[rr].w;
+    }
+    x.x = __uint_as_float((__float_as_uint(x.x) + radd) & rmask);
+    x.y = __uint_as_float((__float_as_uint(x.y) + radd) & rmask);
+    x.z = __uint_as_float((__float_as_uint(x.z) + radd) & rmask);
+    x.w = __uint_as_float((__float_as_uint(x.w) + radd) & rmask);
+    if (FULL || rr * 4 < rows_left) *reinterpret_cast<float4*>(cp + rr * cstep) = x;
+  }
+}
+
+template <int A_MN, int B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ PGroup g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("f2g gemm_pair: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
+  __shared__ __align__(8) uint64_t full_bar[P_STAGES];     // used in the leader CTA only
+  __shared__ __align__(8) uint64_t empty_bar[P_STAGES];    // per CTA, multicast commit
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];       // per CTA, multicast commit
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader CTA only, 16 arrivals
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.n_problems; ++i) {
+      tma_prefetch_desc(&g.p[i].map_a);
+      tma_prefetch_desc(&g.p[i].map_b);
+    }
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * P_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(&tmem_base_smem, P_TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) --------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+        const PTile tc = pdecode(g, tile);
+        const PProblem& pr = g.p[tc.prob];
+        const int bhalf = pr.bn >> 1;
+        const int m_cta = tc.m0 + (int)rank * PBM;
+        const int n_cta = tc.n0 + (int)rank * bhalf;
+        const uint32_t stage_tx = 2u * (uint32_t)(P_A_BYTES + bhalf * PBK * 4);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + P_A_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          const int kc = kb * PBK;                      // beyond K: TMA zero-fills
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < PBM / 32; ++j)
+              tma_load_2d_cg2(sa + j * 4096, &pr.map_a, lbar, m_cta + 32 * j, kc);
+          } else {
+            tma_load_2d_cg2(sa, &pr.map_a, lbar, kc, m_cta);
+          }
+          if (B_MN) {
+            for (int j = 0; j < (bhalf >> 5); ++j)
+              tma_load_2d_cg2(sb + j * 4096, &pr.map_b, lbar, n_cta + 32 * j, kc);
+          } else {
+            tma_load_2d_cg2(sb, &pr.map_b, lbar, kc, n_cta);
+          }
+          if (++stage == P_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) ----------------------
+    if (rank == 0 && elect_one()) {
+      const uint32_t a_addr0 = smem_u32(smem), b_addr0 = a_addr0 + P_A_BYTES;
+      // MN-major TF32 operands: SWIZZLE_128B_BASE32B, 32-wide MN blocks 4096 B apart (LBO),
+      // 4-row swizzle atoms 512 B apart (SBO), one k-step (8 rows) = 1024 B  (see gemm_tf32.cu)
+      const uint64_t adesc0 = A_MN ? make_smem_desc(a_addr0, 4096, 512, 1) : make_smem_desc_sw128(a_addr0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr0, 4096, 512, 1) : make_smem_desc_sw128(b_addr0, 16, 1024);
+      constexpr int a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int ab = 0;
+      uint32_t ab_phase = 0;
+      for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+        const PTile tc = pdecode(g, tile);
+        const uint32_t idesc = make_idesc_tf32(2 * PBM, g.p[tc.prob].bn, A_MN, B_MN);
+        mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + ab * 256;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t soff = (uint32_t)(stage * P_STAGE_BYTES) >> 4;
+#pragma unroll
+          for (int k = 0; k < PBK / 8; ++k) {
+            const uint64_t adesc = adesc0 + soff + (uint32_t)((k * a_kstep) >> 4);
+            const uint64_t bdesc = bdesc0 + soff + (uint32_t)((k * b_kstep) >> 4);
+            umma_tf32_cg2(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
+          }
+          umma_commit_cg2(&empty_bar[stage]);     // frees this smem slot in both CTAs
+          if (++stage == P_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_cg2(&tmem_full_bar[ab]);      // accumulator complete -> both epilogues
+        ab ^= 1;
+        if (ab == 0) ab_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps (both CTAs) ------------------------
+    // TMEM lane = output row of this CTA's 128-row half.  Warps (q, half) drain lanes
+    // [32q, 32q+32) in 32-column chunks c0 = 32*(2i + half): tcgen05.ld -> 8 x STS.128 into a
+    // padded scratch -> re-read as 4 rows x 8 column-quads so every LDG/STG is 128-bit and one
+    // warp instruction covers four full 128 B row segments.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    float* const scratch = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES) + ew * (32 * 36);
+    float* const sparam = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES);
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int et = ew * 32 + lane;
+    const uint32_t lead_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t lead_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    int ab = 0;
+    uint32_t ab_phase = 0;
+    for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+      const PTile tc = pdecode(g, tile);
+      const PProblem& pr = g.p[tc.prob];
+      const int BN = pr.bn;
+      const int n0 = tc.n0;
+      const int row_base = tc.m0 + (int)rank * PBM + q * 32;
+      const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate, ld_pre = pr.ld_pre;
+      const int rows = min(32, pr.M - row_base);
+      float* const cbase = pr.c;
+      float* const pre_p = pr.c_pre;
+      const float* const res_p = pr.res;
+      const float* const rowsc_p = pr.row_scale;
+      const float* const gate_p = pr.gate;
+      const int act = pr.act;
+      const bool do_round = pr.round_tf32 != 0, do_acc = pr.accumulate != 0;
+      const float alpha = pr.alpha;
+      const int split_k = pr.split_k;
+      const uint32_t radd = do_round ? 0x1000u : 0u, rmask = do_round ? 0xffffe000u : 0xffffffffu;
+      const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
+      const bool vec_res = !res_p || (((ld_res & 3) == 0) && ((reinterpret_cast<uintptr_t>(res_p) & 15) == 0));
+      const bool vec_gate = !gate_p || (((ld_gate & 3) == 0) && ((reinterpret_cast<uintptr_t>(gate_p) & 15) == 0));
+      const bool vec_pre = !pre_p || (((ld_pre & 3) == 0) && ((reinterpret_cast<uintptr_t>(pre_p) & 15) == 0));
+      const bool vec_all = vec_c && vec_res && vec_gate && vec_pre;
+
+      // stage bias / slope / residual-scale of this tile's BN columns (overlaps the main loop)
+      {
+        const float* const bias_p = pr.bias;
+        const float* const slope_p = pr.slope;
+        const float* const rsc_p = pr.res_scale;
+        const float leaky = pr.leaky;
+        for (int c = et; c < BN; c += 32 * P_EPI_WARPS) {
+          const int colc = n0 + c;
+          const bool okc = colc < N;
+          sparam[c] = (bias_p && okc) ? __ldg(bias_p + colc) : 0.f;
+          sparam[256 + c] = (slope_p && okc) ? __ldg(slope_p + colc) : leaky;
+          sparam[512 + c] = (rsc_p && okc) ? __ldg(rsc_p + colc) : 1.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+
+      mbar_wait(&tmem_full_bar[ab], ab_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= N || (g.dbg & 2)) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * 256 + c0, v);
+        tmem_ld_wait();
+        if (rows <= 0 || (g.dbg & 1)) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(scratch + lane * 36 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + 4 * cg;
+        const int ncol = min(4, N - col);
+        const float4 bias4 = *reinterpret_cast<const float4*>(sparam + c0 + 4 * cg);
+        const float4 slope4 = *reinterpret_cast<const float4*>(sparam + 256 + c0 + 4 * cg);
+        const float4 rsc4 = *reinterpret_cast<const float4*>(sparam + 512 + c0 + 4 * cg);
+        const bool chunk_full = vec_all && (n0 + c0 + 32 <= N) && split_k == 1;   // warp-uniform
+
+        if (EPI != PEPI_GENERIC && chunk_full) {
+          const size_t r0 = (size_t)(row_base + rsub);
+          const float* sl = scratch + rsub * 36 + 4 * cg;
+          float* cp = cbase + r0 * ldc + col;
+          const float* rp = EPI == PEPI_BIAS_RES ? (res_p ? res_p + r0 * ld_res + col : nullptr)
+                                                 : ((EPI == PEPI_PLAIN && do_acc) ? cp : nullptr);
+          float* pp = (EPI == PEPI_BIAS_ACT && pre_p) ? pre_p + r0 * ld_pre + col : nullptr;
+          const size_t rstep = EPI == PEPI_BIAS_RES ? (size_t)4 * ld_res : (size_t)4 * ldc;
+          if (rows >= 32)
+            epi_fast_chunk<EPI, true>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre, 32, alpha,
+                                      bias4, slope4, rsc4, radd, rmask);
+          else
+            epi_fast_chunk<EPI, false>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre,
+                                       rows - rsub, alpha, bias4, slope4, rsc4, radd, rmask);
+          __syncwarp();
+          continue;
+        }
+
+        const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
+        const float slope[4] = {slope4.x, slope4.y, slope4.z, slope4.w};
+        const float rsc[4] = {rsc4.x, rsc4.y, rsc4.z, rsc4.w};
+        if (split_k > 1) {   // partial-K tile: atomically accumulate into the pre-zeroed C
+#pragma unroll 1
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < ncol)
+                atomicAdd(cbase + (size_t)(row_base + i) * ldc + col + e, scratch[i * 36 + 4 * cg + e] * alpha);
+          }
+          __syncwarp();
+          continue;
+        }
+        const bool quad = vec_all && ncol == 4;
+        if (quad) {
+#pragma unroll 2
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+            const int row = row_base + i;
+            const float4 xq = *reinterpret_cast<const float4*>(scratch + i * 36 + 4 * cg);
+            float x[4] = {fmaf(xq.x, alpha, bias[0]), fmaf(xq.y, alpha, bias[1]), fmaf(xq.z, alpha, bias[2]),
+                          fmaf(xq.w, alpha, bias[3])};
+            if (pre_p)
+              *reinterpret_cast<float4*>(pre_p + (size_t)row * ld_pre + col) = make_float4(x[0], x[1], x[2], x[3]);
+            if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * slope[e];
+            } else if (act == F2G_ACT_SILU) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = x[e] / (1.f + __expf(-x[e]));
+            }
+            if (gate_p) {  // multiply by d(act)/dz evaluated at a saved pre-activation
+              const float4 t = __ldg(reinterpret_cast<const float4*>(gate_p + (size_t)row * ld_gate + col));
+              x[0] *= (t.x > 0.f ? 1.f : slope[0]); x[1] *= (t.y > 0.f ? 1.f : slope[1]);
+              x[2] *= (t.z > 0.f ? 1.f : slope[2]); x[3] *= (t.w > 0.f ? 1.f : slope[3]);
+            }
+            if (res_p) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(res_p + (size_t)row * ld_res + col));
+              x[0] = fmaf(rsc[0], t.x, x[0]); x[1] = fmaf(rsc[1], t.y, x[1]);
+              x[2] = fmaf(rsc[2], t.z, x[2]); x[3] = fmaf(rsc[3], t.w, x[3]);
+            }
+            if (rowsc_p) {
+              const float rs = __ldg(rowsc_p + row);
+              x[0] *= rs; x[1] *= rs; x[2] *= rs; x[3] *= rs;
+            }
+            float* dst = cbase + (size_t)row * ldc + col;
+            if (do_acc) {
+              const float4 t = *reinterpret_cast<const float4*>(dst);
+              x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+            }
+            if (do_round) {
+              x[0] = tf32_rna_fast(x[0]); x[1] = tf32_rna_fast(x[1]); x[2] = tf32_rna_fast(x[2]); x[3] = tf32_rna_fast(x[3]);
+            }
+            *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+        } else if (ncol > 0) {   // unaligned leading dimension or N tail: scalar path
+#pragma unroll 1
+          for (int rr = 0; rr < 8; ++rr) {
+            const int i = rr * 4 + rsub;
+            if (i >= rows) continue;
+            const int row = row_base + i;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e >= ncol) continue;
+              float x = fmaf(scratch[i * 36 + 4 * cg + e], alpha, bias[e]);
+              if (pre_p) pre_p[(size_t)row * ld_pre + col + e] = x;
+              if (act == F2G_ACT_PRELU || act == F2G_ACT_LEAKY) x = x > 0.f ? x : x * slope[e];
+              else if (act == F2G_ACT_SILU) x = x / (1.f + __expf(-x));
+              if (gate_p) x *= (__ldg(gate_p + (size_t)row * ld_gate + col + e) > 0.f ? 1.f : slope[e]);
+              if (res_p) x = fmaf(rsc[e], __ldg(res_p + (size_t)row * ld_res + col + e), x);
+              if (rowsc_p) x *= __ldg(rowsc_p + row);
+              float* dst = cbase + (size_t)row * ldc + col + e;
+              if (do_acc) x += *dst;
+              *dst = do_round ? tf32_rna_fast(x) : x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // staged parameters may be overwritten now
+      ab ^= 1;
+      if (ab == 0) ab_phase ^= 1;
+    }
+  }
+
+  // Neither CTA may exit (or free TMEM) while its peer can still signal its barriers / read its
+  // shared memory through the pair MMA.
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, P_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PEncodeTiledFn pair_encode_fn() {
+  static PEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable (%d)", (int)e);
+      return nullptr;
+    }
+    fn = reinterpret_cast<PEncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map; dims/strides innermost first; box = {32, box_rows}.  The row pitch may be
+// SMALLER than the row length (overlapping rows: the implicit im2col view of a strided conv).
+static int pair_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
+                          uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major) {
+  PEncodeTiledFn fn = pair_encode_fn();
+  if (!fn) return F2G_EDRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems % 4) != 0) {
+    set_error("gemm operand must be 16B aligned with a leading dimension multiple of 4 floats "
+              "(ptr=%p ld=%llu)", (const void*)base, (unsigned long long)outer_stride_elems);
+    return F2G_EINVAL;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {outer_stride_elems * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu box_rows=%u", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer,
+              (unsigned long long)outer_stride_elems, box_rows);
+    return F2G_EDRIVER;
+  }
+  return 0;
+}
+
+// N tile of a problem: the operand bytes a pair streams per output column are ~ (256 + bn) / bn,
+// so wide tiles win unless the last tile is mostly padding.  B_MN needs 32-column TMA boxes per
+// CTA (bn multiple of 64).
+static int pick_bn(int N, bool b_mn) {
+  const int step = b_mn ? 64 : 32;
+  int best = 256;
+  long best_cost = -1;
+  for (int bn = 256; bn >= step; bn -= step) {
+    const long tiles = (N + bn - 1) / bn;
+    const long cost = tiles * (256 + bn);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int A_MN, int B_MN, int EPI>
+static int pair_launch(const PGroup& g, cudaStream_t stream) {
+  static int max_pairs = 0;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI>;
+  if (!max_pairs) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_pair smem=%d): %s", P_SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = P_SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc < 1) {
+      cudaGetLastError();
+      nc = sms / 2;
+    }
+    const char* ov = getenv("F2G_PAIRS");
+    if (ov) nc = atoi(ov);
+    max_pairs = nc < 1 ? 1 : nc;
+  }
+  const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
+  kern<<<2 * pairs, P_THREADS, P_SMEM_BYTES, stream>>>(g);
+  return check_launch("gemm_pair");
+}
+
+int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
+  if (n < 1 || n > F2G_GEMM_MAX_PROBLEMS) {
+    set_error("gemm group size %d out of range", n);
+    return F2G_EINVAL;
+  }
+  PGroup g;
+  memset(&g, 0, sizeof(g));
+  const int a_mn = descs[0].a_mn, b_mn = descs[0].b_mn;
+  // heaviest tiles first: with a static round-robin schedule the long-K problems must not land
+  // in the last (partial) wave
+  int order[F2G_GEMM_MAX_PROBLEMS];
+  for (int i = 0; i < n; ++i) order[i] = i;
+  for (int i = 1; i < n; ++i)
+    for (int j = i; j > 0 && descs[order[j]].K > descs[order[j - 1]].K; --j) {
+      const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+    }
+  int tiles = 0;
+  for (int oi = 0; oi < n; ++oi) {
+    const F2GGemm& d = descs[order[oi]];
+    if (d.a_mn != a_mn || d.b_mn != b_mn) {
+      set_error("all problems of a gemm group must share operand majors");
+      return F2G_EINVAL;
+    }
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) {
+      set_error("gemm problem %d has empty shape %dx%dx%d", order[oi], d.M, d.N, d.K);
+      return F2G_EINVAL;
+    }
+    PProblem& p = g.p[oi];
+    const int bn = pick_bn(d.N, b_mn != 0);
+    int rc;
+    rc = a_mn ? pair_encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32, true)
+              : pair_encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, PBM, false);
+    if (rc) return rc;
+    rc = b_mn ? pair_encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
+              : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false);
+    if (rc) return rc;
+    p.c = d.c; p.ldc = d.ldc; p.c_pre = d.c_pre; p.ld_pre = d.ld_pre;
+    p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
+    p.row_scale = d.row_scale; p.gate = d.gate;
+    p.ld_res = d.ld_res; p.ld_gate = d.ld_gate;
+    p.M = d.M; p.N = d.N; p.K = d.K; p.bn = bn;
+    p.m_tiles = (d.M + 2 * PBM - 1) / (2 * PBM);
+    p.n_tiles = (d.N + bn - 1) / bn;
+    p.tile_begin = tiles;
+    p.act = d.act; p.round_tf32 = d.round_tf32; p.accumulate = d.accumulate;
+    p.leaky = d.leaky; p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
+    p.kb_total = (d.K + PBK - 1) / PBK;
+    int sk = d.split_k < 1 ? 1 : d.split_k;
+    if (sk > p.kb_total) sk = p.kb_total;
+    p.kb_per = (p.kb_total + sk - 1) / sk;
+    p.split_k = (p.kb_total + p.kb_per - 1) / p.kb_per;
+    if (p.split_k > 1 && (d.bias || d.act || d.res || d.gate || d.row_scale || d.c_pre || d.round_tf32)) {
+      set_error("split-K gemm supports the plain (alpha) epilogue only");
+      return F2G_EINVAL;
+    }
+    tiles += p.m_tiles * p.n_tiles * p.split_k;
+  }
+  g.n_problems = n;
+  g.total_tiles = tiles;
+  static const int dbg = getenv("F2G_PAIR_DBG") ? atoi(getenv("F2G_PAIR_DBG")) : 0;
+  g.dbg = dbg;
+
+  int epi = -1;
+  for (int i = 0; i < n; ++i) {
+    const F2GGemm& d = descs[i];
+    int e = PEPI_GENERIC;
+    const bool odd = d.gate || d.row_scale || d.act == F2G_ACT_SILU;
+    if (!odd && d.bias && (d.act == F2G_ACT_PRELU || d.act == F2G_ACT_LEAKY) && !d.res && !d.accumulate)
+      e = PEPI_BIAS_ACT;
+    else if (!odd && d.act == F2G_ACT_NONE && (d.res || d.bias) && !d.accumulate && !d.c_pre)
+      e = PEPI_BIAS_RES;
+    else if (!odd && d.act == F2G_ACT_NONE && !d.res && !d.bias && !d.c_pre)
+      e = PEPI_PLAIN;
+    epi = (epi == -1 || epi == e) ? e : PEPI_GENERIC;
+  }
+
+#define F2G_PDISPATCH_E(AM_, BM_)                                                        \
+  {                                                                                      \
+    if (epi == PEPI_BIAS_ACT) return pair_launch<AM_, BM_, PEPI_BIAS_ACT>(g, stream);    \
+    if (epi == PEPI_BIAS_RES) return pair_launch<AM_, BM_, PEPI_BIAS_RES>(g, stream);    \
+    if (epi == PEPI_PLAIN) return pair_launch<AM_, BM_, PEPI_PLAIN>(g, stream);          \
+    return pair_launch<AM_, BM_, PEPI_GENERIC>(g, stream);                               \
+  }
+  if (!a_mn && !b_mn) F2G_PDISPATCH_E(0, 0)
+  if (!a_mn && b_mn) F2G_PDISPATCH_E(0, 1)
+  if (a_mn && b_mn) F2G_PDISPATCH_E(1, 1)
+  F2G_PDISPATCH_E(1, 0)
+#undef F2G_PDISPATCH_E
+}
+
+}  // namespace f2g

@@ -560,6 +560,13 @@ static int launch(const DevGroup& g, int num_sms, cudaStream_t stream) {
 static int g_num_sms = 0;
 
 int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
+  // default: the CTA-pair kernel; F2G_GEMM_V1=1 keeps this one-CTA kernel for A/B comparisons
+  static const int use_v1 = env_int("F2G_GEMM_V1", 0);
+  // (problems with at most 128 rows -- e.g. weight gradients of the 32-channel MRD convs --
+  // would leave half of every 256-row pair tile empty)
+  int max_m = 0;
+  for (int i = 0; i < n && i < F2G_GEMM_MAX_PROBLEMS; ++i) max_m = descs[i].M > max_m ? descs[i].M : max_m;
+  if (!use_v1 && max_m > 128) return gemm_pair_group(descs, n, stream);
   if (n < 1 || n > F2G_GEMM_MAX_PROBLEMS) {
     set_error("gemm group size %d out of range", n);
     return F2G_EINVAL;

@@ -28,6 +28,7 @@ def test_conv2d_cl_forward_backward(shape, k, s, p, leaky):
     gen = torch.Generator().manual_seed(sum(shape))
     Nb, H, W, C = shape
     Co = 1 if leaky is None else 48
+    torch.manual_seed(1000 + sum(shape))                       # deterministic conv initialisation
     conv = torch.nn.Conv2d(C, Co, k, s, padding=p)
     x = torch.randn(Nb, H, W + 6, C, generator=gen)            # a band [3, 3+W) of a wider tensor
     xg = x.cuda().requires_grad_(True)

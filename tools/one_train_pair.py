@@ -21,6 +21,10 @@ lens = torch.full((bench.B,), 24000, device=dev, dtype=torch.int64)
 for _ in range(2): tr.step(audio, lens)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 for _ in range(2): tr.step(audio, lens)
+e1.record()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
+print("train pair: %.1f ms" % e0.elapsed_time(e1))
