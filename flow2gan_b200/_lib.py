@@ -44,6 +44,14 @@ class F2GLinear(C.Structure):
                 ("K", _i), ("O", _i), ("ld_in", _i), ("ldw", _i), ("ld_out", _i)]
 
 
+class F2GBlockPre(C.Structure):
+    _fields_ = [("x", _fp), ("dw_wT", _fp), ("dw_b", _fp), ("bn_bias", _fp), ("bn_log_scale", _fp),
+                ("row_mask", _fp), ("cond", _fp), ("tscale", _fp), ("out", _fp), ("conv_out", _fp),
+                ("inv_rms_out", _fp),
+                ("B", _i), ("T", _i), ("C", _i), ("ld_x", _i), ("ld_cond", _i), ("cond_T", _i),
+                ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i)]
+
+
 class F2GConv2d(C.Structure):
     _fields_ = [("Nb", _i), ("H", _i), ("W", _i), ("C", _i), ("pitch_h", _ll), ("pitch_n", _ll),
                 ("kh", _i), ("kw", _i), ("sh", _i), ("sw", _i), ("ph", _i), ("pw", _i), ("ldk", _i)]
@@ -82,6 +90,7 @@ _SIGS = {
     "f2g_biasnorm": ([_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp], _i),
     "f2g_block_pre": ([_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i,
                        _fp, _i, _fp, _fp, _fp], _i),
+    "f2g_block_pre_group": ([C.POINTER(F2GBlockPre), _i, _fp], _i),
     "f2g_linear_small": ([C.POINTER(F2GLinear), _i, _i, _i, _fp], _i),
     "f2g_time_sinusoid": ([_fp, _i, _i, _fp, _f, _fp, _fp], _i),
     "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
@@ -234,6 +243,24 @@ def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, c
                                ptr(bn_log_scale), ptr(row_mask), ptr(cond), ld_cond, cond_T, factor,
                                zero_row, ptr(tscale), ld_ts, ptr(out), ld_out, ptr(conv_out),
                                ptr(inv_out), stream()))
+
+
+def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
+                   factor, zero_row, tscale, ld_ts, out, ld_out, conv_out=None, inv_out=None) -> F2GBlockPre:
+    d = F2GBlockPre()
+    d.x, d.dw_wT, d.dw_b, d.bn_bias, d.bn_log_scale = ptr(x), ptr(dw_wT), ptr(dw_b), ptr(bn_bias), ptr(bn_log_scale)
+    d.row_mask, d.cond, d.tscale, d.out = ptr(row_mask), ptr(cond), ptr(tscale), ptr(out)
+    d.conv_out, d.inv_rms_out = ptr(conv_out), ptr(inv_out)
+    d.B, d.T, d.C, d.ld_x, d.ld_cond, d.cond_T = B, T, Cc, ld_x, ld_cond, cond_T
+    d.factor, d.zero_row, d.ld_ts, d.ld_out = factor, zero_row, ld_ts, ld_out
+    return d
+
+
+def block_pre_group(descs) -> None:
+    """Up to 4 block prologues (block_pre_desc) in one launch."""
+    n = len(descs)
+    arr = (F2GBlockPre * n)(*descs)
+    _check(lib().f2g_block_pre_group(arr, n, stream()))
 
 
 def linear_small_group(problems, B, act):

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "../../include/flow2gan_b200.h"
 
+#include <string.h>
+
 namespace f2g {
 
 constexpr int MAX_CHUNKS = 8;  // channels <= 8 * 128 = 1024 per row
@@ -47,77 +49,128 @@ __global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, in
   }
 }
 
-// Fused ConvNeXt-block prologue.  One CTA = PRE_TOK consecutive tokens of one batch element
-// processed CONCURRENTLY (threadIdx.y = token, threadIdx.x = 4-channel group): the 7-row windows
-// of neighbouring tokens overlap and are served by that SM's L1, so L2 sees (PRE_TOK+6)/PRE_TOK
-// reads per row instead of 7 (the one-token-per-CTA version ran at L2 bandwidth, 10 us/launch),
-// while the thread count stays that of the per-token mapping (a serial strip was slower: 14 us).
+// Fused ConvNeXt-block prologue, up to 4 independent problems (the three branches' same-depth
+// blocks) per launch.
 //   y = dwconv7(x * mask) + b ; z = BiasNorm(y) + cond_row ; z *= 1 + ts[b] ; out = tf32(z)
-constexpr int PRE_TOK = 4;
+// One CTA = 384 threads = TL token lanes x C/4 channel quads; every lane slides over PRE_S
+// consecutive tokens: it loads PRE_S+6 input rows ONCE (all loads in flight together) and the 7
+// depthwise taps once, instead of 7 rows + 7 taps per token -- the per-token version was bound by
+// L1 wavefronts (18 LDG.128 per token quad; 33 us for the three branches of one block).
+constexpr int PRE_THREADS = 384;
+constexpr int PRE_S = 4;
+constexpr int PRE_MAX_TL = 4;       // C >= 384
 
-__global__ void block_pre_kernel(const float* __restrict__ x, int B, int T, int C, int ld_x,
-                                 const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
-                                 const float* __restrict__ bn_bias,
-                                 const float* __restrict__ bn_log_scale,
-                                 const float* __restrict__ row_mask,
-                                 const float* __restrict__ cond, int ld_cond, int cond_T,
-                                 int factor, int zero_row, const float* __restrict__ tscale,
-                                 int ld_ts, float* __restrict__ out, int ld_out,
-                                 float* __restrict__ conv_out, float* __restrict__ inv_out) {
-  __shared__ float red[PRE_TOK][8];
-  const int bi = blockIdx.y;
-  const int ty = threadIdx.y;
-  const int t = blockIdx.x * PRE_TOK + ty;
-  const bool live = t < T;
-  const int c = threadIdx.x * 4;
-  const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  const size_t rb = (size_t)bi * T;
-  const size_t row = rb + t;
+struct BlockPreArgs {
+  F2GBlockPre p[4];
+  int cta_begin[5];     // prefix sums of CTAs per problem
+  int tl[4];            // token lanes per CTA
+  int ctas_t[4];        // CTAs along T per batch element
+  int n;
+};
 
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float ssq = 0.f;
-  if (live) {
-    acc = ld4(dw_b + c);
+__global__ void __launch_bounds__(PRE_THREADS, 2) block_pre_kernel(const __grid_constant__ BlockPreArgs a) {
+  __shared__ float red[PRE_MAX_TL * PRE_S][8];
+  int pi = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int tt = t + k - 3;
+  for (int i = 1; i < 4; ++i)
+    if (i < a.n && (int)blockIdx.x >= a.cta_begin[i]) pi = i;
+  const F2GBlockPre& P = a.p[pi];
+  const int C = P.C, T = P.T;
+  const int c4 = C >> 2;
+  const int TL = a.tl[pi];
+  const int local = blockIdx.x - a.cta_begin[pi];
+  const int bi = local / a.ctas_t[pi];
+  const int ty = threadIdx.x / c4;
+  const int tx = threadIdx.x - ty * c4;
+  const int t0 = ((local - bi * a.ctas_t[pi]) * TL + ty) * PRE_S;
+  const bool live = ty < TL && t0 < T;
+  const int c = tx * 4;
+  const int wid = tx >> 5, nw = c4 >> 5;
+  const size_t rb = (size_t)bi * T;
+  const float* __restrict__ x = P.x;
+  const float* __restrict__ row_mask = P.row_mask;
+  const int ld_x = P.ld_x;
+
+  float4 acc[PRE_S];
+  float4 cv[PRE_S];
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ssq[PRE_S];
+#pragma unroll
+  for (int s = 0; s < PRE_S; ++s) {
+    acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cv[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ssq[s] = 0.f;
+  }
+  if (live) {
+    float4 xv[PRE_S + 6];
+#pragma unroll
+    for (int j = 0; j < PRE_S + 6; ++j) {
+      const int tt = t0 - 3 + j;
+      xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (tt >= 0 && tt < T) {
         const float mk = row_mask ? row_mask[rb + tt] : 1.f;
         if (mk != 0.f) {
-          const float4 xv = ld4(x + (rb + tt) * ld_x + c);
-          const float4 w = ld4(dw_wT + k * C + c);
-          acc.x = fmaf(xv.x * mk, w.x, acc.x);
-          acc.y = fmaf(xv.y * mk, w.y, acc.y);
-          acc.z = fmaf(xv.z * mk, w.z, acc.z);
-          acc.w = fmaf(xv.w * mk, w.w, acc.w);
+          const float4 v = ld4(x + (rb + tt) * ld_x + c);
+          xv[j] = make_float4(v.x * mk, v.y * mk, v.z * mk, v.w * mk);
         }
       }
     }
-    const float4 bb = ld4(bn_bias + c);
-    const float d0 = acc.x - bb.x, d1 = acc.y - bb.y, d2 = acc.z - bb.z, d3 = acc.w - bb.w;
-    ssq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-    if (conv_out) st4(conv_out + row * C + c, acc);
+    const float4 b0 = ld4(P.dw_b + c);
+#pragma unroll
+    for (int s = 0; s < PRE_S; ++s) acc[s] = b0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float4 w = ld4(P.dw_wT + k * C + c);
+#pragma unroll
+      for (int s = 0; s < PRE_S; ++s) {
+        acc[s].x = fmaf(xv[s + k].x, w.x, acc[s].x);
+        acc[s].y = fmaf(xv[s + k].y, w.y, acc[s].y);
+        acc[s].z = fmaf(xv[s + k].z, w.z, acc[s].z);
+        acc[s].w = fmaf(xv[s + k].w, w.w, acc[s].w);
+      }
+    }
+    // the window registers are dead now: fetch the conditioning rows under the reduction
+    if (P.cond) {
+#pragma unroll
+      for (int s = 0; s < PRE_S; ++s) {
+        const int t = t0 + s;
+        if (t < T) {
+          const int crow = t < P.cond_T * P.factor ? bi * P.cond_T + t / P.factor : P.zero_row;
+          cv[s] = ld4(P.cond + (size_t)crow * P.ld_cond + c);
+        }
+      }
+    }
+    if (P.tscale) sc = ld4(P.tscale + (size_t)bi * P.ld_ts + c);
+    const float4 bb = ld4(P.bn_bias + c);
+#pragma unroll
+    for (int s = 0; s < PRE_S; ++s) {
+      const float d0 = acc[s].x - bb.x, d1 = acc[s].y - bb.y, d2 = acc[s].z - bb.z, d3 = acc[s].w - bb.w;
+      ssq[s] = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      if (P.conv_out && t0 + s < T) st4(P.conv_out + (rb + t0 + s) * C + c, acc[s]);
+    }
   }
-  // blockDim.x (= C/4) is a multiple of 32, so each warp belongs to exactly one token
-  ssq = warp_sum(ssq);
-  if ((threadIdx.x & 31) == 0) red[ty][wid] = ssq;
+  // c4 is a multiple of 32, so each warp belongs to exactly one token lane
+#pragma unroll
+  for (int s = 0; s < PRE_S; ++s) {
+    const float r = warp_sum(ssq[s]);
+    if ((threadIdx.x & 31) == 0 && ty < PRE_MAX_TL) red[ty * PRE_S + s][wid] = r;
+  }
   __syncthreads();
   if (!live) return;
-  ssq = 0.f;
-  for (int j = 0; j < nw; ++j) ssq += red[ty][j];
-  const float inv = (1.0f / sqrtf(ssq / (float)C)) * expf(*bn_log_scale);
-  if (inv_out && threadIdx.x == 0) inv_out[row] = inv;
-  float4 z = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-  if (cond) {
-    const int crow = t < cond_T * factor ? bi * cond_T + t / factor : zero_row;
-    const float4 cv = ld4(cond + (size_t)crow * ld_cond + c);
-    z.x += cv.x; z.y += cv.y; z.z += cv.z; z.w += cv.w;
-  }
-  if (tscale) {
-    const float4 sc = ld4(tscale + (size_t)bi * ld_ts + c);
+  const float gain = expf(*P.bn_log_scale);
+#pragma unroll
+  for (int s = 0; s < PRE_S; ++s) {
+    const int t = t0 + s;
+    if (t >= T) break;
+    float tot = 0.f;
+    for (int j = 0; j < nw; ++j) tot += red[ty * PRE_S + s][j];
+    const float inv = (1.0f / sqrtf(tot / (float)C)) * gain;
+    if (P.inv_rms_out && tx == 0) P.inv_rms_out[rb + t] = inv;
+    float4 z = make_float4(acc[s].x * inv, acc[s].y * inv, acc[s].z * inv, acc[s].w * inv);
+    z.x += cv[s].x; z.y += cv[s].y; z.z += cv[s].z; z.w += cv[s].w;
     z.x *= 1.f + sc.x; z.y *= 1.f + sc.y; z.z *= 1.f + sc.z; z.w *= 1.f + sc.w;
+    st4(P.out + (rb + t) * P.ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
   }
-  st4(out + row * ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
 }
 
 // Batched small dense layers (up to 4 independent problems per launch, blockIdx.y = problem):
@@ -243,19 +296,49 @@ extern "C" int f2g_biasnorm(const float* x, int rows, int C, int ld, const float
   return check_launch("f2g_biasnorm");
 }
 
+extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream) {
+  if (n < 1 || n > 4) {
+    set_error("f2g_block_pre_group: n=%d out of range (1..4)", n);
+    return F2G_EINVAL;
+  }
+  BlockPreArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n;
+  int ctas = 0;
+  for (int i = 0; i < n; ++i) {
+    F2GBlockPre p = probs[i];
+    if (int rc = check_channels("f2g_block_pre", p.C, p.ld_x | p.ld_out | (p.cond ? p.ld_cond : 0) | (p.tscale ? p.ld_ts : 0)))
+      return rc;
+    if (p.factor < 1) p.factor = 1;
+    a.p[i] = p;
+    if (p.C < PRE_THREADS) {
+      set_error("f2g_block_pre: channels=%d must be >= %d", p.C, PRE_THREADS);
+      return F2G_EINVAL;
+    }
+    int tl = PRE_THREADS / (p.C / 4);
+    if (tl > PRE_MAX_TL) tl = PRE_MAX_TL;
+    a.tl[i] = tl;
+    a.ctas_t[i] = (p.T + tl * PRE_S - 1) / (tl * PRE_S);
+    a.cta_begin[i] = ctas;
+    ctas += a.ctas_t[i] * p.B;
+  }
+  for (int i = n; i <= 4; ++i) a.cta_begin[i] = ctas;
+  block_pre_kernel<<<ctas, PRE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("f2g_block_pre");
+}
+
 extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, const float* dw_wT,
                              const float* dw_b, const float* bn_bias, const float* bn_log_scale,
                              const float* row_mask, const float* cond, int ld_cond, int cond_T,
                              int factor, int zero_row, const float* tscale, int ld_ts, float* out,
                              int ld_out, float* conv_out, float* inv_rms_out, void* stream) {
-  if (int rc = check_channels("f2g_block_pre", C, ld_x | ld_out | (cond ? ld_cond : 0) | (tscale ? ld_ts : 0)))
-    return rc;
-  dim3 grid((T + PRE_TOK - 1) / PRE_TOK, B);
-  dim3 block(C / 4, PRE_TOK);
-  block_pre_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, B, T, C, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
-      factor < 1 ? 1 : factor, zero_row, tscale, ld_ts, out, ld_out, conv_out, inv_rms_out);
-  return check_launch("f2g_block_pre");
+  F2GBlockPre p;
+  p.x = x; p.B = B; p.T = T; p.C = C; p.ld_x = ld_x; p.dw_wT = dw_wT; p.dw_b = dw_b;
+  p.bn_bias = bn_bias; p.bn_log_scale = bn_log_scale; p.row_mask = row_mask; p.cond = cond;
+  p.ld_cond = ld_cond; p.cond_T = cond_T; p.factor = factor; p.zero_row = zero_row;
+  p.tscale = tscale; p.ld_ts = ld_ts; p.out = out; p.ld_out = ld_out; p.conv_out = conv_out;
+  p.inv_rms_out = inv_rms_out;
+  return f2g_block_pre_group(&p, 1, stream);
 }
 
 extern "C" int f2g_linear_small(const F2GLinear* probs, int n, int B, int act, void* stream) {

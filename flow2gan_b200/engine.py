@@ -254,13 +254,15 @@ class InferencePlan:
         L.linear_small_group(prob3, 1, L.ACT_NONE)
         nl = pk.branches[0].nl
         for i in range(nl):
+            pre = []
             for bw, w in zip(pk.branches, self.br):
                 k = bw.blocks[i]
                 b = k.blk
                 ldc = bw.nl * bw.C
-                L.block_pre(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
-                            b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm, bw.factor,
-                            B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C)
+                pre.append(L.block_pre_desc(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
+                                            b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm,
+                                            bw.factor, B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C))
+            L.block_pre_group(pre)          # the three branches' prologues: one launch
             L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
             L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1))
                           for bw, w in zip(pk.branches, self.br)])

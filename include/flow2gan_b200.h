@@ -127,6 +127,24 @@ int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, const float* dw
                   int zero_row, const float* tscale, int ld_ts, float* out, int ld_out,
                   float* conv_out, float* inv_rms_out, void* stream);
 
+/* The same for up to 4 independent problems in ONE launch (the three branches' blocks of equal
+ * depth): fields as the arguments of f2g_block_pre. */
+typedef struct F2GBlockPre {
+  const float* x;
+  const float* dw_wT;
+  const float* dw_b;
+  const float* bn_bias;
+  const float* bn_log_scale;
+  const float* row_mask;
+  const float* cond;
+  const float* tscale;
+  float* out;
+  float* conv_out;
+  float* inv_rms_out;
+  int B, T, C, ld_x, ld_cond, cond_T, factor, zero_row, ld_ts, ld_out;
+} F2GBlockPre;
+int f2g_block_pre_group(const F2GBlockPre* problems, int n_problems, void* stream);
+
 /* Small dense layers for few-row inputs, fp32 SIMT, up to 4 independent problems per launch:
  * out[b,o] = act(bias[o] + in[b,:].W[o,:]), b < B (time_mlp / time_embed_proj of the three
  * branches, modules.py:569-573,451,485).  K multiple of 128 and <= 1536. */
