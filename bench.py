@@ -302,24 +302,45 @@ def run_ours(args):
         e2e_value = world * SAMPLES_PER_STEP * K / (float(t_dev.item()) * 1e-3)
 
         # ---------------- roofline of the dominant kernel (tcgen05 TF32 GEMM) ---------------
+        # The step's GEMM launches (same descriptors, same buffers) are re-issued alone, back to
+        # back, from a CUDA graph so that no host submission latency sits between the two events:
+        # achieved = sum(2MNK) / (event time / launches) -- the in-step average launch duration.
         roof = None
         if rank == 0:
             L.PROFILE = []
-            for _ in range(3):
-                plan.x_audio.copy_(noise)
-                plan._run(n, False)
+            plan.x_audio.copy_(noise)
+            plan._run(n, False)
             torch.cuda.synchronize()
-            flops = sum(f for (_, _, f) in L.PROFILE)
-            ms = sum(a.elapsed_time(b) for (a, b, _) in L.PROFILE)
-            nl = len(L.PROFILE)
-            L.PROFILE = None
+            rec, L.PROFILE = L.PROFILE, None
+            flops = sum(f for (_, _, f) in rec)
+            nl = len(rec)
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                for arr, cnt, _ in rec:
+                    L.gemm_replay(arr, cnt)
+                side.synchronize()
+                gg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gg, stream=side):
+                    for arr, cnt, _ in rec:
+                        L.gemm_replay(arr, cnt)
+                reps = 10
+                for _ in range(3):
+                    gg.replay()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(reps):
+                    gg.replay()
+                g1.record()
+                side.synchronize()
+            ms = g0.elapsed_time(g1) / reps
             pk, how = peaks()
             peak = pk["bf16_tflops"] / 2.0
             ach = flops / (ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)",
+            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                     "launches_timed": nl, "flops_per_launch_avg": flops / nl, "us_per_launch_avg": ms * 1e3 / nl,
-                    "peak_source": f"{how}: bf16_tflops (burst; launches are timed one by one)/2 -- TF32 issues at half the bf16 rate",
+                    "how": "all GEMM launches of one step replayed back to back from a CUDA graph, CUDA events",
+                    "peak_source": f"{how}: bf16_tflops (burst)/2 -- TF32 issues at half the bf16 rate",
                     "step_ref_equiv_tflops": REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12 / 1.0}
 
     train = None

@@ -198,13 +198,13 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
 def gemm_group(descs: Sequence[F2GGemm]) -> None:
     n = len(descs)
     arr = (F2GGemm * n)(*descs)
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _check(lib().f2g_gemm_tf32(arr, n, stream()))
-        e1.record()
-        PROFILE.append((e0, e1, sum(2.0 * d.M * d.N * d.K for d in descs)))
-        return
+    if PROFILE is not None:      # bench.py: record the launch (descriptors + FLOPs) for replay
+        PROFILE.append((arr, n, sum(2.0 * d.M * d.N * d.K for d in descs)))
+    _check(lib().f2g_gemm_tf32(arr, n, stream()))
+
+
+def gemm_replay(arr, n) -> None:
+    """Re-issue a recorded grouped GEMM launch (bench.py roofline leg)."""
     _check(lib().f2g_gemm_tf32(arr, n, stream()))
 
 

@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace f2g {
 
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const int on = [] {
+    const char* v = getenv("F2G_PDL");
+    return v ? atoi(v) : 1;
+  }();
+  return on != 0;
 }
 
 int check_launch(const char* what) {

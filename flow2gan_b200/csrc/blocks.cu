@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) block_pre_kernel(const __grid_
   const float* __restrict__ x = P.x;
   const float* __restrict__ row_mask = P.row_mask;
   const int ld_x = P.ld_x;
+  pdl_wait();
+  pdl_launch();
 
   float4 acc[PRE_S];
   float4 cv[PRE_S];
@@ -323,7 +325,11 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
     ctas += a.ctas_t[i] * p.B;
   }
   for (int i = n; i <= 4; ++i) a.cta_begin[i] = ctas;
-  block_pre_kernel<<<ctas, PRE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t le = launch_pdl(block_pre_kernel, dim3(ctas), dim3(PRE_THREADS), 0, static_cast<cudaStream_t>(stream), a);
+  if (le != cudaSuccess) {
+    set_error("f2g_block_pre launch: %s", cudaGetErrorString(le));
+    return (int)le;
+  }
   return check_launch("f2g_block_pre");
 }
 

@@ -222,6 +222,17 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int m, int n, int a_mn_major
   return d;
 }
 
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched through launch_pdl() may become resident
+// while its predecessor in the stream is still draining: everything before pdl_wait() (barrier
+// init, TMEM allocation, descriptor prefetch, index math) overlaps the predecessor's tail.
+// pdl_wait() returns once the predecessor grid has fully completed and its writes are visible,
+// so it must precede the first global-memory access; it is a no-op for ordinary launches.
+// pdl_launch() lets the successor start becoming resident as SMs free up.
+// ---------------------------------------------------------------------------------------
+F2G_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+F2G_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 F2G_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -230,6 +241,24 @@ F2G_DEVINL bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// host: launch `kern` with the programmatic-stream-serialization attribute (F2G_PDL=0 disables)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace f2g

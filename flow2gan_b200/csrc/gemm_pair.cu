@@ -34,6 +34,8 @@ constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 36 * 4;
 constexpr int P_PARAM_BYTES = 3 * 256 * 4;
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + P_PARAM_BYTES;
 constexpr int P_TMEM_COLS = 512;
+constexpr int P_MAX_SCHED = 1024;
+constexpr int P_MAX_PAIRS = 78;
 
 struct alignas(64) PProblem {
   CUtensorMap map_a;
@@ -58,6 +60,13 @@ struct alignas(64) PGroup {
   PProblem p[F2G_GEMM_MAX_PROBLEMS];
   int n_problems;
   int total_tiles;
+  // Static longest-processing-time schedule (host-computed; groups of <= P_MAX_SCHED tiles):
+  // pair p runs tiles sched[pair_off[p] .. pair_off[p+1]).  Tiles of one launch differ up to 3x
+  // in cost (K = 2304 vs 1152 ...), so round-robin left ~40 % of the SM-time of the pwconv2
+  // group idle.  use_sched == 0: plain round-robin (tile = pair + i * npairs).
+  int use_sched;
+  uint16_t pair_off[P_MAX_PAIRS + 2];
+  uint16_t sched[P_MAX_SCHED];
   int dbg;   // bring-up (F2G_PAIR_DBG): bit0 = epilogue drains TMEM but stores nothing,
              // bit1 = epilogue skips TMEM loads too
 };
@@ -226,6 +235,9 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
+  const int s_off = g.use_sched ? g.pair_off[pair] : 0;
+  const int my_tiles = g.use_sched ? (int)g.pair_off[pair + 1] - s_off
+                                   : (g.total_tiles > pair ? (g.total_tiles - pair + npairs - 1) / npairs : 0);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < g.n_problems; ++i) {
@@ -251,13 +263,16 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                  // everything above overlapped the previous kernel's tail
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) --------------------------
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
         const PTile tc = pdecode(g, tile);
         const PProblem& pr = g.p[tc.prob];
         const int bhalf = pr.bn >> 1;
@@ -304,7 +319,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       uint32_t phase = 0;
       int ab = 0;
       uint32_t ab_phase = 0;
-      for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
         const PTile tc = pdecode(g, tile);
         const uint32_t idesc = make_idesc_tf32(2 * PBM, g.p[tc.prob].bn, A_MN, B_MN);
         mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
@@ -348,7 +364,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     const uint32_t lead_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     int ab = 0;
     uint32_t ab_phase = 0;
-    for (int tile = pair; tile < g.total_tiles; tile += npairs) {
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
       const PTile tc = pdecode(g, tile);
       const PProblem& pr = g.p[tc.prob];
       const int BN = pr.bn;
@@ -600,8 +617,69 @@ static int pick_bn(int N, bool b_mn) {
   return best;
 }
 
+
+// Greedy LPT: tiles sorted by decreasing cost, each to the least-loaded pair (binary heap).
+static void build_schedule(PGroup& g, int pairs) {
+  g.use_sched = 0;
+  const int T = g.total_tiles;
+  if (T > P_MAX_SCHED || pairs > P_MAX_PAIRS || T <= pairs) return;
+  static thread_local int cost[P_MAX_SCHED];
+  static thread_local uint16_t order[P_MAX_SCHED];
+  // tiles are laid out problem by problem (problems already sorted by decreasing K), every tile
+  // of a problem costs the same: the natural order IS the decreasing-cost order unless N tiles
+  // differ, so a stable counting pass is enough
+  int n = 0;
+  bool sorted = true;
+  for (int pi = 0; pi < g.n_problems; ++pi) {
+    const PProblem& p = g.p[pi];
+    const int cnt = p.m_tiles * p.n_tiles * p.split_k;
+    const int c = p.kb_per * (256 + p.bn) + 8 * p.bn;
+    for (int i = 0; i < cnt; ++i) {
+      cost[n] = c;
+      order[n] = (uint16_t)n;
+      if (n && cost[n - 1] < c) sorted = false;
+      ++n;
+    }
+  }
+  if (cost[0] == cost[n - 1] && sorted) return;   // homogeneous tiles: round-robin is already optimal
+  if (!sorted) {
+    for (int i = 1; i < n; ++i) {          // insertion sort by cost (few distinct values, mostly sorted)
+      const uint16_t o = order[i];
+      int j = i;
+      while (j > 0 && cost[order[j - 1]] < cost[o]) { order[j] = order[j - 1]; --j; }
+      order[j] = o;
+    }
+  }
+  long load[P_MAX_PAIRS];
+  int heap[P_MAX_PAIRS];
+  uint16_t owner[P_MAX_SCHED];
+  int count[P_MAX_PAIRS];
+  for (int i = 0; i < pairs; ++i) { load[i] = 0; heap[i] = i; count[i] = 0; }
+  for (int i = 0; i < n; ++i) {
+    const int p = heap[0];                // least-loaded pair (ties: lowest index first)
+    owner[i] = (uint16_t)p;
+    load[p] += cost[order[i]];
+    ++count[p];
+    int k = 0;                            // sift down
+    for (;;) {
+      int l = 2 * k + 1, r = l + 1, m = k;
+      if (l < pairs && (load[heap[l]] < load[heap[m]] || (load[heap[l]] == load[heap[m]] && heap[l] < heap[m]))) m = l;
+      if (r < pairs && (load[heap[r]] < load[heap[m]] || (load[heap[r]] == load[heap[m]] && heap[r] < heap[m]))) m = r;
+      if (m == k) break;
+      const int t = heap[k]; heap[k] = heap[m]; heap[m] = t;
+      k = m;
+    }
+  }
+  int off = 0;
+  int start[P_MAX_PAIRS];
+  for (int i = 0; i < pairs; ++i) { g.pair_off[i] = (uint16_t)off; start[i] = off; off += count[i]; }
+  g.pair_off[pairs] = (uint16_t)off;
+  for (int i = 0; i < n; ++i) g.sched[start[owner[i]]++] = order[i];
+  g.use_sched = 1;
+}
+
 template <int A_MN, int B_MN, int EPI>
-static int pair_launch(const PGroup& g, cudaStream_t stream) {
+static int pair_launch(PGroup& g, cudaStream_t stream) {
   static int max_pairs = 0;
   auto kern = gemm_pair_kernel<A_MN, B_MN, EPI>;
   if (!max_pairs) {
@@ -634,7 +712,13 @@ static int pair_launch(const PGroup& g, cudaStream_t stream) {
     max_pairs = nc < 1 ? 1 : nc;
   }
   const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
-  kern<<<2 * pairs, P_THREADS, P_SMEM_BYTES, stream>>>(g);
+  static const int no_sched = getenv("F2G_PAIR_RR") ? atoi(getenv("F2G_PAIR_RR")) : 0;
+  if (!no_sched) build_schedule(g, pairs);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(P_THREADS), (size_t)P_SMEM_BYTES, stream, g);
+  if (le != cudaSuccess) {
+    set_error("gemm_pair launch: %s", cudaGetErrorString(le));
+    return (int)le;
+  }
   return check_launch("gemm_pair");
 }
 
