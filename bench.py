@@ -175,7 +175,7 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
     audio = audio_input(B, Tt, seed=2 + int(os.environ.get("RANK", "0"))).to(dev)
     lens = torch.full((B,), Tt, device=dev, dtype=torch.int64)
     torch.manual_seed(1 + int(os.environ.get("RANK", "0")))
-    for _ in range(2):                    # warm-up pair
+    for _ in range(6):                    # warm-up: eager pair, graph-capture pair, one replayed pair
         tr.step(audio, lens)
     torch.cuda.synchronize()
     if dist is not None:
@@ -195,7 +195,9 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
             "pairs": pairs, "n_timesteps": n_timesteps, "global_batch": B * world,
             "allreduce_bytes_per_pair": 0 if world == 1 else (78949542 + 42503752) * 4,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-            "includes": "LogMel front-end, GAN.forward, backward, grad all-reduce (world>1), ScaledAdam.step, Eden2"}
+            "step_graphs": sum("graph" in e for e in tr._graphs.values()),
+            "includes": "LogMel front-end, GAN.forward, backward (one CUDA graph per phase), grad all-reduce "
+                        "(world>1), ScaledAdam.step, Eden2"}
 
 
 def run_reference(args):

@@ -285,7 +285,9 @@ class InferencePlan:
         t_span = torch.linspace(0, 1, n + 1)                       # generator.py:253
         dt = float(t_span[1] - t_span[0])
         ts = [float(t_span[k]) for k in range(n)]
-        self.t_all = t_span[:n].to(self.x_audio.device).unsqueeze(1).expand(n, self.B).contiguous()
+        # built on the device (no host->device copy: this also runs under stream capture)
+        self.t_all = torch.linspace(0, 1, n + 1, device=self.x_audio.device)[:n].unsqueeze(1) \
+            .expand(n, self.B).contiguous()
         return ts, dt
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:

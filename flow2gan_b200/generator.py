@@ -162,6 +162,8 @@ class MelAudioGenerator(BaseAudioGenerator):
         cond = self._maybe_noisy_cond(cond)
         if audio_lens is None:
             length = cond.shape[2] * self.mel_hop_length
+        elif getattr(self, "_static_length", None):
+            length = self._static_length        # whole-step graph capture: no host read-back
         else:
             length = int(audio_lens.max().item())
         if noise is None:
@@ -172,4 +174,6 @@ class MelAudioGenerator(BaseAudioGenerator):
             return generator_infer_with_grad(self, cond, noise, audio_lens, n_timesteps, clamp_pred)
         p = self.plan(cond.shape[0], cond.shape[2], length, audio_lens is not None)
         with torch.no_grad():
-            return p.infer(cond.float(), noise.float(), audio_lens, n_timesteps, clamp_pred)
+            # inside an outer stream capture the plan's launches become part of that graph
+            return p.infer(cond.float(), noise.float(), audio_lens, n_timesteps, clamp_pred,
+                           use_graph=not torch.cuda.is_current_stream_capturing())

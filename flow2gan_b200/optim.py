@@ -190,6 +190,9 @@ class ScaledAdam(Optimizer):
                 self._refresh_threshold(group, st)
             L.scaled_adam_step(*args, 1, h)
             st.step += 1
+            # the fused kernel writes the parameters through raw pointers: tell torch (and the
+            # generator's packed-weight cache, engine.py::_params_signature) that they changed
+            torch.autograd.graph.increment_version([p for p in st.params if p.grad is not None])
         return loss
 
     # ------------------------------------------------------------------ checkpoint layout

@@ -51,8 +51,46 @@ def _limit_flip(grad: Tensor, x: Tensor, lo: float, hi: float) -> Tensor:
     return g * torch.where((g < 0) & (x > hi), -1.0, 1.0)
 
 
-def _limit_draw(training: bool, prob: float = 0.6) -> bool:
-    return training and random.random() < prob          # modules.py:267
+class DrawBuffer:
+    """Source of the LimitParamValue coin flips (modules.py:267) when a whole training iteration
+    is captured in a CUDA graph: the forward pass takes device scalars out of `dev` instead of
+    calling random.random(), and the host refills them -- same generator, same order, same
+    count as the eager path -- before every replay."""
+
+    def __init__(self, device, n: int = 512):
+        self.dev = torch.zeros(n, device=device)
+        self.host = torch.zeros(n).pin_memory()
+        self.i = 0
+        self.count = 0
+
+    def take(self) -> Tensor:
+        t = self.dev[self.i]
+        self.i += 1
+        return t
+
+    def refill(self, prob: float = 0.6) -> None:
+        for k in range(self.count):
+            self.host[k] = 1.0 if random.random() < prob else 0.0
+        if self.count:
+            self.dev[: self.count].copy_(self.host[: self.count], non_blocking=True)
+
+
+_draws: Optional[DrawBuffer] = None      # set by GANTrainer while it captures a step graph
+
+
+def _limit_draw(training: bool, prob: float = 0.6):
+    if not training:
+        return False
+    if _draws is not None:
+        return _draws.take()
+    return random.random() < prob          # modules.py:267
+
+
+def _limit_apply(flag, grad: Tensor, x: Tensor, lo: float, hi: float) -> Tensor:
+    """flag: Python bool (eager) or a device 0/1 scalar (graph mode, no host decision)."""
+    if isinstance(flag, Tensor):
+        return torch.where(flag > 0, _limit_flip(grad, x, lo, hi), grad)
+    return _limit_flip(grad, x, lo, hi) if flag else grad
 
 
 # =========================================================================================
@@ -139,11 +177,8 @@ def _blocks_backward(blocks_w, saves, dxo: Tensor, B: int, T: int, C: int, mask,
         L.block_bwd_b(dy, bw.dwT, mask, dxo, C, b.residual_scale.scale, B, T, C, dx, C)
         gdw = _e(C, 1, 7, dev=dev)
         L.pack2d(g_dww.data_ptr(), 1, C, C, 7, gdw.data_ptr(), 7, 7, 0)
-        if s.lim_norm:
-            g_ls = _limit_flip(g_ls, b.norm.log_scale.detach(), -1.5, 1.5)
-        g_rs = g_rs.view(C, 1)
-        if s.lim_rs:
-            g_rs = _limit_flip(g_rs, b.residual_scale.scale.detach(), 0.5, 1.0)
+        g_ls = _limit_apply(s.lim_norm, g_ls, b.norm.log_scale.detach(), -1.5, 1.5)
+        g_rs = _limit_apply(s.lim_rs, g_rs.view(C, 1), b.residual_scale.scale.detach(), 0.5, 1.0)
         grads[pre + "dwconv.weight"] = gdw
         grads[pre + "dwconv.bias"] = g_dwb
         grads[pre + "norm.bias"] = g_beta
@@ -166,8 +201,7 @@ def _norm_backward(dz: Tensor, x0: Tensor, inv: Tensor, norm, R: int, C: int, B:
     L.block_bwd_a(dz, C, x0, inv, norm.bias, norm.log_scale, None, 0, B, T, C, dx, None, coef, gs)
     g_beta, g_ls = _z(C, dev=dev), _z((), dev=dev)
     L.block_bwd_c(y=x0, coef=coef, gs=gs, bn_bias=norm.bias, g_beta=g_beta, g_ls=g_ls, B=B, T=T, C=C)
-    if lim:
-        g_ls = _limit_flip(g_ls, norm.log_scale.detach(), -1.5, 1.5)
+    g_ls = _limit_apply(lim, g_ls, norm.log_scale.detach(), -1.5, 1.5)
     grads[prefix + "bias"] = g_beta
     grads[prefix + "log_scale"] = g_ls
     return dx

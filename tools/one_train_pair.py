@@ -18,7 +18,7 @@ gan = gan.to(dev)
 tr = GANTrainer(gan)
 audio = audio_input(bench.B, 24000, seed=2).to(dev)
 lens = torch.full((bench.B,), 24000, device=dev, dtype=torch.int64)
-for _ in range(2): tr.step(audio, lens)
+for _ in range(6): tr.step(audio, lens)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
