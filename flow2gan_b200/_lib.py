@@ -52,6 +52,11 @@ class F2GBlockPre(C.Structure):
                 ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i)]
 
 
+class F2GSpecProblem(C.Structure):
+    _fields_ = [("inp", _fp), ("out", _fp), ("n_fft", _i), ("hop", _i), ("frames", _i), ("rows", _i),
+                ("ld_in", _i), ("ld_out", _i)]
+
+
 class F2GConv2d(C.Structure):
     _fields_ = [("Nb", _i), ("H", _i), ("W", _i), ("C", _i), ("pitch_h", _ll), ("pitch_n", _ll),
                 ("kh", _i), ("kw", _i), ("sh", _i), ("sw", _i), ("ph", _i), ("pw", _i), ("ldk", _i)]
@@ -92,6 +97,8 @@ _SIGS = {
                        _fp, _i, _fp, _fp, _fp], _i),
     "f2g_block_pre_group": ([C.POINTER(F2GBlockPre), _i, _fp], _i),
     "f2g_linear_small": ([C.POINTER(F2GLinear), _i, _i, _i, _fp], _i),
+    "f2g_stft_group": ([C.POINTER(F2GSpecProblem), _i, _i, _i, _i, _fp], _i),
+    "f2g_irfft_group": ([C.POINTER(F2GSpecProblem), _i, _fp], _i),
     "f2g_time_sinusoid": ([_fp, _i, _i, _fp, _f, _fp, _fp], _i),
     "f2g_pack2d": ([_fp, _ll, _ll, _i, _i, _fp, _i, _i, _i, _fp], _i),
     "f2g_im2col_cf": ([_fp, _i, _i, _i, _i, _fp, _i, _i, _fp], _i),
@@ -212,6 +219,27 @@ def stft(audio, B, T, ld_audio, n_fft, hop, mode, out, ld_out, *, pre=None, fb=N
          log_clip=0.0, round_tf32=0):
     _check(lib().f2g_stft(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(pre), ptr(fb), n_filt,
                           log_clip, ptr(out), ld_out, round_tf32, stream()))
+
+
+def _spec_problems(problems):
+    n = len(problems)
+    arr = (F2GSpecProblem * n)()
+    for d, (inp, out, n_fft, hop, frames, rows, ld_in, ld_out) in zip(arr, problems):
+        d.inp, d.out = ptr(inp), ptr(out)
+        d.n_fft, d.hop, d.frames, d.rows, d.ld_in, d.ld_out = n_fft, hop, frames, rows, ld_in, ld_out
+    return arr, n
+
+
+def stft_group(problems, B, T, round_tf32=0):
+    """problems: (audio, out, n_fft, hop, frames, rows, ld_audio, ld_out) per resolution; packed mode."""
+    arr, n = _spec_problems(problems)
+    _check(lib().f2g_stft_group(arr, n, B, T, round_tf32, stream()))
+
+
+def irfft_group(problems):
+    """problems: (packed, frames_out, n_fft, 0, 0, rows, ld, n_fft) per resolution."""
+    arr, n = _spec_problems(problems)
+    _check(lib().f2g_irfft_group(arr, n, stream()))
 
 
 def dc_peak(audio, B, T, ld_audio, pre):

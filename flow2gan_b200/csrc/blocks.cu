@@ -6,6 +6,7 @@
 #include "../../include/flow2gan_b200.h"
 
 #include <string.h>
+#include <stdlib.h>
 
 namespace f2g {
 
@@ -57,7 +58,6 @@ __global__ void biasnorm_kernel(const float* __restrict__ x, int rows, int C, in
 // depthwise taps once, instead of 7 rows + 7 taps per token -- the per-token version was bound by
 // L1 wavefronts (18 LDG.128 per token quad; 33 us for the three branches of one block).
 constexpr int PRE_THREADS = 384;
-constexpr int PRE_S = 4;
 constexpr int PRE_MAX_TL = 4;       // C >= 384
 
 struct BlockPreArgs {
@@ -68,7 +68,8 @@ struct BlockPreArgs {
   int n;
 };
 
-__global__ void __launch_bounds__(PRE_THREADS, 2) block_pre_kernel(const __grid_constant__ BlockPreArgs a) {
+template <int PRE_S, int MINB>
+__global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __grid_constant__ BlockPreArgs a) {
   __shared__ float red[PRE_MAX_TL * PRE_S][8];
   int pi = 0;
 #pragma unroll
@@ -306,6 +307,9 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
   BlockPreArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n;
+  // sliding-window length per lane / resident CTAs per SM (F2G_PRE_VARIANT: bring-up sweep)
+  static const int variant = getenv("F2G_PRE_VARIANT") ? atoi(getenv("F2G_PRE_VARIANT")) : 0;
+  const int S = variant == 1 ? 2 : (variant == 2 ? 2 : (variant == 3 ? 8 : 4));
   int ctas = 0;
   for (int i = 0; i < n; ++i) {
     F2GBlockPre p = probs[i];
@@ -320,12 +324,16 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
     int tl = PRE_THREADS / (p.C / 4);
     if (tl > PRE_MAX_TL) tl = PRE_MAX_TL;
     a.tl[i] = tl;
-    a.ctas_t[i] = (p.T + tl * PRE_S - 1) / (tl * PRE_S);
+    a.ctas_t[i] = (p.T + tl * S - 1) / (tl * S);
     a.cta_begin[i] = ctas;
     ctas += a.ctas_t[i] * p.B;
   }
   for (int i = n; i <= 4; ++i) a.cta_begin[i] = ctas;
-  cudaError_t le = launch_pdl(block_pre_kernel, dim3(ctas), dim3(PRE_THREADS), 0, static_cast<cudaStream_t>(stream), a);
+  void (*kern)(BlockPreArgs) = block_pre_kernel<4, 2>;
+  if (variant == 1) kern = block_pre_kernel<2, 3>;
+  if (variant == 2) kern = block_pre_kernel<2, 2>;
+  if (variant == 3) kern = block_pre_kernel<8, 1>;
+  cudaError_t le = launch_pdl(kern, dim3(ctas), dim3(PRE_THREADS), 0, static_cast<cudaStream_t>(stream), a);
   if (le != cudaSuccess) {
     set_error("f2g_block_pre launch: %s", cudaGetErrorString(le));
     return (int)le;

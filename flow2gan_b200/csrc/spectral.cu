@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "../../include/flow2gan_b200.h"
 
+#include <string.h>
+
 namespace f2g {
 
 F2G_DEVINL float2 cmul(float2 a, float2 b) {
@@ -38,6 +40,8 @@ F2G_DEVINL float2* block_fft(float2* a, float2* b, const float2* tw, int n, int 
   return a;
 }
 
+// (a precomputed global twiddle table was measured: no change -- these kernels are bound by the
+// per-frame CTA latency chain, not by the sincospif calls)
 F2G_DEVINL void fill_twiddles(float2* tw, int n) {
   for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x) {
     float s, c;
@@ -52,18 +56,17 @@ F2G_DEVINL float hann_from_tw(const float2* tw, int i, int n) {
   return i < h ? 0.5f - 0.5f * tw[i].x : 0.5f + 0.5f * tw[i - h].x;
 }
 
-__global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
-                            int hop, int frames, int mode, const float* __restrict__ pre,
-                            const float* __restrict__ fb, int n_filt, float log_clip,
-                            float* __restrict__ out, int ld_out, int round_tf32, int center,
-                            int adjoint_scale, const float* __restrict__ row_mask) {
+F2G_DEVINL void stft_frame(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
+                           int hop, int frames, int mode, const float* __restrict__ pre,
+                           const float* __restrict__ fb, int n_filt, float log_clip,
+                           float* __restrict__ out, int ld_out, int round_tf32, int center,
+                           int adjoint_scale, const float* __restrict__ row_mask, int row) {
   extern __shared__ float2 sm[];
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
   float* spec = reinterpret_cast<float*>(sm + 2 * n + (n >> 1));
 
-  const int row = blockIdx.x;
   const int bi = row / frames;
   const int f = row - bi * frames;
   const int nb = (n >> 1) + 1;
@@ -132,13 +135,44 @@ __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio
   }
 }
 
-__global__ void irfft_frames_kernel(const float* __restrict__ packed, int ld, int n, int logn,
-                                    float* __restrict__ frames_out) {
+__global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
+                            int hop, int frames, int mode, const float* __restrict__ pre,
+                            const float* __restrict__ fb, int n_filt, float log_clip,
+                            float* __restrict__ out, int ld_out, int round_tf32, int center,
+                            int adjoint_scale, const float* __restrict__ row_mask) {
+  stft_frame(audio, T, ld_audio, n, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out,
+             round_tf32, center, adjoint_scale, row_mask, blockIdx.x);
+}
+
+// Up to 4 packed-mode STFTs / inverse transforms of the SAME signal batch in one launch (the three
+// branch resolutions of AudioConvNeXt, modules.py:699-719): blockIdx.x ranges select the problem;
+// the block size is that of the largest transform (smaller ones leave threads idle).
+struct SpecGroupArgs {
+  const float* in[4];     // stft: audio (B, ld_in) ; irfft: packed rows
+  float* out[4];
+  int n[4], logn[4], hop[4], frames[4], ld_in[4], ld_out[4];
+  int row_begin[5];
+  int np, T, round_tf32;
+};
+
+__global__ void stft_group_kernel(const __grid_constant__ SpecGroupArgs g) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < g.np && (int)blockIdx.x >= g.row_begin[i]) pi = i;
+  pdl_wait();
+  pdl_launch();
+  stft_frame(g.in[pi], g.T, g.ld_in[pi], g.n[pi], g.logn[pi], g.hop[pi], g.frames[pi], F2G_SPEC_PACKED,
+             nullptr, nullptr, 0, 0.f, g.out[pi], g.ld_out[pi], g.round_tf32, 1, 0, nullptr,
+             blockIdx.x - g.row_begin[pi]);
+}
+
+F2G_DEVINL void irfft_frame(const float* __restrict__ packed, int ld, int n, int logn,
+                            float* __restrict__ frames_out, int row) {
   extern __shared__ float2 sm[];
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
-  const int row = blockIdx.x;
   const int nb = (n >> 1) + 1;
   const float* p = packed + (size_t)row * ld;
 
@@ -161,6 +195,21 @@ __global__ void irfft_frames_kernel(const float* __restrict__ packed, int ld, in
   float* o = frames_out + (size_t)row * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     o[i] = y[i].x * inv_n * hann_from_tw(tw, i, n);
+}
+
+__global__ void irfft_frames_kernel(const float* __restrict__ packed, int ld, int n, int logn,
+                                    float* __restrict__ frames_out) {
+  irfft_frame(packed, ld, n, logn, frames_out, blockIdx.x);
+}
+
+__global__ void irfft_group_kernel(const __grid_constant__ SpecGroupArgs g) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < g.np && (int)blockIdx.x >= g.row_begin[i]) pi = i;
+  pdl_wait();
+  pdl_launch();
+  irfft_frame(g.in[pi], g.ld_in[pi], g.n[pi], g.logn[pi], g.out[pi], blockIdx.x - g.row_begin[pi]);
 }
 
 struct OlaArgs {
@@ -366,6 +415,77 @@ extern "C" int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_ff
                         int ld_out, int round_tf32, void* stream) {
   return stft_launch(audio, B, T, ld_audio, n_fft, hop, mode, pre, fb, n_filt, log_clip, out, ld_out,
                      round_tf32, 1, 0, nullptr, stream);
+}
+
+static int spec_group_fill(SpecGroupArgs& g, const F2GSpecProblem* probs, int np, const char* who,
+                           int* max_n) {
+  if (np < 1 || np > 4) {
+    set_error("%s: %d problems (1..4)", who, np);
+    return F2G_EINVAL;
+  }
+  memset(&g, 0, sizeof(g));
+  g.np = np;
+  int rows = 0;
+  *max_n = 0;
+  for (int i = 0; i < np; ++i) {
+    const F2GSpecProblem& p = probs[i];
+    const int logn = ilog2_exact(p.n_fft);
+    if (logn < 5 || p.n_fft > 2048) {
+      set_error("%s: n_fft=%d must be a power of two in [32, 2048]", who, p.n_fft);
+      return F2G_EINVAL;
+    }
+    g.in[i] = p.in; g.out[i] = p.out; g.n[i] = p.n_fft; g.logn[i] = logn; g.hop[i] = p.hop;
+    g.frames[i] = p.frames; g.ld_in[i] = p.ld_in; g.ld_out[i] = p.ld_out;
+    g.row_begin[i] = rows;
+    rows += p.rows;
+    if (p.n_fft > *max_n) *max_n = p.n_fft;
+  }
+  for (int i = np; i <= 4; ++i) g.row_begin[i] = rows;
+  return 0;
+}
+
+extern "C" int f2g_stft_group(const F2GSpecProblem* probs, int np, int B, int T, int round_tf32,
+                              void* stream) {
+  SpecGroupArgs g;
+  int max_n = 0;
+  if (int rc = spec_group_fill(g, probs, np, "f2g_stft_group", &max_n)) return rc;
+  for (int i = 0; i < np; ++i) {
+    if (probs[i].n_fft / 2 >= T) {
+      set_error("f2g_stft_group: signal too short (n_fft=%d, T=%d)", probs[i].n_fft, T);
+      return F2G_EINVAL;
+    }
+    g.frames[i] = 1 + T / probs[i].hop;
+    if (probs[i].rows != B * g.frames[i]) {
+      set_error("f2g_stft_group: rows=%d != B*frames=%d", probs[i].rows, B * g.frames[i]);
+      return F2G_EINVAL;
+    }
+  }
+  g.T = T;
+  g.round_tf32 = round_tf32;
+  const int threads = max_n / 2 < 32 ? 32 : max_n / 2;
+  const size_t smem = (size_t)(2 * max_n + max_n / 2) * sizeof(float2) + (max_n / 2 + 1) * sizeof(float);
+  cudaError_t le = launch_pdl(stft_group_kernel, dim3(g.row_begin[np]), dim3(threads), smem,
+                              static_cast<cudaStream_t>(stream), g);
+  if (le != cudaSuccess) {
+    set_error("f2g_stft_group launch: %s", cudaGetErrorString(le));
+    return (int)le;
+  }
+  return check_launch("f2g_stft_group");
+}
+
+extern "C" int f2g_irfft_group(const F2GSpecProblem* probs, int np, void* stream) {
+  SpecGroupArgs g;
+  int max_n = 0;
+  if (int rc = spec_group_fill(g, probs, np, "f2g_irfft_group", &max_n)) return rc;
+  const int threads = max_n / 2 < 32 ? 32 : max_n / 2;
+  const size_t smem = (size_t)(2 * max_n + max_n / 2) * sizeof(float2);
+  cudaError_t le = launch_pdl(irfft_group_kernel, dim3(g.row_begin[np]), dim3(threads), smem,
+                              static_cast<cudaStream_t>(stream), g);
+  if (le != cudaSuccess) {
+    set_error("f2g_irfft_group launch: %s", cudaGetErrorString(le));
+    return (int)le;
+  }
+  return check_launch("f2g_irfft_group");
 }
 
 extern "C" int f2g_istft_bwd_spec(const float* gs, int B, int Lp, int n_fft, int hop,

@@ -234,8 +234,8 @@ class InferencePlan:
     def process_model(self, t_dev: Tensor) -> None:
         """x_audio, cond (cp) -> per-branch windowed iSTFT frames (w.fr).  t_dev: (B,) device."""
         pk, B, T, Fm = self.pk, self.B, self.T, self.Fm
-        for bw, w in zip(pk.branches, self.br):
-            L.stft(self.x_audio, B, T, T, bw.n_fft, bw.hop, L.SPEC_PACKED, w.pin, bw.ldp, round_tf32=1)
+        L.stft_group([(self.x_audio, w.pin, bw.n_fft, bw.hop, w.F, w.R, T, bw.ldp)
+                      for bw, w in zip(pk.branches, self.br)], B, T, round_tf32=1)
         L.gemm_group([L.gemm_desc(w.pin.data_ptr(), bw.Win.data_ptr(), w.x.data_ptr(), w.R, bw.C,
                                   bw.nin, bw.ldp, bw.ldp, bw.C, bias=bw.dec.in_proj.bias.data_ptr())
                       for bw, w in zip(pk.branches, self.br)])
@@ -270,8 +270,8 @@ class InferencePlan:
                                   bw.C, bw.C, bw.C, bw.ldp, bias=bw.dec.out_proj.bias.data_ptr(),
                                   row_scale=L.ptr(w.mask))
                       for bw, w in zip(pk.branches, self.br)])
-        for bw, w in zip(pk.branches, self.br):
-            L.irfft_frames(w.pout, w.R, bw.ldp, bw.n_fft, w.fr)
+        L.irfft_group([(w.pout, w.fr, bw.n_fft, 0, 0, w.R, bw.ldp, bw.n_fft)
+                       for bw, w in zip(pk.branches, self.br)])
 
     def combine(self, out: Tensor, euler: bool, t: float, dt: float, clamp: bool,
                 weight: Optional[Tensor] = None) -> None:

@@ -89,6 +89,19 @@ int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop,
              const float* pre, const float* fb, int n_filt, float log_clip, float* out,
              int ld_out, int round_tf32, void* stream);
 
+/* Grouped forms: up to 4 resolutions of the same (B, T) batch in one launch (the branch STFTs /
+ * inverse transforms of AudioConvNeXt.forward, modules.py:699-719).
+ *   stft  : in = audio (B, ld_in), out = packed rows (rows = B * (1 + T/hop), ld_out), PACKED mode
+ *   irfft : in = packed rows (rows, ld_in), out = windowed frames (rows, n_fft); hop/frames unused */
+typedef struct F2GSpecProblem {
+  const float* in;
+  float* out;
+  int n_fft, hop, frames, rows, ld_in, ld_out;
+} F2GSpecProblem;
+int f2g_stft_group(const F2GSpecProblem* problems, int n_problems, int B, int T, int round_tf32,
+                   void* stream);
+int f2g_irfft_group(const F2GSpecProblem* problems, int n_problems, void* stream);
+
 /* per-row DC removal + peak normalisation constants (discriminators.py:187-190):
  * pre[b] = (mean_t x, 0.8 / (max_t |x - mean| + 1e-9)). */
 int f2g_dc_peak(const float* audio, int B, int T, int ld_audio, float* pre, void* stream);
