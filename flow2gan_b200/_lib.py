@@ -36,6 +36,7 @@ class F2GGemm(C.Structure):
         ("ld_res", _i), ("ld_gate", _i),
         ("act", _i), ("leaky", _f), ("alpha", _f),
         ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i), ("split_k", _i),
+        ("a_seg_len", _i), ("a_seg_shift", _i), ("a_rows", _i),
     ]
 
 
@@ -117,6 +118,7 @@ _SIGS = {
     "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_conv_w_pack": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
+    "f2g_pad2d": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _ll, _i, _fp, _fp], _i),
     "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
 }
 
@@ -143,7 +145,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 1:
+        if lib.f2g_abi_version() != 2:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -186,7 +188,7 @@ def stream() -> int:
 def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
               act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
-              ld_pre=0, split_k=1) -> F2GGemm:
+              ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -199,6 +201,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.round_tf32, d.accumulate = round_tf32, accumulate
     d.c_pre, d.ld_pre = c_pre, ld_pre
     d.split_k = split_k
+    d.a_seg_len, d.a_seg_shift, d.a_rows = a_seg_len, a_seg_shift, a_rows
     return d
 
 
@@ -395,6 +398,11 @@ def im2col2d(x_ptr, geom, col, round_tf32=1):
 
 def col2im2d(dcol, geom, dx_ptr, accumulate=0):
     _check(lib().f2g_col2im2d(ptr(dcol), C.byref(geom), dx_ptr, accumulate, stream()))
+
+
+def pad2d(x_ptr, Nb, H, W, Cc, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, slack, out, round_tf32=1):
+    _check(lib().f2g_pad2d(x_ptr, Nb, H, W, Cc, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, slack, round_tf32,
+                           ptr(out), stream()))
 
 
 def conv_w_pack(src, Co, Ci, taps, Co_pad, ld, dst, direction):

@@ -112,6 +112,32 @@ __global__ void col2im2d_kernel(const float* __restrict__ dcol, ConvGeom g, floa
   }
 }
 
+
+// Zero-padded (and TF32-rounded) copy feeding the windowed convs: the GEMM then reads its A
+// operand straight from this buffer through an overlapping-row tensor map, so the im2col
+// matrix (kh*kw / (sh*sw) times larger) is never written.  One thread per 4 channels.
+__global__ void pad2d_kernel(const float* __restrict__ x, int Nb, int H, int W, int C4, long long pitch_n,
+                             long long pitch_h, long long pitch_w, int Hl, int Wp, int ph, int pw,
+                             long long total4, long long body4, int round_tf32, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < body4) {
+      const int cq = (int)(i % C4);
+      long long t = i / C4;
+      const int w = (int)(t % Wp) - pw;
+      t /= Wp;
+      const int h = (int)(t % Hl) - ph;
+      const int n = (int)(t / Hl);
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        v = *reinterpret_cast<const float4*>(x + n * pitch_n + h * pitch_h + w * pitch_w + (cq << 2));
+        if (round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+      }
+    }
+    *reinterpret_cast<float4*>(out + (i << 2)) = v;
+  }
+}
+
 // dir 0: param (Co, Ci, kh*kw) -> packed (Co_pad rows, ld), TF32 rounded, padding zeroed
 // dir 1: packed gradient -> param layout (no rounding)
 __global__ void conv_w_pack_kernel(const float* __restrict__ src, int Co, int Ci, int taps, int Co_pad,
@@ -185,6 +211,23 @@ extern "C" int f2g_col2im2d(const float* dcol, const F2GConv2d* p, float* dx, in
   if (vec) col2im2d_kernel<true><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
   else col2im2d_kernel<false><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
   return check_launch("f2g_col2im2d");
+}
+
+extern "C" int f2g_pad2d(const float* x, int Nb, int H, int W, int C, long long pitch_n, long long pitch_h,
+                         long long pitch_w, int Hl, int Wp, int ph, int pw, long long slack, int round_tf32,
+                         float* out, void* stream) {
+  if ((C & 3) || (pitch_n & 3) || (pitch_h & 3) || (pitch_w & 3) || (slack & 3) || slack < 0 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || Hl < H + ph ||
+      Wp < W + pw) {
+    set_error("f2g_pad2d: need C, pitches, slack multiples of 4, 16B-aligned pointers, Hl >= H+ph, Wp >= W+pw "
+              "(C=%d Hl=%d H=%d ph=%d Wp=%d W=%d pw=%d)", C, Hl, H, ph, Wp, W, pw);
+    return F2G_EINVAL;
+  }
+  const long long body4 = (long long)Nb * Hl * Wp * (C >> 2);
+  const long long total4 = body4 + (slack >> 2);
+  pad2d_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, Nb, H, W, C >> 2, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, total4, body4, round_tf32, out);
+  return check_launch("f2g_pad2d");
 }
 
 extern "C" int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int Co_pad, int ld, float* dst,

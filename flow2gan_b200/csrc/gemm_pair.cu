@@ -54,6 +54,7 @@ struct alignas(64) PProblem {
   int split_k, kb_total, kb_per;
   int act, round_tf32, accumulate;
   float leaky, alpha;
+  int seg_len, seg_shift;   // windowed A operand (F2GGemm::a_seg_len / a_seg_shift), 0 = plain
 };
 
 struct alignas(64) PGroup {
@@ -286,12 +287,27 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
           const int kc = kb * PBK;                      // beyond K: TMA zero-fills
+          // windowed A (implicit im2col): contraction segment s = one kernel row, which lives
+          // seg_shift buffer rows further; within a segment consecutive rows overlap
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < PBM / 32; ++j)
-              tma_load_2d_cg2(sa + j * 4096, &pr.map_a, lbar, m_cta + 32 * j, kc);
+            for (int j = 0; j < PBM / 32; ++j) {
+              int mm = m_cta + 32 * j, kk = kc;
+              if (pr.seg_len) {
+                const int s = mm / pr.seg_len;
+                mm -= s * pr.seg_len;
+                kk += s * pr.seg_shift;
+              }
+              tma_load_2d_cg2(sa + j * 4096, &pr.map_a, lbar, mm, kk);
+            }
           } else {
-            tma_load_2d_cg2(sa, &pr.map_a, lbar, kc, m_cta);
+            int kca = kc, ma = m_cta;
+            if (pr.seg_len) {
+              const int s = kc / pr.seg_len;
+              kca -= s * pr.seg_len;
+              ma += s * pr.seg_shift;
+            }
+            tma_load_2d_cg2(sa, &pr.map_a, lbar, kca, ma);
           }
           if (B_MN) {
             for (int j = 0; j < (bhalf >> 5); ++j)
@@ -752,9 +768,19 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     PProblem& p = g.p[oi];
     const int bn = pick_bn(d.N, b_mn != 0);
     int rc;
-    rc = a_mn ? pair_encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32, true)
-              : pair_encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, PBM, false);
+    if (d.a_seg_len && ((d.a_seg_len & 31) || d.a_rows <= 0)) {
+      set_error("windowed gemm operand: a_seg_len=%d must be a multiple of 32 and a_rows=%d > 0",
+                d.a_seg_len, d.a_rows);
+      return F2G_EINVAL;
+    }
+    if (d.a_seg_len)
+      rc = a_mn ? pair_encode_2d(&p.map_a, d.a, d.a_seg_len, d.a_rows, d.lda, 32, true)
+                : pair_encode_2d(&p.map_a, d.a, d.a_seg_len, d.a_rows, d.lda, PBM, false);
+    else
+      rc = a_mn ? pair_encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32, true)
+                : pair_encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, PBM, false);
     if (rc) return rc;
+    p.seg_len = d.a_seg_len; p.seg_shift = d.a_seg_shift;
     rc = b_mn ? pair_encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
               : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false);
     if (rc) return rc;

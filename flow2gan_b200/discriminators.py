@@ -4,12 +4,17 @@ channel-last tensors: every Conv2d = im2col gather + tcgen05 TF32 GEMM (+bias+Le
 the epilogue); backward = act adjoint + split-K wgrad GEMM + dgrad GEMM + col2im (csrc/conv.cu)."""
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor, nn
 
 from . import _lib as L
+from . import convwin
+
+# F2G_CONV_IM2COL=1 forces the gather (im2col) path everywhere -- A/B testing only
+_USE_WINDOWED = os.environ.get("F2G_CONV_IM2COL", "0") != "1"
 
 
 def _ceil4(n: int) -> int:
@@ -79,12 +84,22 @@ class _Conv2dCLFn(torch.autograd.Function):
         return gx, gW, gb, None, None, None, None, None
 
 
-def conv2d_cl(x: Tensor, conv: nn.Conv2d, leaky: Optional[float], train_weights: bool = True) -> Tensor:
+def conv2d_cl(x: Tensor, conv: nn.Conv2d, leaky: Optional[float], train_weights: bool = True,
+              swap_hw: bool = False) -> Tensor:
+    """Channel-last Conv2d (+LeakyReLU).  `swap_hw`: x is laid out (Nb, W, H, C) -- the module's
+    kernel / stride / padding pairs are applied with H and W exchanged (DiscriminatorP runs its
+    (k, 1) convs along the contiguous axis of a (B*period, 1, T/period, C) tensor).  Convs the
+    windowed path supports (C % 32 == 0, unit H stride) never materialise im2col (convwin.py)."""
     w, b = conv.weight, conv.bias
     if not train_weights:
         w, b = w.detach(), b.detach()
     sh, sw = conv.stride
     ph, pw = conv.padding
+    if swap_hw:
+        w = w.transpose(2, 3)
+        sh, sw, ph, pw = sw, sh, pw, ph
+    if _USE_WINDOWED and convwin.supports(x.shape[3], w.shape[2], w.shape[3], sh, sw):
+        return convwin.conv2d_win(x, w, b, sw, ph, pw, leaky)
     return _Conv2dCLFn.apply(x, w, b, sh, sw, ph, pw, leaky)
 
 
@@ -107,19 +122,27 @@ class DiscriminatorP(nn.Module):
         self.lrelu_slope = lrelu_slope
 
     def forward(self, x: Tensor, train_weights: bool = True) -> Tuple[Tensor, List[Tensor]]:
-        """x (B, T) -> (score (B, -1), fmap list); feature maps are channel-last (B, H, p, C)."""
+        """x (B, T) -> (score (B, -1), fmap list); feature maps are channel-last (B, H, p, C) views.
+        Internally the tensor is kept period-major, (B*p, 1, T/p, C): the (k, 1) convs then slide
+        along the contiguous axis and take the windowed (no im2col) path."""
         b, t = x.shape
-        if t % self.period != 0:
-            n_pad = self.period - (t % self.period)
+        p = self.period
+        if t % p != 0:
+            n_pad = p - (t % p)
             x = torch.nn.functional.pad(x.unsqueeze(1), (0, n_pad), "reflect").squeeze(1)
             t += n_pad
-        h = x.reshape(b, t // self.period, self.period, 1)
+        h = x.reshape(b, t // p, p).transpose(1, 2).reshape(b * p, 1, t // p, 1)
+
+        def as_bhpc(v: Tensor) -> Tensor:
+            return v.unflatten(0, (b, p)).squeeze(2).permute(0, 2, 1, 3)
+
         fmap = []
         for i, l in enumerate(self.convs):
-            h = conv2d_cl(h, l, self.lrelu_slope, train_weights)
+            h = conv2d_cl(h, l, self.lrelu_slope, train_weights, swap_hw=True)
             if i > 0:
-                fmap.append(h)
-        h = conv2d_cl(h, self.conv_post, None, train_weights)
+                fmap.append(as_bhpc(h))
+        h = conv2d_cl(h, self.conv_post, None, train_weights, swap_hw=True)
+        h = as_bhpc(h)
         fmap.append(h)
         return h.reshape(b, -1), fmap
 

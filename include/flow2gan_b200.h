@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 1
+#define F2G_ABI_VERSION 2
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -68,6 +68,15 @@ typedef struct F2GGemm {
   int ld_pre;
   int split_k;  /* > 1: K is split over that many CTAs per tile, results atomically added into a
                    pre-zeroed C (plain epilogue only) -- used by weight-gradient GEMMs with huge K */
+  /* Windowed ("implicit im2col") A operand: A is an OVERLAPPING-row view of a padded channel-last
+   * activation buffer -- row r starts at a + r*lda and is a_seg_len floats long (lda < a_seg_len:
+   * consecutive output pixels share taps), and the contraction index is cut into segments of
+   * a_seg_len (one per kernel row); segment s reads buffer row r + s*a_seg_shift.  Rows outside
+   * [0, a_rows) read as zero (TMA out-of-bounds fill).  a_seg_len == 0: plain operand.
+   *   a_mn = 0: element (m, k) = a[(m + (k / a_seg_len) * a_seg_shift) * lda + k % a_seg_len]
+   *   a_mn = 1: element (m, k) = a[(k + (m / a_seg_len) * a_seg_shift) * lda + m % a_seg_len]
+   * a_seg_len must be a multiple of 32.  CTA-pair kernel only (max M > 128). */
+  int a_seg_len, a_seg_shift, a_rows;
 } F2GGemm;
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
@@ -266,6 +275,12 @@ typedef struct F2GConv2d {
 int f2g_im2col2d(const float* x, const F2GConv2d* geom, float* col, int round_tf32, void* stream);
 /* adjoint of im2col2d: dx (+)= sum of the taps that read each input element */
 int f2g_col2im2d(const float* dcol, const F2GConv2d* geom, float* dx, int accumulate, void* stream);
+/* Zero-padded, TF32-rounded copy for the windowed convs: out is (Nb, Hl, Wp, C) contiguous plus
+ * `slack` trailing floats (zeroed); out[n, h, w, :] = x[n, h-ph, w-pw, :] inside, 0 outside.
+ * x element (n, h, w, c) at x[n*pitch_n + h*pitch_h + w*pitch_w + c].  C % 4 == 0. */
+int f2g_pad2d(const float* x, int Nb, int H, int W, int C, long long pitch_n, long long pitch_h,
+              long long pitch_w, int Hl, int Wp, int ph, int pw, long long slack, int round_tf32,
+              float* out, void* stream);
 /* dir 0: (Co, Ci, taps) parameter -> (Co_pad, ld) GEMM operand [co][tap*Ci + ci], TF32-rounded;
  * dir 1: packed gradient -> parameter layout. */
 int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int Co_pad, int ld, float* dst, int dir,
