@@ -78,23 +78,24 @@ class GradBuckets:
             if flat is None or flat.device != bucket[0].device:
                 flat = torch.empty(n, device=bucket[0].device, dtype=torch.float32)
                 self._flat[bi] = flat
-            off = 0
+            # pack / unpack with one multi-tensor copy each (hundreds of small parameters per bucket)
+            views, off = [], 0
             for p in bucket:
                 m = p.numel()
-                if p.grad is None:
-                    flat[off:off + m].zero_()
-                else:
-                    flat[off:off + m].copy_(p.grad.reshape(-1))
+                views.append(flat[off:off + m].view_as(p))
                 off += m
+            have = [i for i, p in enumerate(bucket) if p.grad is not None]
+            for i, p in enumerate(bucket):
+                if p.grad is None:
+                    views[i].zero_()
+            if have:
+                torch._foreach_copy_([views[i] for i in have], [bucket[i].grad for i in have])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                m = p.numel()
+            flat.mul_(1.0 / world)
+            for i, p in enumerate(bucket):
                 if p.grad is None:
-                    p.grad = flat[off:off + m].view_as(p).clone()
-                else:
-                    p.grad.copy_(flat[off:off + m].view_as(p))
-                off += m
+                    p.grad = views[i].clone()
+            if have:
+                torch._foreach_copy_([bucket[i].grad for i in have], [views[i] for i in have])
             total += n * 4
         return total

@@ -1,7 +1,14 @@
 #!/bin/bash
+# 2-GPU bench line (replica inference + data-parallel GAN train pair with NCCL gradient all-reduce)
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
-nvidia-smi -L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-tail -5 gpurun_out/bench_n2.err
-cat gpurun_out/bench_n2.json | cut -c1-1500
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>&1 | tail -2 | cut -c1-600
+N=${1:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+tail -5 gpurun_out/bench_n$N.err
+python - $N <<'P'
+import json, sys
+for l in open('gpurun_out/bench_n%s.json' % sys.argv[1]):
+    if l.startswith('{'):
+        d = json.loads(l)
+        print('ms/step %.3f value %.1fM e2e %.1fM' % (d['ms_per_step'], d['value']/1e6, d['e2e']['value']/1e6))
+        print('train', d.get('gan_train'))
+P
