@@ -37,6 +37,7 @@ class F2GGemm(C.Structure):
         ("act", _i), ("leaky", _f), ("alpha", _f),
         ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i), ("split_k", _i),
         ("a_seg_len", _i), ("a_seg_shift", _i), ("a_rows", _i),
+        ("ab_f16", _i), ("c_f16", _i),
     ]
 
 
@@ -50,7 +51,7 @@ class F2GBlockPre(C.Structure):
                 ("row_mask", _fp), ("cond", _fp), ("tscale", _fp), ("out", _fp), ("conv_out", _fp),
                 ("inv_rms_out", _fp),
                 ("B", _i), ("T", _i), ("C", _i), ("ld_x", _i), ("ld_cond", _i), ("cond_T", _i),
-                ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i)]
+                ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i), ("out_f16", _i)]
 
 
 class F2GSpecProblem(C.Structure):
@@ -145,7 +146,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 2:
+        if lib.f2g_abi_version() != 3:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -174,7 +175,7 @@ def _check(rc: int) -> None:
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
-    assert t.is_cuda and t.dtype in (torch.float32, torch.int32), (t.device, t.dtype)
+    assert t.is_cuda and t.dtype in (torch.float32, torch.int32, torch.float16), (t.device, t.dtype)
     return t.data_ptr()
 
 
@@ -188,7 +189,7 @@ def stream() -> int:
 def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
               act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
-              ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0) -> F2GGemm:
+              ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0, ab_f16=0, c_f16=0) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -202,6 +203,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.c_pre, d.ld_pre = c_pre, ld_pre
     d.split_k = split_k
     d.a_seg_len, d.a_seg_shift, d.a_rows = a_seg_len, a_seg_shift, a_rows
+    d.ab_f16, d.c_f16 = ab_f16, c_f16
     return d
 
 
@@ -270,10 +272,9 @@ def biasnorm(x, rows, Cc, ld, bias, log_scale, y, ld_y, inv_out=None):
 
 def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
               factor, zero_row, tscale, ld_ts, out, ld_out, conv_out=None, inv_out=None):
-    _check(lib().f2g_block_pre(ptr(x), B, T, Cc, ld_x, ptr(dw_wT), ptr(dw_b), ptr(bn_bias),
-                               ptr(bn_log_scale), ptr(row_mask), ptr(cond), ld_cond, cond_T, factor,
-                               zero_row, ptr(tscale), ld_ts, ptr(out), ld_out, ptr(conv_out),
-                               ptr(inv_out), stream()))
+    block_pre_group([block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond,
+                                    ld_cond, cond_T, factor, zero_row, tscale, ld_ts, out, ld_out, conv_out,
+                                    inv_out)])
 
 
 def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
@@ -284,6 +285,7 @@ def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_ma
     d.conv_out, d.inv_rms_out = ptr(conv_out), ptr(inv_out)
     d.B, d.T, d.C, d.ld_x, d.ld_cond, d.cond_T = B, T, Cc, ld_x, ld_cond, cond_T
     d.factor, d.zero_row, d.ld_ts, d.ld_out = factor, zero_row, ld_ts, ld_out
+    d.out_f16 = int(out.dtype == torch.float16)
     return d
 
 

@@ -172,7 +172,12 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     float4 z = make_float4(acc[s].x * inv, acc[s].y * inv, acc[s].z * inv, acc[s].w * inv);
     z.x += cv[s].x; z.y += cv[s].y; z.z += cv[s].z; z.w += cv[s].w;
     z.x *= 1.f + sc.x; z.y *= 1.f + sc.y; z.z *= 1.f + sc.z; z.w *= 1.f + sc.w;
-    st4(P.out + (rb + t) * P.ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
+    if (P.out_f16) {   // operand of a kind::f16 GEMM: same 11-bit significand as the TF32 rounding
+      __half* o = reinterpret_cast<__half*>(P.out) + (rb + t) * (size_t)P.ld_out + c;
+      *reinterpret_cast<uint2*>(o) = pack_half4(z);
+    } else {
+      st4(P.out + (rb + t) * P.ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
+    }
   }
 }
 
@@ -352,6 +357,7 @@ extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, cons
   p.ld_cond = ld_cond; p.cond_T = cond_T; p.factor = factor; p.zero_row = zero_row;
   p.tscale = tscale; p.ld_ts = ld_ts; p.out = out; p.ld_out = ld_out; p.conv_out = conv_out;
   p.inv_rms_out = inv_rms_out;
+  p.out_f16 = 0;
   return f2g_block_pre_group(&p, 1, stream);
 }
 

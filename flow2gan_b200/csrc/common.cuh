@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -34,6 +35,18 @@ F2G_DEVINL float tf32_rna(float x) {
 // are not preserved -- only used on GEMM epilogue outputs.
 F2G_DEVINL float tf32_rna_fast(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// fp32 -> fp16 pair, round-to-nearest-even, clamped to the finite fp16 range (operands of the
+// kind::f16 GEMMs: an overflow saturates instead of poisoning the contraction with Inf)
+F2G_DEVINL uint32_t pack_half2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+F2G_DEVINL uint2 pack_half4(float4 v) {
+  return make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
 }
 
 F2G_DEVINL float warp_sum(float v) {
@@ -217,6 +230,14 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int m, int n, int a_mn_major
   d |= 2u << 10;                       // b_format = TF32
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+// kind::f16 with fp16 operands (a_format = b_format = F16 = 0), fp32 accumulate, K-major
+__host__ __device__ inline uint32_t make_idesc_f16(int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format = F32
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)(m >> 4) << 24;
   return d;

@@ -55,6 +55,7 @@ struct alignas(64) PProblem {
   int act, round_tf32, accumulate;
   float leaky, alpha;
   int seg_len, seg_shift;   // windowed A operand (F2GGemm::a_seg_len / a_seg_shift), 0 = plain
+  int c_f16;                // C stored as fp16 (F2GGemm::c_f16)
 };
 
 struct alignas(64) PGroup {
@@ -147,6 +148,15 @@ F2G_DEVINL void umma_tf32_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+F2G_DEVINL void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs
 F2G_DEVINL void umma_commit_cg2(uint64_t* bar) {
   const uint16_t mask = 3;
@@ -217,9 +227,32 @@ F2G_DEVINL void epi_fast_chunk(const float* __restrict__ sl, float* __restrict__
   }
 }
 
-template <int A_MN, int B_MN, int EPI>
+// F16 = 1: fp16 operands (kind::f16, 64 elements per 128 B swizzle row, K = 16 per instruction);
+// the byte geometry of the pipeline (stages, descriptors, 32 B K-steps) is the TF32 one.
+// BIAS_ACT chunk with an fp16 destination (the hidden activation of a ConvNeXt block, which only
+// the next GEMM reads): x = prelu(alpha*acc + bias) -> RN fp16, one 8-byte store per row quad.
+template <bool FULL>
+F2G_DEVINL void epi_fast_chunk_h(const float* __restrict__ sl, __half* __restrict__ cp, size_t cstep,
+                                 int rows_left, float alpha, float4 bias4, float4 slope4) {
+  float4 xv[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) xv[rr] = *reinterpret_cast<const float4*>(sl + rr * (4 * 36));
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    float4 x;
+    x.x = fmaf(xv[rr].x, alpha, bias4.x); x.y = fmaf(xv[rr].y, alpha, bias4.y);
+    x.z = fmaf(xv[rr].z, alpha, bias4.z); x.w = fmaf(xv[rr].w, alpha, bias4.w);
+    x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;
+    x.z = x.z > 0.f ? x.z : x.z * slope4.z; x.w = x.w > 0.f ? x.w : x.w * slope4.w;
+    if (FULL || rr * 4 < rows_left) *reinterpret_cast<uint2*>(cp + rr * cstep) = pack_half4(x);
+  }
+}
+
+template <int A_MN, int B_MN, int EPI, int F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ PGroup g) {
+  static_assert(!F16 || (!A_MN && !B_MN), "fp16 operands are K-major only");
+  constexpr int KELEM = F16 ? 64 : PBK;        // contraction elements per pipeline stage
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("f2g gemm_pair: dynamic smem base not 1024B aligned\n");
@@ -286,7 +319,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           uint8_t* sb = sa + P_A_BYTES;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          const int kc = kb * PBK;                      // beyond K: TMA zero-fills
+          const int kc = kb * KELEM;                    // beyond K: TMA zero-fills
           // windowed A (implicit im2col): contraction segment s = one kernel row, which lives
           // seg_shift buffer rows further; within a segment consecutive rows overlap
           if (A_MN) {
@@ -338,7 +371,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
         const PTile tc = pdecode(g, tile);
-        const uint32_t idesc = make_idesc_tf32(2 * PBM, g.p[tc.prob].bn, A_MN, B_MN);
+        const uint32_t idesc = F16 ? make_idesc_f16(2 * PBM, g.p[tc.prob].bn)
+                                   : make_idesc_tf32(2 * PBM, g.p[tc.prob].bn, A_MN, B_MN);
         mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + ab * 256;
@@ -350,7 +384,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           for (int k = 0; k < PBK / 8; ++k) {
             const uint64_t adesc = adesc0 + soff + (uint32_t)((k * a_kstep) >> 4);
             const uint64_t bdesc = bdesc0 + soff + (uint32_t)((k * b_kstep) >> 4);
-            umma_tf32_cg2(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
+            if (F16) umma_f16_cg2(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
+            else umma_tf32_cg2(tmem_d, adesc, bdesc, idesc, (kb > tc.kb0 || k) ? 1u : 0u);
           }
           umma_commit_cg2(&empty_bar[stage]);     // frees this smem slot in both CTAs
           if (++stage == P_STAGES) {
@@ -398,6 +433,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       const bool do_round = pr.round_tf32 != 0, do_acc = pr.accumulate != 0;
       const float alpha = pr.alpha;
       const int split_k = pr.split_k;
+      const bool c16 = F16 && pr.c_f16 != 0;       // fp16 destination (never in the TF32 instantiations)
       const uint32_t radd = do_round ? 0x1000u : 0u, rmask = do_round ? 0xffffe000u : 0xffffffffu;
       const bool vec_c = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
       const bool vec_res = !res_p || (((ld_res & 3) == 0) && ((reinterpret_cast<uintptr_t>(res_p) & 15) == 0));
@@ -443,7 +479,15 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         const float4 rsc4 = *reinterpret_cast<const float4*>(sparam + 512 + c0 + 4 * cg);
         const bool chunk_full = vec_all && (n0 + c0 + 32 <= N) && split_k == 1;   // warp-uniform
 
-        if (EPI != PEPI_GENERIC && chunk_full) {
+        if (F16 && EPI == PEPI_BIAS_ACT && chunk_full && c16) {
+          const float* sl = scratch + rsub * 36 + 4 * cg;
+          __half* hp = reinterpret_cast<__half*>(cbase) + (size_t)(row_base + rsub) * ldc + col;
+          if (rows >= 32) epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4);
+          else epi_fast_chunk_h<false>(sl, hp, (size_t)4 * ldc, rows - rsub, alpha, bias4, slope4);
+          __syncwarp();
+          continue;
+        }
+        if (EPI != PEPI_GENERIC && chunk_full && !c16) {
           const size_t r0 = (size_t)(row_base + rsub);
           const float* sl = scratch + rsub * 36 + 4 * cg;
           float* cp = cbase + r0 * ldc + col;
@@ -510,6 +554,11 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               const float rs = __ldg(rowsc_p + row);
               x[0] *= rs; x[1] *= rs; x[2] *= rs; x[3] *= rs;
             }
+            if (c16) {
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(cbase) + (size_t)row * ldc + col) =
+                  pack_half4(make_float4(x[0], x[1], x[2], x[3]));
+              continue;
+            }
             float* dst = cbase + (size_t)row * ldc + col;
             if (do_acc) {
               const float4 t = *reinterpret_cast<const float4*>(dst);
@@ -536,6 +585,11 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               if (gate_p) x *= (__ldg(gate_p + (size_t)row * ld_gate + col + e) > 0.f ? 1.f : slope[e]);
               if (res_p) x = fmaf(rsc[e], __ldg(res_p + (size_t)row * ld_res + col + e), x);
               if (rowsc_p) x *= __ldg(rowsc_p + row);
+              if (c16) {
+                reinterpret_cast<__half*>(cbase)[(size_t)row * ldc + col + e] =
+                    __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+                continue;
+              }
               float* dst = cbase + (size_t)row * ldc + col + e;
               if (do_acc) x += *dst;
               *dst = do_round ? tf32_rna_fast(x) : x;
@@ -590,20 +644,22 @@ static PEncodeTiledFn pair_encode_fn() {
 // 2-D fp32 tensor map; dims/strides innermost first; box = {32, box_rows}.  The row pitch may be
 // SMALLER than the row length (overlapping rows: the implicit im2col view of a strided conv).
 static int pair_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
-                          uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major) {
+                          uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major, bool f16 = false) {
   PEncodeTiledFn fn = pair_encode_fn();
   if (!fn) return F2G_EDRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems % 4) != 0) {
-    set_error("gemm operand must be 16B aligned with a leading dimension multiple of 4 floats "
-              "(ptr=%p ld=%llu)", (const void*)base, (unsigned long long)outer_stride_elems);
+  const uint64_t esize = f16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems * esize) % 16 != 0) {
+    set_error("gemm operand must be 16B aligned with a row pitch multiple of 16 bytes "
+              "(ptr=%p ld=%llu %s)", (const void*)base, (unsigned long long)outer_stride_elems,
+              f16 ? "fp16" : "fp32");
     return F2G_EINVAL;
   }
   cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {outer_stride_elems * 4};
-  cuuint32_t box[2] = {32, box_rows};
+  cuuint64_t gstride[1] = {outer_stride_elems * esize};
+  cuuint32_t box[2] = {f16 ? 64u : 32u, box_rows};      // 128 B = one swizzle row either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -694,10 +750,10 @@ static void build_schedule(PGroup& g, int pairs) {
   g.use_sched = 1;
 }
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, int F16 = 0>
 static int pair_launch(PGroup& g, cudaStream_t stream) {
   static int max_pairs = 0;
-  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, F16>;
   if (!max_pairs) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -746,6 +802,12 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   PGroup g;
   memset(&g, 0, sizeof(g));
   const int a_mn = descs[0].a_mn, b_mn = descs[0].b_mn;
+  const bool f16 = descs[0].ab_f16 != 0;
+  if (f16 && (a_mn || b_mn)) {
+    set_error("fp16 gemm operands must be K-major (a_mn = b_mn = 0)");
+    return F2G_EINVAL;
+  }
+  const int kelem = f16 ? 64 : PBK;
   // heaviest tiles first: with a static round-robin schedule the long-K problems must not land
   // in the last (partial) wave
   int order[F2G_GEMM_MAX_PROBLEMS];
@@ -757,8 +819,16 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   int tiles = 0;
   for (int oi = 0; oi < n; ++oi) {
     const F2GGemm& d = descs[order[oi]];
-    if (d.a_mn != a_mn || d.b_mn != b_mn) {
-      set_error("all problems of a gemm group must share operand majors");
+    if (d.a_mn != a_mn || d.b_mn != b_mn || (d.ab_f16 != 0) != f16) {
+      set_error("all problems of a gemm group must share operand majors and operand type");
+      return F2G_EINVAL;
+    }
+    if (d.c_f16 && (!f16 || d.res || d.gate || d.accumulate || d.c_pre || d.split_k > 1 || d.row_scale)) {
+      set_error("c_f16 needs ab_f16 and a bias / bias+activation epilogue");
+      return F2G_EINVAL;
+    }
+    if (f16 && d.a_seg_len) {
+      set_error("windowed operands are fp32 only");
       return F2G_EINVAL;
     }
     if (d.M <= 0 || d.N <= 0 || d.K <= 0) {
@@ -778,11 +848,12 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
                 : pair_encode_2d(&p.map_a, d.a, d.a_seg_len, d.a_rows, d.lda, PBM, false);
     else
       rc = a_mn ? pair_encode_2d(&p.map_a, d.a, d.M, d.K, d.lda, 32, true)
-                : pair_encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, PBM, false);
+                : pair_encode_2d(&p.map_a, d.a, d.K, d.M, d.lda, PBM, false, f16);
     if (rc) return rc;
     p.seg_len = d.a_seg_len; p.seg_shift = d.a_seg_shift;
+    p.c_f16 = d.c_f16;
     rc = b_mn ? pair_encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
-              : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false);
+              : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false, f16);
     if (rc) return rc;
     p.c = d.c; p.ldc = d.ldc; p.c_pre = d.c_pre; p.ld_pre = d.ld_pre;
     p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
@@ -794,7 +865,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     p.tile_begin = tiles;
     p.act = d.act; p.round_tf32 = d.round_tf32; p.accumulate = d.accumulate;
     p.leaky = d.leaky; p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
-    p.kb_total = (d.K + PBK - 1) / PBK;
+    p.kb_total = (d.K + kelem - 1) / kelem;
     int sk = d.split_k < 1 ? 1 : d.split_k;
     if (sk > p.kb_total) sk = p.kb_total;
     p.kb_per = (p.kb_total + sk - 1) / sk;
@@ -821,7 +892,13 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
       e = PEPI_BIAS_RES;
     else if (!odd && d.act == F2G_ACT_NONE && !d.res && !d.bias && !d.c_pre)
       e = PEPI_PLAIN;
+    if (d.c_f16 && e != PEPI_BIAS_ACT) e = PEPI_GENERIC;
     epi = (epi == -1 || epi == e) ? e : PEPI_GENERIC;
+  }
+  if (f16) {   // K-major only; the three epilogues the inference blocks use
+    if (epi == PEPI_BIAS_ACT) return pair_launch<0, 0, PEPI_BIAS_ACT, 1>(g, stream);
+    if (epi == PEPI_BIAS_RES) return pair_launch<0, 0, PEPI_BIAS_RES, 1>(g, stream);
+    return pair_launch<0, 0, PEPI_GENERIC, 1>(g, stream);
   }
 
 #define F2G_PDISPATCH_E(AM_, BM_)                                                        \

@@ -567,7 +567,7 @@ int gemm_tf32_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   int max_m = 0;
   for (int i = 0; i < n && i < F2G_GEMM_MAX_PROBLEMS; ++i) max_m = descs[i].M > max_m ? descs[i].M : max_m;
   bool windowed = false;
-  for (int i = 0; i < n && i < F2G_GEMM_MAX_PROBLEMS; ++i) windowed |= descs[i].a_seg_len != 0;
+  for (int i = 0; i < n && i < F2G_GEMM_MAX_PROBLEMS; ++i) windowed |= descs[i].a_seg_len != 0 || descs[i].ab_f16 != 0;
   if (windowed || (!use_v1 && max_m > 128)) return gemm_pair_group(descs, n, stream);
   if (n < 1 || n > F2G_GEMM_MAX_PROBLEMS) {
     set_error("gemm group size %d out of range", n);

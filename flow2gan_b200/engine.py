@@ -26,6 +26,16 @@ import os
 BN_G1 = int(os.environ.get("F2G_BN1", "128"))   # N tile of pwconv1-like GEMMs (wide N)
 BN_G2 = int(os.environ.get("F2G_BN2", "128"))   # N tile of pwconv2-like GEMMs (N = channels)
 
+# Operand type of the ConvNeXt-block contractions (pwconv1 / pwconv2) at inference.
+#   "f16"  (default): fp16 operands, fp32 accumulate (tcgen05 kind::f16).  fp16 has the SAME 11-bit
+#          significand as TF32, so inside the fp16 range the rounding error is the TF32 one
+#          (parity tests: same rel-RMS), while the operand bytes through the L2->SM fabric --
+#          the measured bound of these short-K GEMMs -- halve and the MMA rate doubles.
+#          Values are clamped to +-65504 where they are produced.
+#   "tf32": fp32-container TF32 operands everywhere (8-bit exponent; the training path).
+BLOCK_OPERANDS = os.environ.get("F2G_BLOCK_OPERANDS", "f16")
+assert BLOCK_OPERANDS in ("f16", "tf32"), BLOCK_OPERANDS
+
 
 def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
@@ -62,6 +72,16 @@ class _BlockW:
         self.dwT = _pack(blk.dwconv.weight.detach(), 7, C, 1, 7, C, rnd=0)          # (7, C)
         self.W1 = _pack(blk.pwconv1.weight.detach(), H, C, C, 1, C)                  # (H, C)
         self.W2 = _pack(blk.pwconv2.weight.detach(), C, H, H, 1, H)                  # (C, H)
+        self._half = None
+
+    def half(self) -> Tuple[Tensor, Tensor]:
+        """fp16 copies (RN) of the two matrices for the kind::f16 inference GEMMs; built on first
+        use after every refresh (the training path never asks for them)."""
+        if self._half is None:
+            b = self.blk
+            self._half = (b.pwconv1.weight.detach().reshape(self.H, self.C).to(torch.float16),
+                          b.pwconv2.weight.detach().reshape(self.C, self.H).to(torch.float16))
+        return self._half
 
 
 class PackedGenerator:
@@ -128,6 +148,10 @@ class PackedGenerator:
 def _g1(bw: _BlockW, a, h, M, bn=None):
     bn = bn or BN_G1
     b = bw.blk
+    if a.dtype == torch.float16:          # a1 (fp16) x W1 (fp16) -> h (fp16)
+        return L.gemm_desc(a.data_ptr(), bw.half()[0].data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C,
+                           bw.H, bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
+                           act=L.ACT_PRELU, ab_f16=1, c_f16=1)
     return L.gemm_desc(a.data_ptr(), bw.W1.data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C, bw.H,
                        bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
                        act=L.ACT_PRELU, round_tf32=1)
@@ -136,9 +160,11 @@ def _g1(bw: _BlockW, a, h, M, bn=None):
 def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0):
     bn = bn or BN_G2
     b = bw.blk
-    return L.gemm_desc(h.data_ptr(), bw.W2.data_ptr(), x.data_ptr(), M, bw.C, bw.H, bw.H, bw.H, bw.C,
+    f16 = h.dtype == torch.float16        # h (fp16) x W2 (fp16) -> x (fp32 residual stream, in place)
+    return L.gemm_desc(h.data_ptr(), (bw.half()[1] if f16 else bw.W2).data_ptr(), x.data_ptr(), M, bw.C,
+                       bw.H, bw.H, bw.H, bw.C,
                        bn=bn, bias=b.pwconv2.bias.data_ptr(), res=x.data_ptr(), ld_res=bw.C,
-                       res_scale=b.residual_scale.scale.data_ptr(), round_tf32=round_out)
+                       res_scale=b.residual_scale.scale.data_ptr(), round_tf32=round_out, ab_f16=int(f16))
 
 
 class InferencePlan:
@@ -149,6 +175,8 @@ class InferencePlan:
         self.B, self.Fm, self.T, self.masked = B, Fm, T, masked
         dev = next(model.parameters()).device
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        op_dt = torch.float16 if BLOCK_OPERANDS == "f16" else torch.float32
+        zo = lambda *s: torch.zeros(*s, device=dev, dtype=op_dt)      # block GEMM operands (a1, h)
         ce = model.cond_encoder
         self.n_mels = ce.cond_dim
         self.Cc = ce.channels
@@ -156,8 +184,8 @@ class InferencePlan:
         self.mel = z(B, self.n_mels, Fm)
         self.mel_cl = z(B * Fm, packed.ld_mel)
         self.c0 = z(self.Rc, self.Cc)
-        self.ce_a1 = z(self.Rc, self.Cc)
-        self.ce_h = z(self.Rc, ce.blocks[0].hidden_channels)
+        self.ce_a1 = zo(self.Rc, self.Cc)
+        self.ce_h = zo(self.Rc, ce.blocks[0].hidden_channels)
         self.x_audio = z(B, T)
         self.lens = torch.zeros(B, device=dev, dtype=torch.int32)
         self.freqs = model.estimators[0].decoder.time_embed.freqs(dev)
@@ -170,8 +198,8 @@ class InferencePlan:
             w.R = B * w.F
             w.pin = z(w.R, bw.ldp)
             w.x = z(w.R, bw.C)
-            w.a1 = z(w.R, bw.C)
-            w.h = z(w.R, bw.blocks[0].H)
+            w.a1 = zo(w.R, bw.C)
+            w.h = zo(w.R, bw.blocks[0].H)
             w.pout = z(w.R, bw.ldp)
             w.fr = z(w.R, bw.n_fft)
             # the sampler evaluates every batch element at the same t (generator.py:260): the time

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 2
+#define F2G_ABI_VERSION 3
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -77,6 +77,15 @@ typedef struct F2GGemm {
    *   a_mn = 1: element (m, k) = a[(k + (m / a_seg_len) * a_seg_shift) * lda + m % a_seg_len]
    * a_seg_len must be a multiple of 32.  CTA-pair kernel only (max M > 128). */
   int a_seg_len, a_seg_shift, a_rows;
+  /* Half-width operands (tcgen05 kind::f16, fp32 accumulate).  IEEE fp16 carries the same 11-bit
+   * significand as TF32, so for operands inside the fp16 range the products are the ones the TF32
+   * path forms -- at half the bytes through the L2->SM fabric (which bounds this kernel) and
+   * twice the tensor issue rate.  ab_f16 = 1: a and b point to fp16 (__half) matrices, K-major
+   * only (a_mn = b_mn = 0), lda / ldb in ELEMENTS (multiples of 8), 16 B-aligned pointers.
+   * c_f16 = 1: C is stored as fp16 (round-to-nearest, clamped to +-65504), ldc in elements
+   * (multiple of 8); needs a bias+activation or bias-only epilogue (no res / gate / accumulate /
+   * c_pre / split_k).  The epilogue itself always runs in fp32.  CTA-pair kernel only. */
+  int ab_f16, c_f16;
 } F2GGemm;
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
@@ -164,6 +173,8 @@ typedef struct F2GBlockPre {
   float* conv_out;
   float* inv_rms_out;
   int B, T, C, ld_x, ld_cond, cond_T, factor, zero_row, ld_ts, ld_out;
+  int out_f16; /* 1: `out` points to fp16 rows (ld_out in elements, multiple of 4), RN-rounded and
+                  clamped to +-65504 instead of TF32-rounded fp32 -- operand of an ab_f16 GEMM */
 } F2GBlockPre;
 int f2g_block_pre_group(const F2GBlockPre* problems, int n_problems, void* stream);
 

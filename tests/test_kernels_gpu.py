@@ -125,6 +125,81 @@ def test_gemm_grouped(L):
         assert rel_rms(Cg.cpu(), ref) < 3e-6
 
 
+@pytest.mark.parametrize("M,N,K,epi", [
+    (1520, 2304, 768, "prelu_f16"), (6032, 1152, 384, "prelu_f16"), (300, 256, 96, "prelu_f16"),
+    (1505, 1536, 512, "prelu_f16"), (333, 160, 72, "prelu_f16"),
+    (1520, 768, 2304, "res"), (6032, 384, 1152, "res"), (97, 514, 776, "plain"), (421, 384, 160, "res_round"),
+])
+def test_gemm_f16_operands(L, M, N, K, epi):
+    """kind::f16 GEMM (fp16 operands exact in the inputs, fp32 accumulate) vs float64 matmul:
+    the ConvNeXt-block contractions of the inference engine (modules.py:443-451)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).half()
+    Bm = (torch.randn(N, K, generator=g) * 0.05).half()
+    lda = (K + 7) // 8 * 8 + 8
+    Ad = torch.zeros(M, lda, dtype=torch.float16); Ad[:, :K] = A
+    Bd = torch.zeros(N, lda, dtype=torch.float16); Bd[:, :K] = Bm
+    ref = A.double() @ Bm.double().t()
+    bias = torch.randn(N, generator=g)
+    slope = torch.rand(N, generator=g) * 0.5
+    res = torch.randn(M, N, generator=g)
+    rsc = torch.rand(N, generator=g) + 0.5
+    keep = []
+
+    def d(t):
+        t = t.cuda().contiguous(); keep.append(t); return t.data_ptr()
+
+    Ag, Bg = Ad.cuda(), Bd.cuda()
+    if epi == "prelu_f16":
+        ldc = (N + 7) // 8 * 8 + 8
+        C0 = torch.randn(M, ldc, generator=g).half()
+        Cd = C0.clone().cuda()
+        z = ref + bias.double()
+        exp = torch.where(z > 0, z, z * slope.double())
+        L.gemm_group([L.gemm_desc(Ag.data_ptr(), Bg.data_ptr(), Cd.data_ptr(), M, N, K, lda, lda, ldc,
+                                  bias=d(bias), slope=d(slope), act=L.ACT_PRELU, ab_f16=1, c_f16=1)])
+        tol = 3e-4                                       # fp16 output rounding: 2^-11 / sqrt(3)
+    else:
+        ldc = N + 4
+        C0 = torch.randn(M, ldc, generator=g)
+        Cd = C0.clone().cuda()
+        if epi == "plain":
+            exp, kw = ref, {}
+        else:
+            Cd[:, :N] = res.cuda()                       # in-place residual stream, as the engine does
+            exp = ref + bias.double() + rsc.double() * res.double()
+            kw = dict(bias=d(bias), res=Cd.data_ptr(), ld_res=ldc, res_scale=d(rsc),
+                      round_tf32=int(epi == "res_round"))
+        L.gemm_group([L.gemm_desc(Ag.data_ptr(), Bg.data_ptr(), Cd.data_ptr(), M, N, K, lda, lda, ldc,
+                                  ab_f16=1, **kw)])
+        tol = 3e-4 if epi == "res_round" else 1e-5
+    torch.cuda.synchronize()
+    got = Cd.cpu()
+    assert torch.equal(got[:, N:], C0[:, N:]), "GEMM wrote outside its N columns"
+    err = rel_rms(got[:, :N].float(), exp)
+    assert err < tol, (M, N, K, epi, err)
+
+
+def test_gemm_f16_group_matches_tf32_group(L):
+    """Three problems in one launch (the three branches), fp16 vs TF32 operands holding the same
+    values: the products are identical, only the accumulation order may differ."""
+    g = torch.Generator().manual_seed(11)
+    d16, d32, outs = [], [], []
+    for (M, N, K) in ((1520, 768, 2304), (3024, 512, 1536), (6032, 384, 1152)):
+        A = torch.randn(M, K, generator=g).half()
+        Bm = (torch.randn(N, K, generator=g) * 0.03).half()
+        Ah, Bh, A32, B32 = A.cuda(), Bm.cuda(), A.float().cuda(), Bm.float().cuda()
+        C16, C32 = torch.zeros(M, N).cuda(), torch.zeros(M, N).cuda()
+        d16.append(L.gemm_desc(Ah.data_ptr(), Bh.data_ptr(), C16.data_ptr(), M, N, K, K, K, N, ab_f16=1))
+        d32.append(L.gemm_desc(A32.data_ptr(), B32.data_ptr(), C32.data_ptr(), M, N, K, K, K, N))
+        outs.append((C16, C32, Ah, Bh, A32, B32))
+    L.gemm_group(d16)
+    L.gemm_group(d32)
+    torch.cuda.synchronize()
+    for C16, C32, *_ in outs:
+        assert rel_rms(C16, C32) < 1e-5
+
+
 @pytest.mark.parametrize("n_fft,hop", [(128, 64), (256, 128), (512, 256), (1024, 512), (32, 8), (2048, 512)])
 def test_stft_packed(L, n_fft, hop):
     B, T = 3, 6144
@@ -243,6 +318,13 @@ def test_biasnorm_and_block_pre(L, C):
                 Tc, factor, B * Tc, ts.cuda(), C, out, C, conv_out, None)
     assert rel_rms(out.cpu().view(B, T, C).transpose(1, 2), ref) < 3e-4   # tf32 rounding ties
     assert rel_rms(conv_out.cpu().view(B, T, C).transpose(1, 2), conv) < 2e-6
+    # fp16 destination (operand of the kind::f16 block GEMMs): same values, RN to 11 significant bits
+    out16 = torch.empty(B * T, C, device="cuda", dtype=torch.float16)
+    L.block_pre(xr, B, T, C, C, dwT, dwb.cuda(), bias.cuda(), ls.cuda(), mask.reshape(-1).cuda(), crow, C,
+                Tc, factor, B * Tc, ts.cuda(), C, out16, C, None, None)
+    full = ((z + cup) * (1 + ts[:, :, None])).contiguous()
+    assert rel_rms(out16.float().cpu().view(B, T, C).transpose(1, 2), full) < 3e-4
+    assert float((out16.float().cpu() - out.cpu()).abs().max()) <= float(full.abs().max()) * 2 ** -10
 
 
 def test_time_embedding_path(L):
