@@ -11,8 +11,11 @@ configuration).  Prints ONE JSON line (rank 0).
                events (max over ranks; N>1 = N independent replicas, weak scaling).
   e2e        : the same through the public API with HOST buffers: pinned mel -> H2D ->
                model.infer (draws its noise like the reference) -> D2H pinned audio, per step.
-  roofline   : tcgen05 TF32 GEMM launches: sum(2*M*N*K) / sum(CUDA-event launch time), measured
-               in an eager (non-graph) pass of the same step, against the measured tensor peak.
+  roofline   : the dominant kernel = the fp16-operand tcgen05 GEMM of the ConvNeXt blocks
+               (pwconv1/pwconv2): sum(2*M*N*K) of its launches in one step / their time when
+               replayed back to back from a CUDA graph (CUDA events), against the measured dense
+               bf16/fp16 tensor peak; `roofline_other` = the remaining TF32 GEMM launches;
+               `traffic` = dram bytes per launch from the committed ncu capture (profiles/).
   cpu_baseline / --impl reference : the oracle port (oracle/flow2gan_oracle.py, a functional
                restatement of the reference's PyTorch path; the reference itself is Python and
                cannot travel to the GPU box) on the host cores, bounded sample.
@@ -37,6 +40,7 @@ MODEL = "mel_24k_base"
 B, N_MELS, FRAMES, HOP = 16, 100, 94, 256
 T = FRAMES * HOP
 SAMPLES_PER_STEP = B * T
+METRIC = "audio samples/sec (bs=16, 1s, 24 kHz) 1-step infer + GAN train step @1/2/4/8 B200"   # BASELINE.json
 REF_FLOPS = {1: 347.6e9, 2: 675.8e9, 4: 1332.2e9}   # SURVEY.md section 8(d), conv/matmul FLOPs
 
 
@@ -207,7 +211,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     rate, ms, cores = cpu_oracle_rate(args.n_timesteps, steps, warmup=min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": "audio samples/sec (bs=16, 1s, 24 kHz) %d-step infer" % args.n_timesteps,
+        "impl": "reference", "metric": METRIC, "metric_part": "%d-step infer" % args.n_timesteps,
         "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -307,43 +311,68 @@ def run_ours(args):
         # The step's GEMM launches (same descriptors, same buffers) are re-issued alone, back to
         # back, from a CUDA graph so that no host submission latency sits between the two events:
         # achieved = sum(2MNK) / (event time / launches) -- the in-step average launch duration.
-        roof = None
+        roof = roof_other = None
         if rank == 0:
             L.PROFILE = []
             plan.x_audio.copy_(noise)
             plan._run(n, False)
             torch.cuda.synchronize()
             rec, L.PROFILE = L.PROFILE, None
-            flops = sum(f for (_, _, f) in rec)
-            nl = len(rec)
-            side = torch.cuda.Stream()
-            with torch.cuda.stream(side):
-                for arr, cnt, _ in rec:
-                    L.gemm_replay(arr, cnt)
-                side.synchronize()
-                gg = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gg, stream=side):
-                    for arr, cnt, _ in rec:
-                        L.gemm_replay(arr, cnt)
-                reps = 10
-                for _ in range(3):
-                    gg.replay()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record()
-                for _ in range(reps):
-                    gg.replay()
-                g1.record()
-                side.synchronize()
-            ms = g0.elapsed_time(g1) / reps
             pk, how = peaks()
-            peak = pk["bf16_tflops"] / 2.0
-            ach = flops / (ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "launches_timed": nl, "flops_per_launch_avg": flops / nl, "us_per_launch_avg": ms * 1e3 / nl,
-                    "how": "all GEMM launches of one step replayed back to back from a CUDA graph, CUDA events",
-                    "peak_source": f"{how}: bf16_tflops (burst)/2 -- TF32 issues at half the bf16 rate",
-                    "step_ref_equiv_tflops": REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12 / 1.0}
+
+            def replay_timed(sub):
+                """GEMM launches `sub` re-issued alone, back to back, from a CUDA graph on a side
+                stream (no host submission latency between the two events)."""
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    for arr, cnt, _, _ in sub:
+                        L.gemm_replay(arr, cnt)
+                    side.synchronize()
+                    gg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gg, stream=side):
+                        for arr, cnt, _, _ in sub:
+                            L.gemm_replay(arr, cnt)
+                    reps = 10
+                    for _ in range(3):
+                        gg.replay()
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record()
+                    for _ in range(reps):
+                        gg.replay()
+                    g1.record()
+                    side.synchronize()
+                return g0.elapsed_time(g1) / reps
+
+            def roof_entry(sub, kernel, peak, peak_note):
+                fl = sum(r[2] for r in sub)
+                ms = replay_timed(sub)
+                ach = fl / (ms * 1e-3) / 1e12
+                return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "launches_timed": len(sub),
+                        "flops_per_launch_avg": fl / len(sub), "us_per_launch_avg": ms * 1e3 / len(sub),
+                        "share_of_step_flops": fl / sum(r[2] for r in rec),
+                        "how": "the step's launches of this kernel replayed back to back from a CUDA graph, "
+                               "CUDA events on the launching stream",
+                        "peak_source": f"{how}: {peak_note}"}
+
+            f16 = [r for r in rec if r[3]]
+            t32 = [r for r in rec if not r[3]]
+            if f16:      # dominant kernel: the ConvNeXt-block contractions (fp16 operands)
+                roof = roof_entry(f16, "gemm_pair_kernel<F16> (tcgen05.mma.cta_group::2 kind::f16, fp32 accumulate)",
+                                  pk["bf16_tflops"], "bf16_tflops (burst); fp16 issues at the bf16 rate")
+                if t32:
+                    roof_other = roof_entry(t32, "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32)",
+                                            pk["bf16_tflops"] / 2.0,
+                                            "bf16_tflops (burst)/2 -- TF32 issues at half the bf16 rate")
+            else:
+                roof = roof_entry(t32, "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32)",
+                                  pk["bf16_tflops"] / 2.0, "bf16_tflops (burst)/2 -- TF32 issues at half the bf16 rate")
+            roof["step_ref_equiv_tflops"] = REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12
+            tr_path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+            if os.path.exists(tr_path):       # dram__bytes_{read,write}.sum of the same launches (ncu --set full)
+                tj = json.load(open(tr_path))
+                roof["traffic"] = tj.get("dram_bytes_per_launch_avg")
+                roof["traffic_source"] = tj.get("source")
 
     train = None
     if not args.no_train:
@@ -357,10 +386,10 @@ def run_ours(args):
         return
     cpu_rate, cpu_ms, cores = cpu_oracle_rate(n, iters=3 if n == 1 else 1) if world == 1 else (None, None, None)
     line = {
-        "metric": "audio samples/sec (bs=16, 1s, 24 kHz) %d-step infer" % n,
+        "metric": METRIC, "metric_part": "%d-step infer (`value`, `e2e`); GAN train step pair under `gan_train`" % n,
         "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic",
+        "dtype": "f16/tf32 operands -> f32 accumulate", "data": "synthetic",
         "config": {"workload": f"{MODEL} {n}-step inference, synthetic mel (16,100,94) -> (16,24064) per GPU",
                    "global_batch": B * world, "parallelism": f"replicas x{world} (no data-path collective)",
                    "weights": "synthetic (seeded), reference state_dict layout",
@@ -372,6 +401,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    if roof_other is not None:
+        line["roofline_other"] = roof_other
     if train is not None:
         line["gan_train"] = train
     if cpu_rate is not None:

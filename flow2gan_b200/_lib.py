@@ -38,6 +38,7 @@ class F2GGemm(C.Structure):
         ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i), ("split_k", _i),
         ("a_seg_len", _i), ("a_seg_shift", _i), ("a_rows", _i),
         ("ab_f16", _i), ("c_f16", _i),
+        ("done_counter", _fp), ("wait_counter", _fp),
     ]
 
 
@@ -51,7 +52,8 @@ class F2GBlockPre(C.Structure):
                 ("row_mask", _fp), ("cond", _fp), ("tscale", _fp), ("out", _fp), ("conv_out", _fp),
                 ("inv_rms_out", _fp),
                 ("B", _i), ("T", _i), ("C", _i), ("ld_x", _i), ("ld_cond", _i), ("cond_T", _i),
-                ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i), ("out_f16", _i)]
+                ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i),
+                ("zero_ptr", _fp), ("zero_n", _i), ("out_f16", _i)]
 
 
 class F2GSpecProblem(C.Structure):
@@ -126,7 +128,7 @@ _SIGS = {
 _lib: Optional[C.CDLL] = None
 _device_ok = False
 COUNT = 0            # native launches issued through this module (bench.py's gpu_launches)
-PROFILE = None       # when a list: gemm_group appends (start_event, end_event, flops)
+PROFILE = None       # when a list: gemm_group appends (descriptor array, n, flops, fp16 operands?)
 
 
 def exported_symbols() -> Sequence[str]:
@@ -146,7 +148,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 3:
+        if lib.f2g_abi_version() != 4:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -189,7 +191,8 @@ def stream() -> int:
 def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=None, slope=None,
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
               act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
-              ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0, ab_f16=0, c_f16=0) -> F2GGemm:
+              ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0, ab_f16=0, c_f16=0,
+              done_counter=None, wait_counter=None) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -204,6 +207,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.split_k = split_k
     d.a_seg_len, d.a_seg_shift, d.a_rows = a_seg_len, a_seg_shift, a_rows
     d.ab_f16, d.c_f16 = ab_f16, c_f16
+    d.done_counter, d.wait_counter = done_counter, wait_counter
     return d
 
 
@@ -211,7 +215,7 @@ def gemm_group(descs: Sequence[F2GGemm]) -> None:
     n = len(descs)
     arr = (F2GGemm * n)(*descs)
     if PROFILE is not None:      # bench.py: record the launch (descriptors + FLOPs) for replay
-        PROFILE.append((arr, n, sum(2.0 * d.M * d.N * d.K for d in descs)))
+        PROFILE.append((arr, n, sum(2.0 * d.M * d.N * d.K for d in descs), bool(descs[0].ab_f16)))
     _check(lib().f2g_gemm_tf32(arr, n, stream()))
 
 
@@ -289,10 +293,13 @@ def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_ma
     return d
 
 
-def block_pre_group(descs) -> None:
-    """Up to 4 block prologues (block_pre_desc) in one launch."""
+def block_pre_group(descs, zero: Optional[torch.Tensor] = None) -> None:
+    """Up to 4 block prologues (block_pre_desc) in one launch; `zero` (int32 tensor) is cleared by
+    the same launch (chaining counters of the GEMM group that follows)."""
     n = len(descs)
     arr = (F2GBlockPre * n)(*descs)
+    if zero is not None:
+        arr[0].zero_ptr, arr[0].zero_n = ptr(zero), zero.numel()
     _check(lib().f2g_block_pre_group(arr, n, stream()))
 
 

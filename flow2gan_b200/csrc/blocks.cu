@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   const int ld_x = P.ld_x;
   pdl_wait();
   pdl_launch();
+  if (blockIdx.x == 0 && a.p[0].zero_ptr)      // chaining counters of the GEMM group that follows
+    for (int i = threadIdx.x; i < a.p[0].zero_n; i += PRE_THREADS) a.p[0].zero_ptr[i] = 0;
 
   float4 acc[PRE_S];
   float4 cv[PRE_S];
@@ -357,7 +359,7 @@ extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, cons
   p.ld_cond = ld_cond; p.cond_T = cond_T; p.factor = factor; p.zero_row = zero_row;
   p.tscale = tscale; p.ld_ts = ld_ts; p.out = out; p.ld_out = ld_out; p.conv_out = conv_out;
   p.inv_rms_out = inv_rms_out;
-  p.out_f16 = 0;
+  p.out_f16 = 0; p.zero_ptr = nullptr; p.zero_n = 0;
   return f2g_block_pre_group(&p, 1, stream);
 }
 

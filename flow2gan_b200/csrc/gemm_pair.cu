@@ -56,6 +56,9 @@ struct alignas(64) PProblem {
   float leaky, alpha;
   int seg_len, seg_shift;   // windowed A operand (F2GGemm::a_seg_len / a_seg_shift), 0 = plain
   int c_f16;                // C stored as fp16 (F2GGemm::c_f16)
+  int* done;                // chaining (F2GGemm::done_counter / wait_counter)
+  const int* wait;
+  int wait_count;
 };
 
 struct alignas(64) PGroup {
@@ -167,7 +170,18 @@ F2G_DEVINL void umma_commit_cg2(uint64_t* bar) {
       : "memory");
 }
 
-enum { PEPI_GENERIC = 0, PEPI_BIAS_ACT = 1, PEPI_BIAS_RES = 2, PEPI_PLAIN = 3 };
+// PEPI_MLP (fp16 operands only): per problem either BIAS_ACT with an fp16 destination or BIAS_RES --
+// the two halves of a chained pwconv1 -> pwconv2 launch, both on their fast paths.
+enum { PEPI_GENERIC = 0, PEPI_BIAS_ACT = 1, PEPI_BIAS_RES = 2, PEPI_PLAIN = 3, PEPI_MLP = 4 };
+
+F2G_DEVINL int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// orders the async proxy (TMA reads issued after it) behind what this thread has observed
+// through the generic proxy (the acquire above)
+F2G_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // Fast epilogue of one 32x32 chunk, after the transpose through `scratch`: this lane owns the
 // column quad `col` of rows rsub, rsub+4, ..., rsub+28.  Straight-line on purpose (one epilogue
@@ -313,6 +327,12 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         const int m_cta = tc.m0 + (int)rank * PBM;
         const int n_cta = tc.n0 + (int)rank * bhalf;
         const uint32_t stage_tx = 2u * (uint32_t)(P_A_BYTES + bhalf * PBK * 4);
+        if (pr.wait) {   // chained consumer: the A rows of this 256-row tile come from a producer
+                         // problem of this launch; wait until all of its tiles over them are stored
+          const int* wp = pr.wait + tc.m0 / (2 * PBM);
+          while (ld_acquire_gpu(wp) < pr.wait_count) __nanosleep(64);
+          fence_proxy_async_all();
+        }
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
@@ -479,7 +499,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         const float4 rsc4 = *reinterpret_cast<const float4*>(sparam + 512 + c0 + 4 * cg);
         const bool chunk_full = vec_all && (n0 + c0 + 32 <= N) && split_k == 1;   // warp-uniform
 
-        if (F16 && EPI == PEPI_BIAS_ACT && chunk_full && c16) {
+        if (F16 && (EPI == PEPI_BIAS_ACT || EPI == PEPI_MLP) && chunk_full && c16) {
           const float* sl = scratch + rsub * 36 + 4 * cg;
           __half* hp = reinterpret_cast<__half*>(cbase) + (size_t)(row_base + rsub) * ldc + col;
           if (rows >= 32) epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4);
@@ -487,20 +507,21 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           __syncwarp();
           continue;
         }
-        if (EPI != PEPI_GENERIC && chunk_full && !c16) {
+        constexpr int EF = EPI == PEPI_MLP ? PEPI_BIAS_RES : EPI;   // fp32-destination fast path
+        if (EF != PEPI_GENERIC && chunk_full && !c16 && (EPI != PEPI_MLP || act == F2G_ACT_NONE)) {
           const size_t r0 = (size_t)(row_base + rsub);
           const float* sl = scratch + rsub * 36 + 4 * cg;
           float* cp = cbase + r0 * ldc + col;
-          const float* rp = EPI == PEPI_BIAS_RES ? (res_p ? res_p + r0 * ld_res + col : nullptr)
-                                                 : ((EPI == PEPI_PLAIN && do_acc) ? cp : nullptr);
-          float* pp = (EPI == PEPI_BIAS_ACT && pre_p) ? pre_p + r0 * ld_pre + col : nullptr;
-          const size_t rstep = EPI == PEPI_BIAS_RES ? (size_t)4 * ld_res : (size_t)4 * ldc;
+          const float* rp = EF == PEPI_BIAS_RES ? (res_p ? res_p + r0 * ld_res + col : nullptr)
+                                                : ((EF == PEPI_PLAIN && do_acc) ? cp : nullptr);
+          float* pp = (EF == PEPI_BIAS_ACT && pre_p) ? pre_p + r0 * ld_pre + col : nullptr;
+          const size_t rstep = EF == PEPI_BIAS_RES ? (size_t)4 * ld_res : (size_t)4 * ldc;
           if (rows >= 32)
-            epi_fast_chunk<EPI, true>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre, 32, alpha,
-                                      bias4, slope4, rsc4, radd, rmask);
+            epi_fast_chunk<EF, true>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre, 32, alpha,
+                                     bias4, slope4, rsc4, radd, rmask);
           else
-            epi_fast_chunk<EPI, false>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre,
-                                       rows - rsub, alpha, bias4, slope4, rsc4, radd, rmask);
+            epi_fast_chunk<EF, false>(sl, cp, (size_t)4 * ldc, rp, rstep, pp, (size_t)4 * ld_pre,
+                                      rows - rsub, alpha, bias4, slope4, rsc4, radd, rmask);
           __syncwarp();
           continue;
         }
@@ -602,6 +623,10 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
       asm volatile("bar.sync 1, 256;" ::: "memory");   // staged parameters may be overwritten now
+      if (et == 0 && pr.done) {   // all 256 epilogue threads' stores precede the barrier: publish them
+        __threadfence();
+        atomicAdd(pr.done + tc.m0 / (2 * PBM), 1);
+      }
       ab ^= 1;
       if (ab == 0) ab_phase ^= 1;
     }
@@ -705,7 +730,8 @@ static void build_schedule(PGroup& g, int pairs) {
   for (int pi = 0; pi < g.n_problems; ++pi) {
     const PProblem& p = g.p[pi];
     const int cnt = p.m_tiles * p.n_tiles * p.split_k;
-    const int c = p.kb_per * (256 + p.bn) + 8 * p.bn;
+    // waiting (phase 1) tiles sort behind every phase-0 tile: LPT within a phase, phases in order
+    const int c = p.kb_per * (256 + p.bn) + 8 * p.bn + (p.wait ? 0 : (1 << 24));
     for (int i = 0; i < cnt; ++i) {
       cost[n] = c;
       order[n] = (uint16_t)n;
@@ -730,7 +756,7 @@ static void build_schedule(PGroup& g, int pairs) {
   for (int i = 0; i < n; ++i) {
     const int p = heap[0];                // least-loaded pair (ties: lowest index first)
     owner[i] = (uint16_t)p;
-    load[p] += cost[order[i]];
+    load[p] += cost[order[i]] & ((1 << 24) - 1);
     ++count[p];
     int k = 0;                            // sift down
     for (;;) {
@@ -810,10 +836,18 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   const int kelem = f16 ? 64 : PBK;
   // heaviest tiles first: with a static round-robin schedule the long-K problems must not land
   // in the last (partial) wave
+  // Chained groups: every problem that waits on a counter (phase 1) comes after all the others
+  // (phase 0) -- in the tile numbering AND in every pair's schedule -- so no CTA ever waits for a
+  // tile that is queued behind a waiting tile.
   int order[F2G_GEMM_MAX_PROBLEMS];
-  for (int i = 0; i < n; ++i) order[i] = i;
+  bool chained = false;
+  for (int i = 0; i < n; ++i) { order[i] = i; chained |= descs[i].wait_counter != nullptr; }
+  auto before = [&](int a, int b) {   // a must precede b
+    const int pa = descs[a].wait_counter ? 1 : 0, pb = descs[b].wait_counter ? 1 : 0;
+    return pa != pb ? pa < pb : descs[a].K > descs[b].K;
+  };
   for (int i = 1; i < n; ++i)
-    for (int j = i; j > 0 && descs[order[j]].K > descs[order[j - 1]].K; --j) {
+    for (int j = i; j > 0 && before(order[j], order[j - 1]); --j) {
       const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
     }
   int tiles = 0;
@@ -874,7 +908,24 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
       set_error("split-K gemm supports the plain (alpha) epilogue only");
       return F2G_EINVAL;
     }
+    p.done = d.done_counter; p.wait = d.wait_counter; p.wait_count = 0;
+    if ((p.done || p.wait) && p.split_k > 1) {
+      set_error("chained gemm problems cannot be split along K");
+      return F2G_EINVAL;
+    }
     tiles += p.m_tiles * p.n_tiles * p.split_k;
+  }
+  for (int oi = 0; oi < n; ++oi) {   // resolve consumers to their producers
+    PProblem& c = g.p[oi];
+    if (!c.wait) continue;
+    const PProblem* prod = nullptr;
+    for (int oj = 0; oj < n; ++oj)
+      if (g.p[oj].done == c.wait && !g.p[oj].wait) prod = &g.p[oj];
+    if (!prod || prod->M != c.M) {
+      set_error("gemm wait_counter without a producer (done_counter of a non-waiting problem with the same M) in the group");
+      return F2G_EINVAL;
+    }
+    c.wait_count = 2 * prod->n_tiles;
   }
   g.n_problems = n;
   g.total_tiles = tiles;
@@ -882,6 +933,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   g.dbg = dbg;
 
   int epi = -1;
+  bool mlp_ok = true;
   for (int i = 0; i < n; ++i) {
     const F2GGemm& d = descs[i];
     int e = PEPI_GENERIC;
@@ -893,11 +945,17 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     else if (!odd && d.act == F2G_ACT_NONE && !d.res && !d.bias && !d.c_pre)
       e = PEPI_PLAIN;
     if (d.c_f16 && e != PEPI_BIAS_ACT) e = PEPI_GENERIC;
+    if (f16 && e == PEPI_BIAS_ACT && !d.c_f16) mlp_ok = false;
+    if (e != PEPI_BIAS_ACT && e != PEPI_BIAS_RES) mlp_ok = false;
     epi = (epi == -1 || epi == e) ? e : PEPI_GENERIC;
   }
+  if (f16 && epi == PEPI_GENERIC && mlp_ok) epi = PEPI_MLP;   // mixed pwconv1 / pwconv2 problems
+  static const int force_generic = getenv("F2G_PAIR_FORCE_GENERIC") ? atoi(getenv("F2G_PAIR_FORCE_GENERIC")) : 0;
+  if (force_generic) epi = PEPI_GENERIC;     // timing experiments only
   if (f16) {   // K-major only; the three epilogues the inference blocks use
     if (epi == PEPI_BIAS_ACT) return pair_launch<0, 0, PEPI_BIAS_ACT, 1>(g, stream);
     if (epi == PEPI_BIAS_RES) return pair_launch<0, 0, PEPI_BIAS_RES, 1>(g, stream);
+    if (epi == PEPI_MLP) return pair_launch<0, 0, PEPI_MLP, 1>(g, stream);
     return pair_launch<0, 0, PEPI_GENERIC, 1>(g, stream);
   }
 

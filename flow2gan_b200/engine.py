@@ -35,6 +35,10 @@ BN_G2 = int(os.environ.get("F2G_BN2", "128"))   # N tile of pwconv2-like GEMMs (
 #   "tf32": fp32-container TF32 operands everywhere (8-bit exponent; the training path).
 BLOCK_OPERANDS = os.environ.get("F2G_BLOCK_OPERANDS", "f16")
 assert BLOCK_OPERANDS in ("f16", "tf32"), BLOCK_OPERANDS
+# pwconv1 -> pwconv2 of a block as ONE chained launch (per-row-tile counters instead of a kernel
+# boundary; fp16 operands only)
+CHAIN_MLP = os.environ.get("F2G_CHAIN_MLP", "1") == "1"
+FORK_COND = os.environ.get("F2G_FORK_COND", "1") == "1"    # conditioning path on a second stream
 
 
 def _ceil(a: int, b: int) -> int:
@@ -145,26 +149,27 @@ class PackedGenerator:
         self.signature = _params_signature(self._plist)
 
 
-def _g1(bw: _BlockW, a, h, M, bn=None):
+def _g1(bw: _BlockW, a, h, M, bn=None, done=None):
     bn = bn or BN_G1
     b = bw.blk
     if a.dtype == torch.float16:          # a1 (fp16) x W1 (fp16) -> h (fp16)
         return L.gemm_desc(a.data_ptr(), bw.half()[0].data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C,
                            bw.H, bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
-                           act=L.ACT_PRELU, ab_f16=1, c_f16=1)
+                           act=L.ACT_PRELU, ab_f16=1, c_f16=1, done_counter=done)
     return L.gemm_desc(a.data_ptr(), bw.W1.data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C, bw.H,
                        bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
                        act=L.ACT_PRELU, round_tf32=1)
 
 
-def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0):
+def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0, wait=None):
     bn = bn or BN_G2
     b = bw.blk
     f16 = h.dtype == torch.float16        # h (fp16) x W2 (fp16) -> x (fp32 residual stream, in place)
     return L.gemm_desc(h.data_ptr(), (bw.half()[1] if f16 else bw.W2).data_ptr(), x.data_ptr(), M, bw.C,
                        bw.H, bw.H, bw.H, bw.C,
                        bn=bn, bias=b.pwconv2.bias.data_ptr(), res=x.data_ptr(), ld_res=bw.C,
-                       res_scale=b.residual_scale.scale.data_ptr(), round_tf32=round_out, ab_f16=int(f16))
+                       res_scale=b.residual_scale.scale.data_ptr(), round_tf32=round_out, ab_f16=int(f16),
+                       wait_counter=wait)
 
 
 class InferencePlan:
@@ -212,7 +217,17 @@ class InferencePlan:
             w.cp = z(self.Rc, bw.nl * bw.C)
             w.mask = z(w.R) if masked else None
             self.br.append(w)
+        # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
+        self.chained = CHAIN_MLP and BLOCK_OPERANDS == "f16"
+        self.ce_chain = torch.zeros((self.Rc + 255) // 256, device=dev, dtype=torch.int32)
+        offs, tot = [], 0
+        for w in self.br:
+            offs.append(tot)
+            tot += (w.R + 255) // 256
+        self.chain = torch.zeros(tot, device=dev, dtype=torch.int32)
+        self.chain_off = offs
         self.t_all: Optional[Tensor] = None
+        self._side: Optional[torch.cuda.Stream] = None
         self.graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
         self._seen: Dict[Tuple[int, bool], bool] = {}
 
@@ -229,10 +244,17 @@ class InferencePlan:
         for li, bw in enumerate(pk.ce_blocks):
             b = bw.blk
             last = li == len(pk.ce_blocks) - 1      # c0 is then only a GEMM operand: RN-round it
-            L.block_pre(self.c0, B, Fm, bw.C, bw.C, bw.dwT, b.dwconv.bias, b.norm.bias,
-                        b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C)
-            L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M)])
-            L.gemm_group([_g2(bw, self.ce_h, self.c0, M, round_out=int(last))])
+            pre = L.block_pre_desc(self.c0, B, Fm, bw.C, bw.C, bw.dwT, b.dwconv.bias, b.norm.bias,
+                                   b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C)
+            if self.chained:
+                L.block_pre_group([pre], zero=self.ce_chain)
+                cnt = self.ce_chain.data_ptr()
+                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M, done=cnt),
+                              _g2(bw, self.ce_h, self.c0, M, round_out=int(last), wait=cnt)])
+            else:
+                L.block_pre_group([pre])
+                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M)])
+                L.gemm_group([_g2(bw, self.ce_h, self.c0, M, round_out=int(last))])
         self.cond_paths()
 
     def cond_paths(self) -> None:
@@ -261,6 +283,12 @@ class InferencePlan:
     # ------------------------------------------------------------------ one model evaluation
     def process_model(self, t_dev: Tensor) -> None:
         """x_audio, cond (cp) -> per-branch windowed iSTFT frames (w.fr).  t_dev: (B,) device."""
+        self.process_front(t_dev)
+        self.process_blocks()
+
+    def process_front(self, t_dev: Tensor) -> None:
+        """The part of one model evaluation that does not read the conditioning: STFT, in_proj,
+        in_norm and the time-embedding path."""
         pk, B, T, Fm = self.pk, self.B, self.T, self.Fm
         L.stft_group([(self.x_audio, w.pin, bw.n_fft, bw.hop, w.F, w.R, T, bw.ldp)
                       for bw, w in zip(pk.branches, self.br)], B, T, round_tf32=1)
@@ -280,6 +308,10 @@ class InferencePlan:
         L.linear_small_group(prob1, 1, L.ACT_SILU)
         L.linear_small_group(prob2, 1, L.ACT_NONE)
         L.linear_small_group(prob3, 1, L.ACT_NONE)
+
+    def process_blocks(self) -> None:
+        """ConvNeXt blocks (read cp, the per-layer conditioning rows), out_proj, inverse FFT."""
+        pk, B, T, Fm = self.pk, self.B, self.T, self.Fm
         nl = pk.branches[0].nl
         for i in range(nl):
             pre = []
@@ -290,6 +322,14 @@ class InferencePlan:
                 pre.append(L.block_pre_desc(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
                                             b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm,
                                             bw.factor, B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C))
+            if self.chained:                # prologues, then pwconv1 -> pwconv2 of all branches: 2 launches
+                L.block_pre_group(pre, zero=self.chain)
+                cnt = [self.chain.data_ptr() + 4 * o for o in self.chain_off]
+                L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R, done=c)
+                              for bw, w, c in zip(pk.branches, self.br, cnt)] +
+                             [_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1), wait=c)
+                              for bw, w, c in zip(pk.branches, self.br, cnt)])
+                continue
             L.block_pre_group(pre)          # the three branches' prologues: one launch
             L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
             L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1))
@@ -319,11 +359,34 @@ class InferencePlan:
         return ts, dt
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
-        if with_cond:
-            self.encode_cond()
         ts, dt = self._steps
+        forked = with_cond and FORK_COND
+        if forked:
+            # The conditioning path (CondEncoder + cond_mlp + cond_proj: ~20 launches of GEMMs with
+            # 36-72 tiles, i.e. at most half the SMs busy) and the front of the first model
+            # evaluation (STFT, in_proj, norms, time MLP: small kernels) are independent: run them
+            # on two streams and join before the first block prologue.  Under stream capture the
+            # fork/join becomes two parallel branches of the graph.
+            if BLOCK_OPERANDS == "f16":        # lazily built fp16 weights: allocate on the main stream
+                for bw in self.pk.ce_blocks:
+                    bw.half()
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.x_audio.device)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                self.encode_cond()
+                join.record(self._side)
+            self.process_front(self.t_all[0])
+            main.wait_event(join)
+        elif with_cond:
+            self.encode_cond()
         for k in range(n):
-            self.process_model(self.t_all[k])
+            if not (forked and k == 0):
+                self.process_front(self.t_all[k])
+            self.process_blocks()
             self.combine(self.x_audio, True, ts[k], dt, clamp and k == n - 1)
 
     def set_masks(self, lens: Tensor) -> None:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 3
+#define F2G_ABI_VERSION 4
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -86,6 +86,19 @@ typedef struct F2GGemm {
    * (multiple of 8); needs a bias+activation or bias-only epilogue (no res / gate / accumulate /
    * c_pre / split_k).  The epilogue itself always runs in fp32.  CTA-pair kernel only. */
   int ab_f16, c_f16;
+  /* Producer -> consumer chaining INSIDE one launch (pwconv1 -> PReLU -> pwconv2 of a ConvNeXt
+   * block without a kernel boundary): a problem with done_counter != NULL adds 1 (release, gpu
+   * scope) to done_counter[m / 256] every time one CTA has stored its 128 rows of one output
+   * tile; a problem with wait_counter != NULL does not read the A rows of the 256-row tile
+   * m / 256 before wait_counter[m / 256] has reached 2 * (number of N tiles of the producer), the
+   * producer being the problem of the SAME group whose done_counter equals this wait_counter
+   * (same M, split_k = 1).  All producer tiles are scheduled before any consumer tile on every
+   * CTA pair, so the launch cannot deadlock as long as its <= 148 CTAs are co-resident -- do not
+   * run two chained groups concurrently on different streams.  The caller zeroes the counters
+   * (ceil(M / 256) ints) before every launch (f2g_block_pre_group can do it: zero_ptr).
+   * CTA-pair kernel only. */
+  int* done_counter;
+  const int* wait_counter;
 } F2GGemm;
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
@@ -173,6 +186,8 @@ typedef struct F2GBlockPre {
   float* conv_out;
   float* inv_rms_out;
   int B, T, C, ld_x, ld_cond, cond_T, factor, zero_row, ld_ts, ld_out;
+  int* zero_ptr; /* problem 0 only: zero_n ints are cleared by this launch (the chaining counters of */
+  int zero_n;    /* the GEMM group that follows in the stream), or NULL */
   int out_f16; /* 1: `out` points to fp16 rows (ld_out in elements, multiple of 4), RN-rounded and
                   clamped to +-65504 instead of TF32-rounded fp32 -- operand of an ab_f16 GEMM */
 } F2GBlockPre;

@@ -200,6 +200,67 @@ def test_gemm_f16_group_matches_tf32_group(L):
         assert rel_rms(C16, C32) < 1e-5
 
 
+@pytest.mark.parametrize("shapes", [
+    ((1520, 768), (3024, 512), (6032, 384)),          # the three branches of one block (bench shape)
+    ((1505, 512),),                                   # CondEncoder block (+ the zero row)
+    ((300, 384), (77, 512)),                          # fewer tiles than CTA pairs
+])
+def test_gemm_chained_mlp_matches_two_launches(L, shapes):
+    """pwconv1 -> PReLU -> pwconv2 (+ residual) as ONE chained launch (per-row-tile counters) must
+    give bit-identical results to the two-launch sequence (modules.py:486-493), repeatedly."""
+    g = torch.Generator().manual_seed(len(shapes) * 100 + shapes[0][0])
+    keep, chained, g1s, g2s = [], [], [], []
+    n_cnt = sum((M + 255) // 256 for M, _ in shapes)
+    cnt = torch.zeros(n_cnt, dtype=torch.int32, device="cuda")
+    off = 0
+    for M, C in shapes:
+        H = 3 * C
+        a = torch.randn(M, C, generator=g).half().cuda()
+        W1 = (torch.randn(H, C, generator=g) * 0.04).half().cuda()
+        W2 = (torch.randn(C, H, generator=g) * 0.03).half().cuda()
+        b1, sl = torch.randn(H, generator=g).cuda(), (torch.rand(H, generator=g) * 0.5).cuda()
+        b2, rs = torch.randn(C, generator=g).cuda(), (torch.rand(C, generator=g) + 0.5).cuda()
+        x0 = torch.randn(M, C, generator=g).cuda()
+        xa, xb = x0.clone(), x0.clone()
+        ha = torch.zeros(M, H, dtype=torch.float16, device="cuda")
+        hb = torch.zeros(M, H, dtype=torch.float16, device="cuda")
+        keep += [a, W1, W2, b1, sl, b2, rs, x0, xa, xb, ha, hb]
+        cp = cnt.data_ptr() + 4 * off
+        off += (M + 255) // 256
+
+        def d1(h, done=None):
+            return L.gemm_desc(a.data_ptr(), W1.data_ptr(), h.data_ptr(), M, H, C, C, C, H, bias=b1.data_ptr(),
+                               slope=sl.data_ptr(), act=L.ACT_PRELU, ab_f16=1, c_f16=1, done_counter=done)
+
+        def d2(h, x, wait=None):
+            return L.gemm_desc(h.data_ptr(), W2.data_ptr(), x.data_ptr(), M, C, H, H, H, C, bias=b2.data_ptr(),
+                               res=x.data_ptr(), ld_res=C, res_scale=rs.data_ptr(), ab_f16=1, wait_counter=wait)
+        g1s.append(d1(ha)); g2s.append(d2(ha, xa))
+        chained += [(d1(hb, cp), d2(hb, xb, cp), x0, xa, xb, ha, hb)]
+    L.gemm_group(g1s)
+    L.gemm_group(g2s)
+    torch.cuda.synchronize()
+    descs = [c[0] for c in chained] + [c[1] for c in chained]
+    for it in range(12):
+        cnt.zero_()
+        for _, _, x0, xa, xb, ha, hb in chained:
+            xb.copy_(x0)
+            hb.fill_(float("nan"))                  # a consumer that runs ahead of its producer reads NaN
+        L.gemm_group(descs)
+        torch.cuda.synchronize()
+        for _, _, x0, xa, xb, ha, hb in chained:
+            assert torch.equal(hb, ha), it
+            assert torch.equal(xb, xa), (it, float((xb - xa).abs().max()))
+    # sanity of the reference sequence itself against float64
+    d1_, d2_, x0, xa, xb, ha, hb = chained[0]
+    M, C = shapes[0]
+    a, W1, W2, b1, sl, b2, rs = keep[:7]
+    z = a.double().cpu() @ W1.double().cpu().t() + b1.double().cpu()
+    h = torch.where(z > 0, z, z * sl.double().cpu()).half().double()
+    exp = h @ W2.double().cpu().t() + b2.double().cpu() + rs.double().cpu() * x0.double().cpu()
+    assert rel_rms(xa.cpu(), exp) < 3e-4
+
+
 @pytest.mark.parametrize("n_fft,hop", [(128, 64), (256, 128), (512, 256), (1024, 512), (32, 8), (2048, 512)])
 def test_stft_packed(L, n_fft, hop):
     B, T = 3, 6144

@@ -59,5 +59,16 @@ if os.path.exists(rep):
     for d in ms:
         md.append(f"| {d.get('grid')} | {d.get('time_us')} | {d.get('dram_read')} {d.get('dram_read_unit','')} | {d.get('dram_write')} {d.get('dram_write_unit','')} | {d.get('tensor_pct_active')} | {d.get('dram_pct')} | {d.get('l2_pct')} | {d.get('regs')} |")
     json.dump(ms, open(os.path.join(OUT, f"{tag}_gemm_metrics.json"), "w"), indent=1)
+    # bench.py's roofline.traffic: dram bytes per launch of the dominant kernel (fp16-operand
+    # instantiation: last template argument 1; falls back to all pair-GEMM launches)
+    def _bytes(v, unit):
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        return float(v.replace(",", "")) * scale
+    dom = [d for d in ms if d.get("kernel", "").rstrip(">").endswith(", 1") ] or ms
+    tot = [_bytes(d["dram_read"], d.get("dram_read_unit", "byte")) + _bytes(d["dram_write"], d.get("dram_write_unit", "byte")) for d in dom]
+    json.dump({"kernel": dom[0].get("kernel"), "launches": len(dom), "dram_bytes_per_launch_avg": sum(tot) / len(tot),
+               "source": f"profiles/{tag}_gemm_metrics.json (ncu --set full --clock-control none, tools/one_step.py; "
+                         "ncu flushes L2 before every kernel, so weights AND activations are re-read from HBM)"},
+              open(os.path.join(OUT, "gemm_traffic.json"), "w"), indent=1)
 open(os.path.join(OUT, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md)[:6000])
