@@ -850,6 +850,30 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     for (int j = i; j > 0 && before(order[j], order[j - 1]); --j) {
       const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
     }
+  // N tile per problem.  Few-row groups (CondEncoder: 6 row tiles) would leave most CTA pairs
+  // idle with the byte-optimal wide tiles and are bound by one tile's latency chain: narrow the
+  // tiles (>= 64 columns) until the group has at least ~one tile per pair.
+  int bns[F2G_GEMM_MAX_PROBLEMS];
+  {
+    static const int fill = getenv("F2G_PAIR_FILL") ? atoi(getenv("F2G_PAIR_FILL")) : 1;
+    const int step = b_mn ? 64 : 32;
+    for (int oi = 0; oi < n; ++oi) bns[oi] = pick_bn(descs[order[oi]].N, b_mn != 0);
+    for (int round = 0; fill && round < 3; ++round) {
+      long tl = 0;
+      for (int oi = 0; oi < n; ++oi) {
+        const F2GGemm& d = descs[order[oi]];
+        const int sk = d.split_k < 1 ? 1 : d.split_k;
+        tl += (long)((d.M + 2 * PBM - 1) / (2 * PBM)) * ((d.N + bns[oi] - 1) / bns[oi]) * sk;
+      }
+      if (tl >= 56) break;
+      bool changed = false;
+      for (int oi = 0; oi < n; ++oi) {
+        const int nb = ((bns[oi] / 2 + step - 1) / step) * step;
+        if (nb >= 64 && nb < bns[oi]) { bns[oi] = nb; changed = true; }
+      }
+      if (!changed) break;
+    }
+  }
   int tiles = 0;
   for (int oi = 0; oi < n; ++oi) {
     const F2GGemm& d = descs[order[oi]];
@@ -870,7 +894,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
       return F2G_EINVAL;
     }
     PProblem& p = g.p[oi];
-    const int bn = pick_bn(d.N, b_mn != 0);
+    const int bn = bns[oi];
     int rc;
     if (d.a_seg_len && ((d.a_seg_len & 31) || d.a_rows <= 0)) {
       set_error("windowed gemm operand: a_seg_len=%d must be a multiple of 32 and a_rows=%d > 0",
