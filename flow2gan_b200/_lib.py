@@ -211,6 +211,21 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     return d
 
 
+def pick_split_k(M: int, N: int, K: int, pairs: int = 74, max_split: int = 64) -> int:
+    """K split of a weight-gradient GEMM (C pre-zeroed, atomic epilogue): minimises
+    waves x (k-blocks per tile + a per-tile overhead) over the 74 CTA pairs -- e.g. 80 tiles of
+    341 k-blocks run 2 half-empty waves unsplit, 8 full waves of 49 k-blocks with split 7."""
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    kb = (K + 31) // 32
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(max_split, kb // 8)) + 1):
+        per = (kb + s - 1) // s
+        cost = ((tiles * s + pairs - 1) // pairs) * (per + 8)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
 def gemm_group(descs: Sequence[F2GGemm]) -> None:
     n = len(descs)
     arr = (F2GGemm * n)(*descs)

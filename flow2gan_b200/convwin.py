@@ -103,10 +103,6 @@ def _round_inplace(w: Tensor) -> None:
     L.pack2d(w.data_ptr(), cols, 1, rows, cols, w.data_ptr(), cols, cols, 1)
 
 
-def _split_k(g_tiles: int, kblocks: int) -> int:
-    return max(1, min(148 // max(g_tiles, 1), kblocks // 8))
-
-
 class _ConvWinFn(torch.autograd.Function):
     """y = leaky_relu(conv2d(x, stride (1, sw)) + b) on channel-last (Nb, H, W, C) ->
     (Nb, Ho, Wo, Co); the result is a strided view of the (Nb, Hl, R, Cop) GEMM output."""
@@ -149,9 +145,8 @@ class _ConvWinFn(torch.autograd.Function):
         gW = gb = gx = None
         if ctx.needs_input_grad[1]:
             dwt = torch.zeros(g.K, Cop, device=dev, dtype=torch.float32)
-            tiles = _ceil(g.K, 256) * _ceil(g.Co, 256)
             L.gemm_group([L.gemm_desc(xp.data_ptr(), dz.data_ptr(), dwt.data_ptr(), g.K, g.Co, g.M, sw * C, Cop, Cop,
-                                      a_mn=1, b_mn=1, split_k=_split_k(tiles, _ceil(g.M, 32)),
+                                      a_mn=1, b_mn=1, split_k=L.pick_split_k(g.K, g.Co, g.M),
                                       a_seg_len=g.seg, a_seg_shift=g.R, a_rows=g.M)])
             gW = dwt.view(g.kh, g.kw, C, Cop)[..., :g.Co].permute(3, 2, 0, 1).contiguous()
         if ctx.needs_input_grad[2]:

@@ -5,8 +5,10 @@
 // from flow2gan/models/modules.py:68-84,105-116 and the torchaudio (Mel)Spectrogram wrappers.
 #include "common.cuh"
 #include "../../include/flow2gan_b200.h"
+#include "fft_warp.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 
 namespace f2g {
 
@@ -210,6 +212,62 @@ __global__ void irfft_group_kernel(const __grid_constant__ SpecGroupArgs g) {
   pdl_wait();
   pdl_launch();
   irfft_frame(g.in[pi], g.ld_in[pi], g.n[pi], g.logn[pi], g.out[pi], blockIdx.x - g.row_begin[pi]);
+}
+
+// ---- warp-per-frame versions (n_fft <= 1024): 8 frames per CTA, no block barriers ---------------
+constexpr int FFT_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * FFT_WARPS) stft_group_warp_kernel(const __grid_constant__ SpecGroupArgs g) {
+  __shared__ float srow[FFT_WARPS][2][FFT_WARP_ROW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_all = blockIdx.x * FFT_WARPS + warp;
+  pdl_wait();
+  pdl_launch();
+  if (row_all >= g.row_begin[g.np]) return;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < g.np && row_all >= g.row_begin[i]) pi = i;
+  const int row = row_all - g.row_begin[pi];
+  const int n = g.n[pi], frames = g.frames[pi];
+  const int bi = row / frames, f = row - bi * frames;
+  const float* x = g.in[pi] + (size_t)bi * g.ld_in[pi];
+  float* o = g.out[pi] + (size_t)row * g.ld_out[pi];
+  const int start = f * g.hop[pi] - (n >> 1);
+  float* sre = srow[warp][0];
+  float* sim = srow[warp][1];
+  const bool rnd = g.round_tf32 != 0;
+  switch (n) {
+    case 128: warp_rfft_packed<2>(x, g.T, start, o, g.ld_out[pi], rnd, sre, sim, lane); break;
+    case 256: warp_rfft_packed<4>(x, g.T, start, o, g.ld_out[pi], rnd, sre, sim, lane); break;
+    case 512: warp_rfft_packed<8>(x, g.T, start, o, g.ld_out[pi], rnd, sre, sim, lane); break;
+    default: warp_rfft_packed<16>(x, g.T, start, o, g.ld_out[pi], rnd, sre, sim, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__(32 * FFT_WARPS) irfft_group_warp_kernel(const __grid_constant__ SpecGroupArgs g) {
+  __shared__ float srow[FFT_WARPS][2][FFT_WARP_ROW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_all = blockIdx.x * FFT_WARPS + warp;
+  pdl_wait();
+  pdl_launch();
+  if (row_all >= g.row_begin[g.np]) return;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < g.np && row_all >= g.row_begin[i]) pi = i;
+  const int row = row_all - g.row_begin[pi];
+  const int n = g.n[pi];
+  const float* pk = g.in[pi] + (size_t)row * g.ld_in[pi];
+  float* fr = g.out[pi] + (size_t)row * n;
+  float* sre = srow[warp][0];
+  float* sim = srow[warp][1];
+  switch (n) {
+    case 128: warp_irfft_frame<2>(pk, fr, sre, sim, lane); break;
+    case 256: warp_irfft_frame<4>(pk, fr, sre, sim, lane); break;
+    case 512: warp_irfft_frame<8>(pk, fr, sre, sim, lane); break;
+    default: warp_irfft_frame<16>(pk, fr, sre, sim, lane); break;
+  }
 }
 
 struct OlaArgs {
@@ -444,6 +502,19 @@ static int spec_group_fill(SpecGroupArgs& g, const F2GSpecProblem* probs, int np
   return 0;
 }
 
+// The warp-per-frame kernels cover n_fft 128..1024 (F2G_FFT_SMEM=1 forces the shared-memory
+// Stockham kernels -- A/B testing).
+static bool spec_group_warp_ok(const F2GSpecProblem* probs, int np) {
+  static const int force_smem = getenv("F2G_FFT_SMEM") ? atoi(getenv("F2G_FFT_SMEM")) : 0;
+  if (force_smem) return false;
+  for (int i = 0; i < np; ++i) {
+    const int n = probs[i].n_fft;
+    if (n != 128 && n != 256 && n != 512 && n != 1024) return false;
+    if ((probs[i].ld_out & 1) || (reinterpret_cast<uintptr_t>(probs[i].out) & 7)) return false;
+  }
+  return true;
+}
+
 extern "C" int f2g_stft_group(const F2GSpecProblem* probs, int np, int B, int T, int round_tf32,
                               void* stream) {
   SpecGroupArgs g;
@@ -462,6 +533,17 @@ extern "C" int f2g_stft_group(const F2GSpecProblem* probs, int np, int B, int T,
   }
   g.T = T;
   g.round_tf32 = round_tf32;
+  if (spec_group_warp_ok(probs, np)) {      // warp-per-frame shuffle FFT
+    if (int rc = fft_roots_init()) return rc;
+    const int rows = g.row_begin[np];
+    cudaError_t le = launch_pdl(stft_group_warp_kernel, dim3((rows + FFT_WARPS - 1) / FFT_WARPS),
+                                dim3(32 * FFT_WARPS), 0, static_cast<cudaStream_t>(stream), g);
+    if (le != cudaSuccess) {
+      set_error("f2g_stft_group launch: %s", cudaGetErrorString(le));
+      return (int)le;
+    }
+    return check_launch("f2g_stft_group");
+  }
   const int threads = max_n / 2 < 32 ? 32 : max_n / 2;
   const size_t smem = (size_t)(2 * max_n + max_n / 2) * sizeof(float2) + (max_n / 2 + 1) * sizeof(float);
   cudaError_t le = launch_pdl(stft_group_kernel, dim3(g.row_begin[np]), dim3(threads), smem,
@@ -477,6 +559,17 @@ extern "C" int f2g_irfft_group(const F2GSpecProblem* probs, int np, void* stream
   SpecGroupArgs g;
   int max_n = 0;
   if (int rc = spec_group_fill(g, probs, np, "f2g_irfft_group", &max_n)) return rc;
+  if (spec_group_warp_ok(probs, np)) {
+    if (int rc = fft_roots_init()) return rc;
+    const int rows = g.row_begin[np];
+    cudaError_t le = launch_pdl(irfft_group_warp_kernel, dim3((rows + FFT_WARPS - 1) / FFT_WARPS),
+                                dim3(32 * FFT_WARPS), 0, static_cast<cudaStream_t>(stream), g);
+    if (le != cudaSuccess) {
+      set_error("f2g_irfft_group launch: %s", cudaGetErrorString(le));
+      return (int)le;
+    }
+    return check_launch("f2g_irfft_group");
+  }
   const int threads = max_n / 2 < 32 ? 32 : max_n / 2;
   const size_t smem = (size_t)(2 * max_n + max_n / 2) * sizeof(float2);
   cudaError_t le = launch_pdl(irfft_group_kernel, dim3(g.row_begin[np]), dim3(threads), smem,

@@ -62,9 +62,7 @@ class _Conv2dCLFn(torch.autograd.Function):
         gW = gb = gx = None
         if ctx.needs_input_grad[1]:
             dWp = torch.zeros(Cop, ldk, device=dev)
-            tiles = ((Co + 127) // 128) * ((K + 127) // 128)
-            kb = (M + 31) // 32
-            split = max(1, min(296 // max(tiles, 1), kb // 8))
+            split = L.pick_split_k(Co, K, M)
             L.gemm_group([L.gemm_desc(dz.data_ptr(), col.data_ptr(), dWp.data_ptr(), Co, K, M, Cop, ldk, ldk,
                                       bn=128, a_mn=1, b_mn=1, split_k=split)])
             gW = torch.empty(Co, Ci, kh, kw, device=dev)

@@ -149,10 +149,11 @@ def _blocks_backward(blocks_w, saves, dxo: Tensor, B: int, T: int, C: int, mask,
         L.gemm_group([_nn(dxo, C, bw.W2, H, dh, H, R, H, C, bn=BN_G1)])
         g_b1, g_sl = _z(H, dev=dev), _z(H, dev=dev)
         L.act_bwd(dh, H, s.hpre, H, b.act.weight, 0.0, L.ACT_PRELU, R, H, dh, H, g_b1, g_sl, round_tf32=1)
-        gW2 = _e(C, H, dev=dev)
-        gW1 = _e(H, C, dev=dev)
-        L.gemm_group([_tn(dxo, C, s.h, H, gW2, H, C, H, R)])
-        L.gemm_group([_tn(dh, H, s.a1, C, gW1, C, H, C, R)])
+        sk = L.pick_split_k(C, H, R)                # few output tiles, long K: split over the CTA pairs
+        gW2 = _z(C, H, dev=dev) if sk > 1 else _e(C, H, dev=dev)
+        gW1 = _z(H, C, dev=dev) if sk > 1 else _e(H, C, dev=dev)
+        L.gemm_group([_tn(dxo, C, s.h, H, gW2, H, C, H, R, split_k=sk)])
+        L.gemm_group([_tn(dh, H, s.a1, C, gW1, C, H, C, R, split_k=sk)])
         da1 = _e(R, C, dev=dev)
         L.gemm_group([_nn(dh, H, bw.W1, C, da1, C, R, C, H, bn=BN_G2)])
         dy, coef, gs = _e(R, C, dev=dev), _e(R, dev=dev), _e(R, dev=dev)

@@ -275,6 +275,43 @@ def test_stft_packed(L, n_fft, hop):
     assert float(out[:, n_fft + 2:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n_ffts,T", [((512, 256, 128), 6144), ((1024, 512, 256), 7168), ((256,), 1000)])
+def test_warp_fft_group_vs_oracle(L, n_ffts, T):
+    """Grouped warp-shuffle STFT / inverse (one launch for the branch resolutions,
+    modules.py:699-719) against the oracle's torch.stft / istft restatement; hop = n/2, reflect
+    edges on both sides, TF32 rounding off."""
+    B = 3
+    x = audio_input(B, T, seed=T)
+    xg = x.cuda()
+    outs, probs = [], []
+    for n in n_ffts:
+        hop = n // 2
+        F = 1 + T // hop
+        ld = n + 4
+        o = torch.full((B * F, ld), 7.0, device="cuda")
+        outs.append((n, hop, F, ld, o))
+        probs.append((xg, o, n, hop, F, B * F, T, ld))
+    L.stft_group(probs, B, T, round_tf32=0)
+    frs, iprobs = [], []
+    for n, hop, F, ld, o in outs:
+        ref = O.stft_packed(x, n, hop)
+        got = o.cpu().view(B, F, ld)[:, :, : n + 2].transpose(1, 2)
+        assert rel_rms(got, ref) < 2e-6, n
+        assert float(o[:, n + 2:].abs().max()) == 0.0
+        fr = torch.empty(B * F, n, device="cuda")
+        frs.append(fr)
+        iprobs.append((o, fr, n, 0, 0, B * F, ld, n))
+    L.irfft_group(iprobs)
+    for (n, hop, F, ld, o), fr in zip(outs, frs):
+        ref_fr = torch.empty(B * F, n, device="cuda")
+        L.irfft_frames(o, B * F, ld, n, ref_fr)               # shared-memory Stockham kernel
+        assert rel_rms(fr, ref_fr) < 2e-6, n
+        out = torch.empty(B, T, device="cuda")
+        L.ola_combine([fr], [n], [hop], [F], None, None, out, B, T, False, 0.0, 0.0, False)
+        keep = hop * (F - 1)
+        assert rel_rms(out.cpu()[:, :keep], x[:, :keep]) < 3e-6      # STFT -> iSTFT round trip
+
+
 def test_logmel_fused_vs_oracle_and_fixture():
     import os
     from _cases import GOLDEN
