@@ -33,7 +33,7 @@ const char* f2g_last_error(void);
 int f2g_check_device(void);
 
 /* ---------------------------------------------------------------------------------------
- * Tensor-core contraction  C[M,N] = epi(alpha * A[M,K] . B[N,K]^T)   (tcgen05 kind::tf32)
+ * Tensor-core contraction  C[M,N] = epi(alpha * A[M,K] . B[N,K]^T)   (tcgen05 kind::tf32 / kind::f16)
  * replaces: nn.Conv1d(kernel_size=1) / nn.Linear (flow2gan/models/modules.py:443-451,
  * 563,570-579,593) and, via overlapping-row operands, nn.Conv2d of the discriminators
  * (flow2gan/models/discriminators.py:65-76,171-184) plus their dgrad / wgrad.
