@@ -21,6 +21,7 @@ from torch import Tensor
 from . import _lib as L
 
 
+import operator
 import os
 
 BN_G1 = int(os.environ.get("F2G_BN1", "128"))   # N tile of pwconv1-like GEMMs (wide N)
@@ -45,14 +46,14 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+_version_of = operator.attrgetter("_version")
+
+
 def _params_signature(plist) -> Tuple[int, int]:
     """Cheap change detector over a cached parameter list: in-place updates (optimizer steps,
     load_state_dict) bump tensor versions; storage moves go through Module._apply, which drops
     the packed weights altogether.  (Walking model.parameters() each call cost 0.5 ms.)"""
-    v = 0
-    for p in plist:
-        v += p._version
-    return v, plist[0].data_ptr()
+    return sum(map(_version_of, plist)), plist[0].data_ptr()
 
 
 def _pack(src: Tensor, rows: int, cols: int, rs: int, cs: int, ld: int, rnd: int = 1,

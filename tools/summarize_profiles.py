@@ -64,7 +64,8 @@ if os.path.exists(rep):
     def _bytes(v, unit):
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
         return float(v.replace(",", "")) * scale
-    dom = [d for d in ms if d.get("kernel", "").rstrip(">").endswith(", 1") ] or ms
+    import re
+    dom = [d for d in ms if re.search(r"gemm_pair_kernel<\d+, \d+, \d+, 1>", d.get("kernel", ""))] or ms
     tot = [_bytes(d["dram_read"], d.get("dram_read_unit", "byte")) + _bytes(d["dram_write"], d.get("dram_write_unit", "byte")) for d in dom]
     json.dump({"kernel": dom[0].get("kernel"), "launches": len(dom), "dram_bytes_per_launch_avg": sum(tot) / len(tot),
                "source": f"profiles/{tag}_gemm_metrics.json (ncu --set full --clock-control none, tools/one_step.py; "
