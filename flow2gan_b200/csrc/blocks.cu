@@ -65,6 +65,7 @@ struct BlockPreArgs {
   int cta_begin[5];     // prefix sums of CTAs per problem
   int tl[4];            // token lanes per CTA
   int ctas_t[4];        // CTAs along T per batch element
+  int fshift[4];        // log2(factor) if factor is a power of two, else -1
   int n;
 };
 
@@ -108,15 +109,23 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   }
   if (live) {
     float4 xv[PRE_S + 6];
+    if (!row_mask && t0 >= 3 && t0 + PRE_S + 3 <= T) {
+      // interior window without a length mask (every CTA but the two at the sequence ends of an
+      // unmasked batch): one base pointer, no per-row bounds or mask tests
+      const float* xp = x + (rb + (size_t)(t0 - 3)) * ld_x + c;
 #pragma unroll
-    for (int j = 0; j < PRE_S + 6; ++j) {
-      const int tt = t0 - 3 + j;
-      xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tt >= 0 && tt < T) {
-        const float mk = row_mask ? row_mask[rb + tt] : 1.f;
-        if (mk != 0.f) {
-          const float4 v = ld4(x + (rb + tt) * ld_x + c);
-          xv[j] = make_float4(v.x * mk, v.y * mk, v.z * mk, v.w * mk);
+      for (int j = 0; j < PRE_S + 6; ++j) xv[j] = ld4(xp + (size_t)j * ld_x);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PRE_S + 6; ++j) {
+        const int tt = t0 - 3 + j;
+        xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tt >= 0 && tt < T) {
+          const float mk = row_mask ? row_mask[rb + tt] : 1.f;
+          if (mk != 0.f) {
+            const float4 v = ld4(x + (rb + tt) * ld_x + c);
+            xv[j] = make_float4(v.x * mk, v.y * mk, v.z * mk, v.w * mk);
+          }
         }
       }
     }
@@ -136,12 +145,18 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     }
     // the window registers are dead now: fetch the conditioning rows under the reduction
     if (P.cond) {
+      // conditioning row of token t: frame t / factor (factor is 1, 2 or 4 in every released
+      // config: shift), or the all-zero row past the last mel frame
+      const int fsh = a.fshift[pi];
+      const int t_cond = P.cond_T * P.factor;
+      const float* cbase = P.cond + c;
 #pragma unroll
       for (int s = 0; s < PRE_S; ++s) {
         const int t = t0 + s;
         if (t < T) {
-          const int crow = t < P.cond_T * P.factor ? bi * P.cond_T + t / P.factor : P.zero_row;
-          cv[s] = ld4(P.cond + (size_t)crow * P.ld_cond + c);
+          const int fr = fsh >= 0 ? (t >> fsh) : t / P.factor;
+          const int crow = t < t_cond ? bi * P.cond_T + fr : P.zero_row;
+          cv[s] = ld4(cbase + (size_t)crow * P.ld_cond);
         }
       }
     }
@@ -328,6 +343,9 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
       set_error("f2g_block_pre: channels=%d must be >= %d", p.C, PRE_THREADS);
       return F2G_EINVAL;
     }
+    a.fshift[i] = -1;
+    for (int sft = 0; sft < 16; ++sft)
+      if (p.factor == (1 << sft)) a.fshift[i] = sft;
     int tl = PRE_THREADS / (p.C / 4);
     if (tl > PRE_MAX_TL) tl = PRE_MAX_TL;
     a.tl[i] = tl;

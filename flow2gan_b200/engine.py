@@ -395,17 +395,33 @@ class InferencePlan:
         for bw, w in zip(self.pk.branches, self.br):
             L.frame_mask(self.lens, self.B, w.F, bw.hop, w.mask)
 
-    def infer(self, mel: Tensor, noise: Tensor, lens: Optional[Tensor], n: int, clamp: bool,
-              use_graph: bool = True) -> Tensor:
-        self.mel.copy_(mel)
-        self.x_audio.copy_(noise)
+    def infer(self, mel: Tensor, noise: Optional[Tensor], lens: Optional[Tensor], n: int, clamp: bool,
+              use_graph: bool = True, noise_scale: float = 1.0, out: Optional[Tensor] = None) -> Tensor:
+        """`mel` may live on the host (pinned or not): it is copied straight into the plan's static
+        input buffer.  `noise=None` draws randn * noise_scale from torch's global CUDA generator
+        directly into the sample buffer (same draw as the reference's `torch.randn(...) * scale`,
+        generator.py:356).  `out` (optional, host or device) receives the audio instead of a fresh
+        device tensor."""
+        self.mel.copy_(mel, non_blocking=True)
+        if noise is None:
+            torch.randn(self.x_audio.shape, out=self.x_audio)
+            self.x_audio.mul_(noise_scale)
+        else:
+            self.x_audio.copy_(noise, non_blocking=True)
         if self.masked:
             self.set_masks(lens)
         key = (n, bool(clamp))
+
+        def result() -> Tensor:
+            if out is None:
+                return self.x_audio.clone()
+            out.copy_(self.x_audio, non_blocking=True)
+            return out
+
         if not use_graph:
             self._steps = self._prepare_steps(n)
             self._run(n, clamp)
-            return self.x_audio.clone()
+            return result()
         g = self.graphs.get(key)
         if g is None and not self._seen.get(key):
             # first call for this (weights, shape): run eagerly; capture on the second call, so a
@@ -413,11 +429,12 @@ class InferencePlan:
             self._seen[key] = True
             self._steps = self._prepare_steps(n)
             self._run(n, clamp)
-            return self.x_audio.clone()
+            return result()
         if g is None:
+            x0 = self.x_audio.clone()
             self._steps = self._prepare_steps(n)
             self._run(n, clamp)                     # warm-up (also sets kernel attributes)
-            self.x_audio.copy_(noise)
+            self.x_audio.copy_(x0)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -426,7 +443,7 @@ class InferencePlan:
         else:
             g, self._steps, self.t_all = g
         g.replay()
-        return self.x_audio.clone()
+        return result()
 
     def infer_from_cond(self, cond: Tensor, noise: Tensor, lens: Optional[Tensor], n: int,
                         clamp: bool) -> Tensor:

@@ -152,13 +152,20 @@ class MelAudioGenerator(BaseAudioGenerator):
         return cond
 
     def infer(self, cond: Tensor, audio_lens: Optional[Tensor] = None, n_timesteps: int = 1,
-              clamp_pred: bool = False, noise: Optional[Tensor] = None) -> Tensor:
+              clamp_pred: bool = False, noise: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
         """mel (B, n_mels, F) -> audio (B, T); T = F*mel_hop_length or audio_lens.max().
         `noise` (optional, extension) pins the initial noise; by default it is drawn from
         torch's global RNG exactly like the reference (generator.py:356).
+        Extensions for host-side callers: `cond` may be a host tensor (copied straight into the
+        launch graph's input buffer) and `out` (host, ideally pinned, or device) receives the audio
+        asynchronously on the current stream instead of a new device tensor.
         With grad enabled and parameters requiring grad this call is differentiable (GAN
         G-phase, gan.py:138-143) and runs through flow2gan_b200.train instead of the graph."""
         self._require_cuda()
+        dev = next(self.parameters()).device
+        differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if differentiable or (self.training and self.max_add_noise_scale > 0.0):
+            cond = cond.to(dev)
         cond = self._maybe_noisy_cond(cond)
         if audio_lens is None:
             length = cond.shape[2] * self.mel_hop_length
@@ -166,14 +173,15 @@ class MelAudioGenerator(BaseAudioGenerator):
             length = self._static_length        # whole-step graph capture: no host read-back
         else:
             length = int(audio_lens.max().item())
-        if noise is None:
-            noise = torch.randn((cond.shape[0], length), device=cond.device, dtype=cond.dtype) \
-                * self.init_noise_scale
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if differentiable:
+            if noise is None:
+                noise = torch.randn((cond.shape[0], length), device=dev, dtype=cond.dtype) * self.init_noise_scale
             from .train import generator_infer_with_grad
             return generator_infer_with_grad(self, cond, noise, audio_lens, n_timesteps, clamp_pred)
         p = self.plan(cond.shape[0], cond.shape[2], length, audio_lens is not None)
         with torch.no_grad():
-            # inside an outer stream capture the plan's launches become part of that graph
-            return p.infer(cond.float(), noise.float(), audio_lens, n_timesteps, clamp_pred,
-                           use_graph=not torch.cuda.is_current_stream_capturing())
+            # inside an outer stream capture the plan's launches become part of that graph;
+            # noise=None: drawn from the global RNG straight into the plan's sample buffer
+            return p.infer(cond, None if noise is None else noise.float(), audio_lens, n_timesteps, clamp_pred,
+                           use_graph=not torch.cuda.is_current_stream_capturing(),
+                           noise_scale=self.init_noise_scale, out=out)

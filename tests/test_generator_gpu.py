@@ -85,6 +85,12 @@ def test_infer_bench_shape_vs_oracle_and_rng_semantics():
     nz = torch.randn((16, 24064), device="cuda") * 0.1
     b = m.infer(mel.cuda(), n_timesteps=1, noise=nz)
     assert torch.equal(a, b)
+    # host-side extension: pinned host mel in, pinned host audio out -- same numbers
+    torch.manual_seed(123)
+    out_pin = torch.empty(16, 24064).pin_memory()
+    r = m.infer(mel.pin_memory(), n_timesteps=1, out=out_pin)
+    torch.cuda.synchronize()
+    assert r is out_pin and torch.equal(out_pin, a.cpu())
     # parameters changed in place -> packed weights refresh automatically
     with torch.no_grad():
         m.estimators[0].decoder.out_proj.bias.add_(0.5)
