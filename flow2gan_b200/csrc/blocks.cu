@@ -66,6 +66,7 @@ struct BlockPreArgs {
   int tl[4];            // token lanes per CTA
   int ctas_t[4];        // CTAs along T per batch element
   int fshift[4];        // log2(factor) if factor is a power of two, else -1
+  float inv_ctas_t[4], inv_c4[4];
   int n;
 };
 
@@ -81,8 +82,9 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   const int c4 = C >> 2;
   const int TL = a.tl[pi];
   const int local = blockIdx.x - a.cta_begin[pi];
-  const int bi = local / a.ctas_t[pi];
-  const int ty = threadIdx.x / c4;
+  // two small exact integer divisions done in fp32 (operands < 2^20)
+  const int bi = __float2int_rd(((float)local + 0.5f) * a.inv_ctas_t[pi]);
+  const int ty = __float2int_rd(((float)threadIdx.x + 0.5f) * a.inv_c4[pi]);
   const int tx = threadIdx.x - ty * c4;
   const int t0 = ((local - bi * a.ctas_t[pi]) * TL + ty) * PRE_S;
   const bool live = ty < TL && t0 < T;
@@ -170,21 +172,40 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     }
   }
   // c4 is a multiple of 32, so each warp belongs to exactly one token lane
+  if (PRE_S == 4) {
+    // the four tokens' sums in ONE butterfly (6 shuffles instead of 20): fold tokens {2,3} onto the
+    // upper half-warp, then {1} / {3} onto the odd quarter-warps, then reduce within 8 lanes;
+    // lane 8k ends up with the warp total of token k
+    const int lane = threadIdx.x & 31;
+    const bool hi = (lane & 16) != 0;
+    const float k0 = hi ? ssq[2] : ssq[0], k1 = hi ? ssq[3] : ssq[1];
+    const float s0 = hi ? ssq[0] : ssq[2], s1 = hi ? ssq[1] : ssq[3];
+    const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+    const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool b8 = (lane & 8) != 0;
+    float q = (b8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, b8 ? r0 : r1, 8);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    if ((lane & 7) == 0 && ty < PRE_MAX_TL) red[ty * PRE_S + (lane >> 3)][wid] = q;
+  } else {
 #pragma unroll
-  for (int s = 0; s < PRE_S; ++s) {
-    const float r = warp_sum(ssq[s]);
-    if ((threadIdx.x & 31) == 0 && ty < PRE_MAX_TL) red[ty * PRE_S + s][wid] = r;
+    for (int s = 0; s < PRE_S; ++s) {
+      const float r = warp_sum(ssq[s]);
+      if ((threadIdx.x & 31) == 0 && ty < PRE_MAX_TL) red[ty * PRE_S + s][wid] = r;
+    }
   }
   __syncthreads();
   if (!live) return;
   const float gain = expf(*P.bn_log_scale);
+  const float inv_c = 1.0f / (float)C;
 #pragma unroll
   for (int s = 0; s < PRE_S; ++s) {
     const int t = t0 + s;
     if (t >= T) break;
     float tot = 0.f;
     for (int j = 0; j < nw; ++j) tot += red[ty * PRE_S + s][j];
-    const float inv = (1.0f / sqrtf(tot / (float)C)) * gain;
+    const float inv = rsqrtf(tot * inv_c) * gain;      // 2 ulp; the result is rounded to 11 bits below
     if (P.inv_rms_out && tx == 0) P.inv_rms_out[rb + t] = inv;
     float4 z = make_float4(acc[s].x * inv, acc[s].y * inv, acc[s].z * inv, acc[s].w * inv);
     z.x += cv[s].x; z.y += cv[s].y; z.z += cv[s].z; z.w += cv[s].w;
@@ -350,6 +371,8 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
     if (tl > PRE_MAX_TL) tl = PRE_MAX_TL;
     a.tl[i] = tl;
     a.ctas_t[i] = (p.T + tl * S - 1) / (tl * S);
+    a.inv_ctas_t[i] = 1.0f / (float)a.ctas_t[i];
+    a.inv_c4[i] = 1.0f / (float)(p.C / 4);
     a.cta_begin[i] = ctas;
     ctas += a.ctas_t[i] * p.B;
   }

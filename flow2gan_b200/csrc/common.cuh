@@ -40,10 +40,9 @@ F2G_DEVINL float tf32_rna_fast(float x) {
 // fp32 -> fp16 pair, round-to-nearest-even, clamped to the finite fp16 range (operands of the
 // kind::f16 GEMMs: an overflow saturates instead of poisoning the contraction with Inf)
 F2G_DEVINL uint32_t pack_half2_sat(float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;     // {b, a} -> upper / lower half; .satfinite clamps to +-65504 in the conversion
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 F2G_DEVINL uint2 pack_half4(float4 v) {
   return make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
