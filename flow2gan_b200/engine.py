@@ -404,8 +404,9 @@ class InferencePlan:
         device tensor."""
         self.mel.copy_(mel, non_blocking=True)
         if noise is None:
-            torch.randn(self.x_audio.shape, out=self.x_audio)
-            self.x_audio.mul_(noise_scale)
+            # one kernel; torch.randn IS empty().normal_(0, 1) and normal_(0, s) applies `z * s + 0`
+            # to the same Philox stream, so this equals the reference's `torch.randn(...) * s`
+            self.x_audio.normal_(0.0, noise_scale)
         else:
             self.x_audio.copy_(noise, non_blocking=True)
         if self.masked:
