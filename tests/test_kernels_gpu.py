@@ -261,6 +261,42 @@ def test_gemm_chained_mlp_matches_two_launches(L, shapes):
     assert rel_rms(xa.cpu(), exp) < 3e-4
 
 
+@pytest.mark.parametrize("rows,cols,act", [(5000, 32, "leaky"), (777, 48, "prelu"), (1505, 1152, "prelu"),
+                                           (300, 30, "leaky"), (1000, 64, "none"), (515, 1536, "silu")])
+def test_act_bwd_fused_reductions(L, rows, cols, act):
+    """dz = dh * act'(z) with the fused bias / slope gradient column sums (autograd of PReLU,
+    LeakyReLU, SiLU after a conv: modules.py:486-489,570-572, discriminators.py:99-104), in place,
+    padded leading dimensions; vector (cols % 4 == 0) and scalar kernels."""
+    g = torch.Generator().manual_seed(rows + cols)
+    ld = (cols + 3) // 4 * 4 + 4
+    dh = torch.randn(rows, ld, generator=g)
+    z = torch.randn(rows, ld, generator=g)
+    slope = torch.rand(cols, generator=g) * 0.5
+    code = {"leaky": L.ACT_LEAKY, "prelu": L.ACT_PRELU, "none": L.ACT_NONE, "silu": L.ACT_SILU}[act]
+    d, zz = dh[:, :cols].double(), z[:, :cols].double()
+    if act == "leaky":
+        exp = torch.where(zz > 0, d, d * 0.1)
+    elif act == "prelu":
+        exp = torch.where(zz > 0, d, d * slope.double())
+    elif act == "silu":
+        sg = torch.sigmoid(zz)
+        exp = d * sg * (1 + zz * (1 - sg))
+    else:
+        exp = d
+    dzg = dh.clone().cuda()
+    gb = torch.zeros(cols + 4, device="cuda")
+    gs = torch.zeros(cols + 4, device="cuda")
+    L.act_bwd(dzg, ld, z.cuda() if act != "none" else None, ld, slope.cuda() if act == "prelu" else None, 0.1, code,
+              rows, cols, dzg, ld, gb, gs if act in ("prelu", "leaky") else None)
+    torch.cuda.synchronize()
+    got = dzg.cpu()
+    assert torch.equal(got[:, cols:], dh[:, cols:]), "wrote outside its columns"
+    assert rel_rms(got[:, :cols], exp) < 1e-6
+    assert rel_rms(gb[:cols].cpu(), exp.sum(0)) < 1e-5 and float(gb[cols:].abs().max()) == 0.0
+    if act in ("prelu", "leaky"):
+        assert rel_rms(gs[:cols].cpu(), (d * zz.clamp(max=0)).sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("n_fft,hop", [(128, 64), (256, 128), (512, 256), (1024, 512), (32, 8), (2048, 512)])
 def test_stft_packed(L, n_fft, hop):
     B, T = 3, 6144
