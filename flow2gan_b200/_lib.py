@@ -111,6 +111,7 @@ _SIGS = {
     "f2g_block_bwd_c": ([C.POINTER(F2GBlockBwdC), _fp], _i),
     "f2g_block_bwd_b": ([_fp, _fp, _fp, _fp, _i, _fp, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_act_bwd": ([_fp, _i, _fp, _i, _fp, _f, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp], _i),
+    "f2g_act_bwd_win": ([_fp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _fp, _i, _f, _i, _i, _i, _fp, _i, _i, _fp, _i, _fp], _i),
     "f2g_cond_reduce": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_istft_bwd_prep": ([_fp, _i, _i, _i, _i, _i, _f, _fp, _fp], _i),
     "f2g_istft_bwd_spec": ([_fp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp], _i),
@@ -121,6 +122,7 @@ _SIGS = {
     "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_conv_w_pack": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
+    "f2g_conv_w_pack_dgrad": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp], _i),
     "f2g_pad2d": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _ll, _i, _fp, _fp], _i),
     "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
 }
@@ -377,6 +379,14 @@ def act_bwd(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, dz, ld_dz, g_bias
                              ptr(dz), ld_dz, ptr(g_bias), ptr(g_slope), round_tf32, stream()))
 
 
+def act_bwd_win(dy, Nb, Hl, R, Ho, Wo, z, ld_z, leaky, act, cols, cols_total, dz_ptr, ld_dz, guard_rows, g_bias,
+                round_tf32=1):
+    """dy: (Nb, Ho, Wo, cols) view with unit channel stride; dz_ptr: address of GEMM row 0."""
+    _check(lib().f2g_act_bwd_win(ptr(dy), dy.stride(0), dy.stride(1), dy.stride(2), Nb, Hl, R, Ho, Wo, ptr(z), ld_z,
+                                 float(leaky), act, cols, cols_total, dz_ptr, ld_dz, guard_rows, ptr(g_bias),
+                                 round_tf32, stream()))
+
+
 def cond_reduce(du, B, T, Cc, cond_T, factor, zero_row, out, ld_out):
     _check(lib().f2g_cond_reduce(ptr(du), B, T, Cc, cond_T, factor, zero_row, ptr(out), ld_out, stream()))
 
@@ -431,3 +441,7 @@ def pad2d(x_ptr, Nb, H, W, Cc, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, slack,
 
 def conv_w_pack(src, Co, Ci, taps, Co_pad, ld, dst, direction):
     _check(lib().f2g_conv_w_pack(ptr(src), Co, Ci, taps, Co_pad, ld, ptr(dst), direction, stream()))
+
+
+def conv_w_pack_dgrad(weight, Co, Ci, kh, kw, sw, Cop, out):
+    _check(lib().f2g_conv_w_pack_dgrad(ptr(weight), Co, Ci, kh, kw, sw, Cop, ptr(out), stream()))

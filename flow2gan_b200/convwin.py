@@ -93,8 +93,11 @@ def pack_dgrad_weight(weight: Tensor, g: WinGeom, phase: int) -> Tensor:
     W[co, ci, s, phase + sw*(nt_phase-1-jj)] (the window runs over ascending dz rows)."""
     ntp = g.taps(phase)
     sel = weight[:, :, :, phase::g.sw].flip(-1)                   # (Co, Ci, kh, ntp), jj ascending
-    wd = weight.new_zeros(g.C, g.kh, ntp, g.Cop)
-    wd[..., :g.Co] = sel.permute(1, 2, 3, 0)
+    if g.Cop == g.Co:
+        wd = sel.permute(1, 2, 3, 0).contiguous()
+    else:
+        wd = weight.new_zeros(g.C, g.kh, ntp, g.Cop)
+        wd[..., :g.Co] = sel.permute(1, 2, 3, 0)
     return wd.view(g.C, g.kh * ntp * g.Cop)
 
 
@@ -136,15 +139,30 @@ class _ConvWinFn(torch.autograd.Function):
         xp, y, weight = ctx.saved
         dev = dy.device
         Cop, C, sw = g.Cop, g.C, g.sw
-        dz_full = torch.zeros((g.guard + g.M) * Cop, device=dev, dtype=torch.float32)
-        dz = dz_full[g.guard * Cop:].view(g.M, Cop)
-        dz.view(g.Nb, g.Hl, g.R, Cop)[:, :g.Ho, :g.Wo, :g.Co].copy_(dy)
-        g_bias = torch.zeros(Cop, device=dev, dtype=torch.float32)
-        L.act_bwd(dz, Cop, y if leaky is not None else None, Cop, None, leaky or 0.0,
-                  L.ACT_LEAKY if leaky is not None else L.ACT_NONE, g.M, g.Co, dz, Cop, g_bias, None, round_tf32=1)
+        need_w = ctx.needs_input_grad[1]
+        # one zero-filled buffer for everything that is accumulated into (bias gradient, split-K
+        # weight gradient): one fill launch instead of two
+        zb = torch.zeros(Cop + (g.K * Cop if need_w else 0), device=dev, dtype=torch.float32)
+        g_bias = zb[:Cop]
+        act = L.ACT_LEAKY if leaky is not None else L.ACT_NONE
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        fused = g.Co % 4 == 0 and all(st % 4 == 0 for st in dy.stride()[:3]) and dy.data_ptr() % 16 == 0
+        if fused:
+            # gather dy, apply act', zero the padding rows / guard, bias sums: ONE pass (f2g_act_bwd_win)
+            dz_full = torch.empty((g.guard + g.M) * Cop, device=dev, dtype=torch.float32)
+            dz = dz_full[g.guard * Cop:].view(g.M, Cop)
+            L.act_bwd_win(dy, g.Nb, g.Hl, g.R, g.Ho, g.Wo, y if leaky is not None else None, Cop, leaky or 0.0,
+                          act, g.Co, Cop, dz.data_ptr(), Cop, g.guard, g_bias)
+        else:
+            dz_full = torch.zeros((g.guard + g.M) * Cop, device=dev, dtype=torch.float32)
+            dz = dz_full[g.guard * Cop:].view(g.M, Cop)
+            dz.view(g.Nb, g.Hl, g.R, Cop)[:, :g.Ho, :g.Wo, :g.Co].copy_(dy)
+            L.act_bwd(dz, Cop, y if leaky is not None else None, Cop, None, leaky or 0.0, act, g.M, g.Co, dz, Cop,
+                      g_bias, None, round_tf32=1)
         gW = gb = gx = None
         if ctx.needs_input_grad[1]:
-            dwt = torch.zeros(g.K, Cop, device=dev, dtype=torch.float32)
+            dwt = zb[Cop:].view(g.K, Cop)
             L.gemm_group([L.gemm_desc(xp.data_ptr(), dz.data_ptr(), dwt.data_ptr(), g.K, g.Co, g.M, sw * C, Cop, Cop,
                                       a_mn=1, b_mn=1, split_k=L.pick_split_k(g.K, g.Co, g.M),
                                       a_seg_len=g.seg, a_seg_shift=g.R, a_rows=g.M)])
@@ -155,15 +173,19 @@ class _ConvWinFn(torch.autograd.Function):
             dxp = torch.empty(g.M, sw * C, device=dev, dtype=torch.float32)
             descs: List[L.F2GGemm] = []
             keep = []
+            # all phases' transposed-conv weights in one launch, phase blocks back to back
+            wd_all = torch.empty(C * g.kh * g.kw * Cop, device=dev, dtype=torch.float32)
+            L.conv_w_pack_dgrad(weight.contiguous(), g.Co, C, g.kh, g.kw, sw, Cop, wd_all)
+            keep.append(wd_all)
+            off = 0
             for phase in range(sw):
                 ntp = g.taps(phase)
-                wd = pack_dgrad_weight(weight, g, phase)
-                _round_inplace(wd)
-                keep.append(wd)
+                kd = g.kh * ntp * Cop
                 a_ptr = dz_full.data_ptr() + 4 * (g.guard - (ntp - 1)) * Cop
-                descs.append(L.gemm_desc(a_ptr, wd.data_ptr(), dxp.data_ptr() + 4 * phase * C, g.M, C,
-                                         g.kh * ntp * Cop, Cop, g.kh * ntp * Cop, sw * C,
+                descs.append(L.gemm_desc(a_ptr, wd_all.data_ptr() + 4 * off, dxp.data_ptr() + 4 * phase * C, g.M, C,
+                                         kd, Cop, kd, sw * C,
                                          a_seg_len=ntp * Cop, a_seg_shift=-g.R, a_rows=g.M))
+                off += C * kd
             L.gemm_group(descs)
             gx = dxp.view(g.Nb, g.Hl, g.Wp, C)[:, g.ph:g.ph + g.H, g.pw:g.pw + g.W, :]
         return gx, gW, gb, None, None, None, None

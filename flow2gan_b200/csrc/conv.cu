@@ -190,6 +190,35 @@ static int grid_for(long long total) {
   return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
+// Weights of the phase-decomposed transposed convolution (input gradient of a stride-(1, sw)
+// windowed conv, convwin.py): for phase p in [0, sw) with ntp = ceil((kw - p) / sw) taps,
+//   out_p[ci][s][jj][co] = W[co][ci][s][p + sw * (ntp - 1 - jj)]   (co < Co, else 0), TF32-rounded,
+// all phases in one launch, phase blocks back to back (block p starts at Ci*kh*Cop*sum_{q<p} ntq).
+__global__ void conv_w_pack_dgrad_kernel(const float* __restrict__ w, int Co, int Ci, int kh, int kw, int sw,
+                                         int Cop, float* __restrict__ out) {
+  const long long total = (long long)Ci * kh * kw * Cop;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long rem = i;
+    int p = 0, ntp = 0;
+    for (; p < sw; ++p) {
+      ntp = (kw - p + sw - 1) / sw;
+      const long long blk = (long long)Ci * kh * ntp * Cop;
+      if (rem < blk) break;
+      rem -= blk;
+    }
+    const int co = (int)(rem % Cop);
+    rem /= Cop;
+    const int jj = (int)(rem % ntp);
+    rem /= ntp;
+    const int s = (int)(rem % kh);
+    const int ci = (int)(rem / kh);
+    float v = 0.f;
+    if (co < Co) v = w[(((long long)co * Ci + ci) * kh + s) * kw + p + sw * (ntp - 1 - jj)];
+    out[i] = tf32_rna(v);
+  }
+}
+
 extern "C" int f2g_im2col2d(const float* x, const F2GConv2d* p, float* col, int round_tf32, void* stream) {
   ConvGeom g;
   if (int rc = fill_geom(g, p)) return rc;
@@ -240,4 +269,16 @@ extern "C" int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int C
   conv_w_pack_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, Co, Ci, taps,
                                                                                     Co_pad, ld, dst, dir);
   return check_launch("f2g_conv_w_pack");
+}
+
+extern "C" int f2g_conv_w_pack_dgrad(const float* w, int Co, int Ci, int kh, int kw, int sw, int Cop, float* out,
+                                     void* stream) {
+  if (sw < 1 || kw < sw || Cop < Co || kh < 1) {
+    set_error("f2g_conv_w_pack_dgrad: bad geometry (kw=%d sw=%d Co=%d Cop=%d)", kw, sw, Co, Cop);
+    return F2G_EINVAL;
+  }
+  const long long total = (long long)Ci * kh * kw * Cop;
+  conv_w_pack_dgrad_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, Co, Ci, kh, kw, sw,
+                                                                                          Cop, out);
+  return check_launch("f2g_conv_w_pack_dgrad");
 }

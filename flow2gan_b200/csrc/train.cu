@@ -299,6 +299,64 @@ __global__ void __launch_bounds__(128) act_bwd_vec_kernel(
   }
 }
 
+// Activation backward for the windowed convs (convwin.py): the GEMM-row space is (n, line, r) with
+// Hl lines of R columns per image, of which only line < Ho, r < Wo are real outputs.  Gathers the
+// incoming gradient from its (N, Ho, Wo, C) view, applies act'(z), and writes EVERY row of dz
+// (zeros on the padding rows / columns and on `guard` rows in front) plus the bias-gradient column
+// sums -- one pass instead of zero-fill + strided copy + in-place act_bwd.
+template <int TPR>
+__global__ void __launch_bounds__(128) act_bwd_win_kernel(
+    const float* __restrict__ dy, long long s_n, long long s_h, long long s_w, int Hl, int R, int Ho, int Wo,
+    const float* __restrict__ z, int ld_z, float leaky, int act, int rows, int cols, int cols_total,
+    int rows_per_cta, float* __restrict__ dz, int ld_dz, int guard, float* __restrict__ g_bias, int round_tf32) {
+  constexpr int RPP = 128 / TPR;
+  __shared__ float4 red[128];
+  const int cq = threadIdx.x % TPR, rs = threadIdx.x / TPR;
+  const int c = (blockIdx.x * TPR + cq) * 4;
+  const bool active = c < cols_total, real_col = c < cols;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sb = zero4;
+  if (active) {
+    if (blockIdx.y == 0)
+      for (int r = rs; r < guard; r += RPP) st4(dz - (size_t)(r + 1) * ld_dz + c, zero4);
+    const int per_img = Hl * R;
+#pragma unroll 4
+    for (int r = r0 + rs; r < r1; r += RPP) {
+      const int n = r / per_img;
+      const int rem = r - n * per_img;
+      const int line = rem / R;
+      const int rr = rem - line * R;
+      float4 o = zero4;
+      if (real_col && line < Ho && rr < Wo) {
+        const float4 d = ld4(dy + n * s_n + line * s_h + rr * s_w + c);
+        if (act == F2G_ACT_NONE) {
+          o = d;
+        } else {
+          const float4 zv = ld4(z + (size_t)r * ld_z + c);
+          o = make_float4(zv.x > 0.f ? d.x : d.x * leaky, zv.y > 0.f ? d.y : d.y * leaky,
+                          zv.z > 0.f ? d.z : d.z * leaky, zv.w > 0.f ? d.w : d.w * leaky);
+        }
+        sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
+        if (round_tf32) o = make_float4(tf32_rna(o.x), tf32_rna(o.y), tf32_rna(o.z), tf32_rna(o.w));
+      }
+      st4(dz + (size_t)r * ld_dz + c, o);
+    }
+  }
+  red[threadIdx.x] = sb;
+  __syncthreads();
+  if (rs == 0 && real_col && g_bias) {
+    float4 tb = zero4;
+#pragma unroll
+    for (int j = 0; j < RPP; ++j) {
+      const float4 a = red[j * TPR + cq];
+      tb.x += a.x; tb.y += a.y; tb.z += a.z; tb.w += a.w;
+    }
+    atomicAdd(g_bias + c, tb.x); atomicAdd(g_bias + c + 1, tb.y);
+    atomicAdd(g_bias + c + 2, tb.z); atomicAdd(g_bias + c + 3, tb.w);
+  }
+}
+
 // dcp[b*cond_T + tm, c] = sum_{f<factor} du[b, tm*factor+f, c]; zero row = all remaining frames
 __global__ void cond_reduce_kernel(const float* __restrict__ du, int B, int T, int C, int cond_T, int factor,
                                    int zero_row, float* __restrict__ out, int ld_out) {
@@ -466,6 +524,41 @@ extern "C" int f2g_act_bwd(const float* dh, int ld_dh, const float* z, int ld_z,
   act_bwd_kernel<<<grid, 128, 0, st>>>(
       dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
   return check_launch("f2g_act_bwd");
+}
+
+extern "C" int f2g_act_bwd_win(const float* dy, long long s_n, long long s_h, long long s_w, int Nb, int Hl,
+                               int R, int Ho, int Wo, const float* z, int ld_z, float leaky, int act, int cols,
+                               int cols_total, float* dz, int ld_dz, int guard_rows, float* g_bias,
+                               int round_tf32, void* stream) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((cols & 3) || (cols_total & 3) || cols > cols_total || cols_total > ld_dz || (ld_dz & 3) || (z && (ld_z & 3)) ||
+      (s_n & 3) || (s_h & 3) || (s_w & 3) || !al16(dy) || !al16(z) || !al16(dz) || !al16(g_bias) ||
+      (act != F2G_ACT_NONE && act != F2G_ACT_LEAKY) || (act == F2G_ACT_LEAKY && !z) || Ho > Hl || Wo > R) {
+    set_error("f2g_act_bwd_win: needs 4-float aligned columns / strides / pointers and act NONE or LEAKY "
+              "(cols=%d/%d ld_dz=%d)", cols, cols_total, ld_dz);
+    return F2G_EINVAL;
+  }
+  const long long rows_ll = (long long)Nb * Hl * R;
+  if (rows_ll <= 0 || rows_ll > 0x7fffffffLL) {
+    set_error("f2g_act_bwd_win: %lld rows out of range", rows_ll);
+    return F2G_EINVAL;
+  }
+  const int rows = (int)rows_ll;
+  const int quads = cols_total >> 2;
+  const int tpr = quads >= 32 ? 32 : (quads > 8 ? 16 : 8);
+  const int cb = (quads + tpr - 1) / tpr;
+  int rpc = pick_rows_per_cta(rows, cb);
+  const int rpp = 128 / tpr;
+  rpc = ((rpc + 4 * rpp - 1) / (4 * rpp)) * (4 * rpp);
+  dim3 grid(cb, (rows + rpc - 1) / rpc);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define F2G_ABW(T_) act_bwd_win_kernel<T_><<<grid, 128, 0, st>>>(dy, s_n, s_h, s_w, Hl, R, Ho, Wo, z, ld_z, leaky, act, \
+    rows, cols, cols_total, rpc, dz, ld_dz, guard_rows, g_bias, round_tf32)
+  if (tpr == 32) F2G_ABW(32);
+  else if (tpr == 16) F2G_ABW(16);
+  else F2G_ABW(8);
+#undef F2G_ABW
+  return check_launch("f2g_act_bwd_win");
 }
 
 extern "C" int f2g_cond_reduce(const float* du, int B, int T, int C, int cond_T, int factor, int zero_row,

@@ -258,6 +258,16 @@ int f2g_act_bwd(const float* dh, int ld_dh, const float* z, int ld_z, const floa
                 int act, int rows, int cols, float* dz, int ld_dz, float* g_bias, float* g_slope,
                 int round_tf32, void* stream);
 
+/* The same for the windowed convs (F2GGemm::a_seg_len): GEMM rows are (n, line, r) with Hl lines of
+ * R columns per image, real outputs at line < Ho, r < Wo.  dy is the (Nb, Ho, Wo, cols) gradient
+ * view with element strides s_n / s_h / s_w (channel stride 1); z the saved GEMM output rows.
+ * Writes ALL Nb*Hl*R rows of dz (zeros on padding rows, on columns [cols, cols_total) and on the
+ * guard_rows rows in front of dz) and adds the column sums of the real rows to g_bias.
+ * act = F2G_ACT_NONE or F2G_ACT_LEAKY; columns, strides, leading dimensions multiples of 4. */
+int f2g_act_bwd_win(const float* dy, long long s_n, long long s_h, long long s_w, int Nb, int Hl, int R,
+                    int Ho, int Wo, const float* z, int ld_z, float leaky, int act, int cols, int cols_total,
+                    float* dz, int ld_dz, int guard_rows, float* g_bias, int round_tf32, void* stream);
+
 /* Adjoint of upsample_cond (modules.py:668-680): frame-rate gradient rows -> mel-rate rows
  * (+ the shared zero row). */
 int f2g_cond_reduce(const float* du, int B, int T, int C, int cond_T, int factor, int zero_row,
@@ -311,6 +321,12 @@ int f2g_pad2d(const float* x, int Nb, int H, int W, int C, long long pitch_n, lo
  * dir 1: packed gradient -> parameter layout. */
 int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int Co_pad, int ld, float* dst, int dir,
                     void* stream);
+/* Weights of the phase-decomposed transposed convolution = input gradient of a stride-(1, sw)
+ * windowed conv: for every phase p < sw (ntp = ceil((kw-p)/sw) taps) the matrix
+ * out_p[ci][(s, jj, co)] = W[co][ci][s][p + sw*(ntp-1-jj)] (zero for co >= Co), TF32-rounded; phase
+ * blocks back to back, block p at float offset Ci*kh*Cop*sum_{q<p} ntq.  w: (Co, Ci, kh, kw). */
+int f2g_conv_w_pack_dgrad(const float* w, int Co, int Ci, int kh, int kw, int sw, int Cop, float* out,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused multi-tensor ScaledAdam step (flow2gan/optim.py:125-255,451-619) for ONE param group.

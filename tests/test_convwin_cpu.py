@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture()
 def emul():
     from flow2gan_b200 import _lib as L
-    saved = {k: getattr(L, k) for k in ("pad2d", "conv_w_pack", "pack2d", "act_bwd", "gemm_group", "ptr")}
+    saved = {k: getattr(L, k) for k in ("pad2d", "conv_w_pack", "pack2d", "act_bwd", "act_bwd_win", "conv_w_pack_dgrad", "gemm_group", "ptr")}
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     try:
         mod = importlib.import_module("convwin_cpu_emul")

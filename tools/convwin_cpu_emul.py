@@ -46,6 +46,30 @@ def act_bwd(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, dz, ld_dz, g_bias
     g_bias.numpy()[:cols] += d[:, :cols].sum(0)
 
 
+def act_bwd_win(dy, Nb, Hl, R, Ho, Wo, z, ld_z, leaky, act, cols, cols_total, dz_ptr, ld_dz, guard_rows, g_bias,
+                round_tf32=1):
+    M = Nb * Hl * R
+    full = arr(dz_ptr - 4 * guard_rows * ld_dz, (guard_rows + M) * ld_dz)
+    full[:] = 0
+    dzv = full[guard_rows * ld_dz:].reshape(Nb, Hl, R, ld_dz)
+    o = dy.numpy().copy()
+    if act == L.ACT_LEAKY:
+        zz = z.numpy().reshape(Nb, Hl, R, ld_z)[:, :Ho, :Wo, :cols]
+        o *= np.where(zz > 0, 1.0, leaky).astype(np.float32)
+    dzv[:, :Ho, :Wo, :cols] = o
+    g_bias.numpy()[:cols] += o.sum((0, 1, 2))
+
+
+def conv_w_pack_dgrad(weight, Co, Ci, kh, kw, sw, Cop, out):
+    g = convwin.WinGeom(0, 0, 0, Ci, Co, kh, kw, sw, 0, 0, 0, 0, 0, 0, 0, Cop, 0, 0, 0, 0, 0)
+    o, off = out.numpy(), 0
+    for phase in range(sw):
+        wd = convwin.pack_dgrad_weight(weight, g, phase).contiguous().numpy().reshape(-1)
+        o[off:off + wd.size] = wd
+        off += wd.size
+    assert off == o.size
+
+
 def gemm_group(descs):
     for d in descs:
         M, N, K = d.M, d.N, d.K
@@ -84,6 +108,7 @@ def gemm_group(descs):
 
 
 L.pad2d, L.conv_w_pack, L.pack2d, L.act_bwd, L.gemm_group = pad2d, conv_w_pack, pack2d, act_bwd, gemm_group
+L.act_bwd_win, L.conv_w_pack_dgrad = act_bwd_win, conv_w_pack_dgrad
 L.ptr = lambda t: None if t is None else t.data_ptr()
 
 
