@@ -173,6 +173,17 @@ def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0, wait=None):
                        wait_counter=wait)
 
 
+def _half(holder, name: str) -> Tensor:
+    """fp16 copy of a packed (TF32-rounded, hence exactly representable) fp32 matrix, cached on
+    its holder until the next PackedGenerator.refresh()."""
+    key = "_h_" + name
+    t = holder.__dict__.get(key)
+    if t is None:
+        t = getattr(holder, name).to(torch.float16)
+        holder.__dict__[key] = t
+    return t
+
+
 class InferencePlan:
     """Workspaces + launch sequence for one (B, mel frames, T, masked?) shape."""
 
@@ -213,13 +224,16 @@ class InferencePlan:
             w.te1 = z(1, bw.dec.time_mlp[0].weight.shape[0])
             w.te2 = z(1, bw.te)
             w.ts = z(1, bw.nl * bw.C)
-            w.cm_h = z(self.Rc, bw.ch)
-            w.c1 = z(self.Rc, bw.cc)
+            w.cm_h = zo(self.Rc, bw.ch)       # cond_mlp hidden / output: GEMM operands only
+            w.c1 = zo(self.Rc, bw.cc)
             w.cp = z(self.Rc, bw.nl * bw.C)
             w.mask = z(w.R) if masked else None
             self.br.append(w)
         # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
-        self.chained = CHAIN_MLP and BLOCK_OPERANDS == "f16"
+        self.f16 = BLOCK_OPERANDS == "f16"
+        self.chained = CHAIN_MLP and self.f16
+        self.c0h = zo(self.Rc, self.Cc)
+        self.cm_chain = torch.zeros(len(packed.branches) * ((self.Rc + 255) // 256), device=dev, dtype=torch.int32)
         self.ce_chain = torch.zeros((self.Rc + 255) // 256, device=dev, dtype=torch.int32)
         offs, tot = [], 0
         for w in self.br:
@@ -261,6 +275,36 @@ class InferencePlan:
     def cond_paths(self) -> None:
         """cond_mlp + all cond_proj of every branch at mel-frame rate (+ the zero row)."""
         pk, Rc = self.pk, self.Rc
+        if self.f16:
+            # fp16 operands (c0 was RN-rounded to 11 significant bits by the last CondEncoder block, so
+            # the conversion is exact); cond_mlp[0] -> PReLU -> cond_mlp[2] is one chained launch
+            self.c0h.copy_(self.c0)
+            if self.chained:
+                self.cm_chain.zero_()
+            g0, g2, g3 = [], [], []
+            ntile = (Rc + 255) // 256
+            for i, (bw, w) in enumerate(zip(pk.branches, self.br)):
+                cm = bw.dec.cond_mlp
+                cnt = self.cm_chain.data_ptr() + 4 * i * ntile if self.chained else None
+                W0, W2, Wc = _half(bw, "cmW0"), _half(bw, "cmW2"), _half(bw, "Wcp")
+                g0.append(L.gemm_desc(self.c0h.data_ptr(), W0.data_ptr(), w.cm_h.data_ptr(), Rc, bw.ch, bw.cc,
+                                      bw.cc, bw.cc, bw.ch, bias=cm[0].bias.data_ptr(),
+                                      slope=cm[1].weight.data_ptr(), act=L.ACT_PRELU, ab_f16=1, c_f16=1,
+                                      done_counter=cnt))
+                # bias-only epilogue with an fp16 destination = "leaky ReLU with slope 1"
+                g2.append(L.gemm_desc(w.cm_h.data_ptr(), W2.data_ptr(), w.c1.data_ptr(), Rc, bw.cc, bw.ch,
+                                      bw.ch, bw.ch, bw.cc, bias=cm[2].bias.data_ptr(), act=L.ACT_LEAKY,
+                                      leaky=1.0, ab_f16=1, c_f16=1, wait_counter=cnt))
+                N = bw.nl * bw.C
+                g3.append(L.gemm_desc(w.c1.data_ptr(), Wc.data_ptr(), w.cp.data_ptr(), Rc, N, bw.cc,
+                                      bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1))
+            if self.chained:
+                L.gemm_group(g0 + g2)
+            else:
+                L.gemm_group(g0)
+                L.gemm_group(g2)
+            L.gemm_group(g3)
+            return
         ds = []
         for bw, w in zip(pk.branches, self.br):
             cm = bw.dec.cond_mlp
@@ -371,6 +415,9 @@ class InferencePlan:
             if BLOCK_OPERANDS == "f16":        # lazily built fp16 weights: allocate on the main stream
                 for bw in self.pk.ce_blocks:
                     bw.half()
+                for bw in self.pk.branches:
+                    for nm in ("cmW0", "cmW2", "Wcp"):
+                        _half(bw, nm)
             main = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.x_audio.device)
