@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libflow2gan_b200.so")
 ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_SILU = 0, 1, 2, 3
 SPEC_PACKED, SPEC_MAG, SPEC_POWER, SPEC_COMPLEX = 0, 1, 2, 3
 GEMM_MAX_PROBLEMS = 8
+PCM_F32, PCM_S16, PCM_S24, PCM_S32 = 1, 16, 24, 32
 
 _fp = C.c_void_p
 _i = C.c_int
@@ -80,6 +81,10 @@ class F2GAdamTensor(C.Structure):
                 ("is_scalar", _i), ("reserved", _i)]
 
 
+class F2GAvgTensor(C.Structure):
+    _fields_ = [("avg", _fp), ("cur", _fp), ("numel", _ll), ("cur_is_f64", _i), ("reserved", _i)]
+
+
 class F2GAdamHyper(C.Structure):
     _fields_ = [("lr", _f), ("scalar_lr_scale", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
                 ("param_min_rms", _f), ("param_max_rms", _f), ("scalar_max", _f),
@@ -125,6 +130,10 @@ _SIGS = {
     "f2g_conv_w_pack_dgrad": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp], _i),
     "f2g_pad2d": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _ll, _i, _fp, _fp], _i),
     "f2g_scaled_adam_step": ([_fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _i, _i, C.POINTER(F2GAdamHyper), _fp], _i),
+    "f2g_pcm_decode": ([_fp, _i, _i, _ll, _ll, _fp, _fp, _fp], _i),
+    "f2g_gain_resample": ([_fp, _ll, _fp, _f, _i, _i, _i, _fp, _fp, _ll, _fp], _i),
+    "f2g_pcm16_encode": ([_fp, _ll, _i, _fp, _fp], _i),
+    "f2g_average_update": ([_fp, _fp, _i, C.c_double, C.c_double, C.c_double, _fp], _i),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -150,7 +159,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 4:
+        if lib.f2g_abi_version() != 5:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -445,3 +454,36 @@ def conv_w_pack(src, Co, Ci, taps, Co_pad, ld, dst, direction):
 
 def conv_w_pack_dgrad(weight, Co, Ci, kh, kw, sw, Cop, out):
     _check(lib().f2g_conv_w_pack_dgrad(ptr(weight), Co, Ci, kh, kw, sw, Cop, ptr(out), stream()))
+
+
+# ---------------------------------------------------------------------------------------
+# data path (csrc/datapath.cu): raw-pointer wrappers; dtype checks live in datapath.py / averaging.py
+# ---------------------------------------------------------------------------------------
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"flow2gan_b200: {what} must be a CUDA tensor (got {t.device}); there is no CPU fallback")
+
+
+def pcm_decode(pcm_u8, sample_format, channels, first_frame, n_frames, mono, stats):
+    require_cuda(pcm_u8, "PCM payload")
+    assert pcm_u8.dtype == torch.uint8
+    _check(lib().f2g_pcm_decode(pcm_u8.data_ptr(), sample_format, channels, first_frame, n_frames, ptr(mono),
+                                ptr(stats), stream()))
+
+
+def gain_resample(x, n_in, stats, norm_db, orig_r, new_r, width, taps, out, n_out):
+    _check(lib().f2g_gain_resample(ptr(x), n_in, ptr(stats), float(norm_db), orig_r, new_r, width, ptr(taps),
+                                   ptr(out), n_out, stream()))
+
+
+def pcm16_encode(x, n, clamp, out_i16):
+    require_cuda(out_i16, "PCM16 output")
+    assert out_i16.dtype == torch.int16
+    _check(lib().f2g_pcm16_encode(ptr(x), n, int(clamp), out_i16.data_ptr(), stream()))
+
+
+def average_update(tab_u8, chunks_i32, n_chunks, w_avg, w_cur, scale):
+    require_cuda(tab_u8, "tensor table")
+    assert chunks_i32.is_cuda and chunks_i32.dtype == torch.int32
+    _check(lib().f2g_average_update(tab_u8.data_ptr(), chunks_i32.data_ptr(), n_chunks, float(w_avg),
+                                    float(w_cur), float(scale), stream()))

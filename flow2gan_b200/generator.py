@@ -93,6 +93,17 @@ class BaseAudioGenerator(nn.Module):
         self._packed, self._plans = None, {}
         return super()._apply(fn, *a, **k)
 
+    def __deepcopy__(self, memo):
+        # `copy.deepcopy(model).to(torch.float64)` is how the training scripts create model_avg
+        # (finetune.py:902, pretrain.py:777).  Packed weights and captured CUDA graphs are derived
+        # from the parameters and are not copyable: the copy starts without them.
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_packed" else {} if k == "_plans" else copy.deepcopy(v, memo)
+        return new
+
     def _require_cuda(self) -> None:
         dev = next(self.parameters()).device
         if dev.type != "cuda":

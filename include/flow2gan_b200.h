@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 4
+#define F2G_ABI_VERSION 5
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -356,6 +356,50 @@ int f2g_scaled_adam_step(const F2GAdamTensor* tab_dev, int n_tensors, const int*
                          int n_chunks, float* acc_dev, float* tensor_state_dev,
                          float* group_state_dev, float* model_norms_dev, int step, int phase,
                          const F2GAdamHyper* hyper, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Data path either side of the generator: wav payload -> training /
+ * inference waveform, waveform -> wav payload, and the fp64 running model average.
+ * ------------------------------------------------------------------------------------- */
+enum { F2G_PCM_F32 = 1, F2G_PCM_S16 = 16, F2G_PCM_S24 = 24, F2G_PCM_S32 = 32 };
+
+/* mono[i] = mean over channels of frame first_frame + i of an interleaved little-endian PCM
+ * payload (device memory), i < n_frames; integer formats are scaled by 2^-(bits-1) like
+ * libsndfile / torchaudio.load.  stats (optional, 2 floats, zeroed by the caller): [0] += sum
+ * mono^2 (the loader's silence test), [1] = max |mono| (sox `norm`).
+ * replaces: lhotse Recording.load_audio(offset, duration) + is_silence + y.mean(dim=0)
+ * (flow2gan/dataset.py:122-160), torchaudio.load + torch.mean (flow2gan/bin/infer_dir.py:217-220,
+ * test_from_wav.py:62-66). */
+int f2g_pcm_decode(const void* pcm, int sample_format, int channels, long long first_frame,
+                   long long n_frames, float* mono, float* stats, void* stream);
+
+/* out = resample(g * x): g = 10^(norm_db/20) / stats[1] when `stats` is given (sox effect
+ * ["norm", dB], dataset.py:164-168), else 1; polyphase sinc interpolation with the
+ * (new_r, 2*width + orig_r) tap table of torchaudio.functional.resample (orig_r/new_r = the
+ * rates divided by their gcd; dataset.py:170-173); n_out <= (n_in / orig_r + 1) * new_r, the
+ * reference keeps ceil(new_r * n_in / orig_r).  orig_r = new_r = 1, width = 0, taps = {1} is the
+ * gain-only pass. */
+int f2g_gain_resample(const float* x, long long n_in, const float* stats, float norm_db, int orig_r,
+                      int new_r, int width, const float* taps, float* out, long long n_out,
+                      void* stream);
+
+/* out[i] = (int16) lrintf(x[i] * 32767) -- soundfile.write's default PCM_16 conversion
+ * (flow2gan/bin/infer.py:208-212, bin/infer_dir.py:237); clamp != 0 bounds x to [-1, 1] first. */
+int f2g_pcm16_encode(const float* x, long long n, int clamp, short* out, void* stream);
+
+/* avg = (avg * w_avg + cur * w_cur) * scale on fp64 accumulators, every tensor of a model in one
+ * launch (chunks: int pairs {tensor, 4096-element chunk}); replaces average_state_dict as used by
+ * update_averaged_model / update_ema_model / average_checkpoints_with_averaged_model
+ * (flow2gan/checkpoint.py:378-409,411-441,443-531). */
+typedef struct F2GAvgTensor {
+  double* avg;
+  const void* cur; /* fp32 (model parameters / buffers) or fp64 (another averaged model) */
+  long long numel;
+  int cur_is_f64;
+  int reserved;
+} F2GAvgTensor;
+int f2g_average_update(const F2GAvgTensor* tab_dev, const int* chunks_dev, int n_chunks, double w_avg,
+                       double w_cur, double scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+"""Host emulation of the thread-independent SIMT kernels (csrc/datapath.cu written against
+csrc/simt.cuh): the SAME source is compiled with g++ -DF2G_HOST_EMUL so its index arithmetic and
+rounding can be checked on a box without a GPU.  Test infrastructure only; the product library
+never contains this build and flow2gan_b200/_lib.py never loads it."""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "flow2gan_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "_build")
+
+_lib = None
+
+
+class AvgTensor(C.Structure):
+    _fields_ = [("avg", C.c_void_p), ("cur", C.c_void_p), ("numel", C.c_longlong),
+                ("cur_is_f64", C.c_int), ("reserved", C.c_int)]
+
+
+def available() -> bool:
+    return shutil.which("g++") is not None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(CSRC, f) for f in ("datapath.cu", "simt.cuh")] + \
+               [os.path.join(ROOT, "include", "flow2gan_b200.h")]
+        h = hashlib.sha256()
+        for s in srcs:
+            h.update(open(s, "rb").read())
+        os.makedirs(OUT, exist_ok=True)
+        so = os.path.join(OUT, f"libf2g_datapath_emul_{h.hexdigest()[:12]}.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2G_HOST_EMUL",
+                                   "-shared", "-fPIC", srcs[0], "-o", so])
+        l = C.CDLL(so)
+        vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
+        l.f2g_pcm_decode.argtypes = [vp, i, i, ll, ll, vp, vp, vp]
+        l.f2g_gain_resample.argtypes = [vp, ll, vp, f, i, i, i, vp, vp, ll, vp]
+        l.f2g_pcm16_encode.argtypes = [vp, ll, i, vp, vp]
+        l.f2g_average_update.argtypes = [vp, vp, i, d, d, d, vp]
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    fn = lib().f2g_emul_last_error
+    fn.restype = C.c_char_p
+    return fn().decode()
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pcm_decode(raw: bytes, fmt: int, channels: int, first: int, n: int, with_stats: bool = True):
+    buf = np.frombuffer(bytearray(raw) + bytearray(8), dtype=np.uint8)     # aligned copy
+    mono = np.full(n, np.nan, dtype=np.float32)
+    stats = np.zeros(2, dtype=np.float32) if with_stats else None
+    rc = lib().f2g_pcm_decode(_p(buf), fmt, channels, first, n, _p(mono), _p(stats), None)
+    return rc, mono, stats
+
+
+def gain_resample(x: np.ndarray, stats, norm_db: float, orig_r: int, new_r: int, width: int, taps: np.ndarray,
+                  n_out: int):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    out = np.full(n_out, np.nan, dtype=np.float32)
+    rc = lib().f2g_gain_resample(_p(x), x.size, _p(stats), norm_db, orig_r, new_r, width, _p(taps), _p(out), n_out,
+                                 None)
+    return rc, out
+
+
+def pcm16_encode(x: np.ndarray, clamp: bool):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros(x.size, dtype=np.int16)
+    rc = lib().f2g_pcm16_encode(_p(x), x.size, int(clamp), _p(out), None)
+    return rc, out
+
+
+def average_update(pairs, w_avg: float, w_cur: float, scale: float, chunk: int = 4096):
+    """pairs: [(avg float64 ndarray (updated in place), cur float32|float64 ndarray)]"""
+    tab = (AvgTensor * len(pairs))()
+    chunks = []
+    for i, (a, c) in enumerate(pairs):
+        assert a.dtype == np.float64 and a.flags.c_contiguous and c.flags.c_contiguous
+        tab[i].avg, tab[i].cur, tab[i].numel = a.ctypes.data, c.ctypes.data, a.size
+        tab[i].cur_is_f64 = int(c.dtype == np.float64)
+        for ci in range((a.size + chunk - 1) // chunk):
+            chunks += [i, ci]
+    ch = np.asarray(chunks, dtype=np.int32)
+    return lib().f2g_average_update(C.cast(tab, C.c_void_p), _p(ch), len(chunks) // 2, w_avg, w_cur, scale, None)
