@@ -264,12 +264,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
         # ---------------- kernel-only (HBM-resident inputs), K graph replays ----------------
+        # clocks are sampled from the warm-up through the end-to-end loop: the device-timed region
+        # alone (K x 0.7 ms) is shorter than nvidia-smi's sampling period
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(W):
             plan.x_audio.copy_(noise)
             graph.replay()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -277,7 +279,6 @@ def run_ours(args):
             graph.replay()      # x_audio keeps evolving; the work per replay is data independent
         e1.record()
         barrier()
-        clocks = sampler.stop()
         ms_total = e0.elapsed_time(e1)
         t_dev = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         if dist is not None:
@@ -302,6 +303,7 @@ def run_ours(args):
         e3.record()
         barrier()
         wall = time.perf_counter() - t0
+        clocks = sampler.stop()
         ms_e2e = max(e2.elapsed_time(e3), wall * 1e3)
         t_dev = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
         if dist is not None:
@@ -394,7 +396,8 @@ def run_ours(args):
         "config": {"workload": f"{MODEL} {n}-step inference, synthetic mel (16,100,94) -> (16,24064) per GPU",
                    "global_batch": B * world, "parallelism": f"replicas x{world} (no data-path collective)",
                    "weights": "synthetic (seeded), reference state_dict layout",
-                   "l2": "no explicit flush: every step streams 316 MB of weights (> 126 MB L2)",
+                   "l2": "no explicit flush: every step streams its packed weights (~185 MB: fp16 block / conditioning "
+                         "matrices + TF32 projections) plus ~90 MB of activations, more than the 126 MB L2",
                    "timed": "K CUDA-graph replays between two CUDA events"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * N_MELS * FRAMES * 4,
                 "d2h_bytes_per_step": B * T * 4},

@@ -20,17 +20,10 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-def load_checkpoint(filename, model, strict: bool = False) -> dict:
-    """Loads `{"model": state_dict, ...}` checkpoints written by the reference
-    (flow2gan/checkpoint.py:111-168), including DDP 'module.'-prefixed ones."""
-    import torch
-    ckpt = torch.load(filename, map_location="cpu", weights_only=False)
-    sd = ckpt["model"]
-    if next(iter(sd)).startswith("module."):
-        sd = {k[len("module."):]: v for k, v in sd.items()}
-    model.load_state_dict(sd, strict=strict)
-    ckpt.pop("model")
-    return ckpt
+def load_checkpoint(filename, model, *args, **kwargs) -> dict:
+    """flow2gan.checkpoint.load_checkpoint (see flow2gan_b200/checkpoint.py)."""
+    from .checkpoint import load_checkpoint as _load
+    return _load(filename, model, *args, **kwargs)
 
 
 def get_model(model_name: str = "mel_24k_base", hf_model_name: Optional[str] = "libritts-mel-4-step",

@@ -82,7 +82,7 @@ class F2GAdamTensor(C.Structure):
 
 
 class F2GAvgTensor(C.Structure):
-    _fields_ = [("avg", _fp), ("cur", _fp), ("numel", _ll), ("cur_is_f64", _i), ("reserved", _i)]
+    _fields_ = [("avg", _fp), ("cur", _fp), ("numel", _ll), ("cur_is_f64", _i), ("avg_is_f32", _i)]
 
 
 class F2GAdamHyper(C.Structure):

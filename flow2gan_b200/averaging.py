@@ -41,6 +41,7 @@ def build_table(pairs: List[Tuple[Tensor, Tensor]]):
         tab[i].avg, tab[i].cur = a.data_ptr(), c.data_ptr()
         tab[i].numel = a.numel()
         tab[i].cur_is_f64 = int(c.dtype == torch.float64)
+        tab[i].avg_is_f32 = int(a.dtype == torch.float32)
         for ci in range((a.numel() + _CHUNK - 1) // _CHUNK):
             chunks += [i, ci]
     return tab, chunks
@@ -49,7 +50,8 @@ def build_table(pairs: List[Tuple[Tensor, Tensor]]):
 def average_state_dict(state_dict_1: Dict[str, Tensor], state_dict_2: Dict[str, Tensor], weight_1: float,
                        weight_2: float, scaling_factor: float = 1.0) -> Dict[str, Tensor]:
     """state_dict_1 = (state_dict_1 * weight_1 + state_dict_2 * weight_2) * scaling_factor, in place.
-    state_dict_1: fp64 CUDA tensors (the reference's `model_avg`, finetune.py:902)."""
+    state_dict_1: fp64 CUDA tensors (the reference's `model_avg`, finetune.py:902) -- or fp32 ones, which
+    is what the reference's model_avg becomes after its first save_checkpoint (checkpoint.py:94-95)."""
     keys = unique_float_keys(state_dict_1)
     pairs, keep_alive = [], []
     for k in keys:
@@ -57,8 +59,9 @@ def average_state_dict(state_dict_1: Dict[str, Tensor], state_dict_2: Dict[str, 
         if a.numel() == 0:
             continue
         L.require_cuda(a, f"average_state_dict: '{k}'")
-        if not (a.dtype == torch.float64 and a.is_contiguous()):
-            raise RuntimeError(f"average_state_dict: '{k}' must be a contiguous fp64 accumulator (got {a.dtype})")
+        if not (a.dtype in (torch.float64, torch.float32) and a.is_contiguous()):
+            raise RuntimeError(f"average_state_dict: '{k}' must be a contiguous fp64 / fp32 accumulator "
+                               f"(got {a.dtype})")
         c = state_dict_2[k]
         if c.device != a.device or c.dtype not in (torch.float32, torch.float64) or not c.is_contiguous():
             c = c.to(device=a.device)
@@ -68,7 +71,7 @@ def average_state_dict(state_dict_1: Dict[str, Tensor], state_dict_2: Dict[str, 
         pairs.append((a, c))
     if not pairs:
         return state_dict_1
-    key = tuple((a.data_ptr(), c.data_ptr(), a.numel(), c.dtype == torch.float64) for a, c in pairs)
+    key = tuple((a.data_ptr(), c.data_ptr(), a.numel(), a.dtype, c.dtype) for a, c in pairs)
     ent = _TABLES.get(key) if not keep_alive else None
     if ent is None:
         tab, chunks = build_table(pairs)
@@ -85,7 +88,7 @@ def average_state_dict(state_dict_1: Dict[str, Tensor], state_dict_2: Dict[str, 
 
 
 def _unwrap(m: nn.Module) -> nn.Module:
-    return m.module if hasattr(m, "module") and isinstance(getattr(m, "module"), nn.Module) else m
+    return m.module if isinstance(m, nn.parallel.DistributedDataParallel) else m
 
 
 def update_averaged_model(params, model_cur: nn.Module, model_avg: nn.Module) -> None:

@@ -96,25 +96,42 @@ F2G_KERNEL void pcm16_encode_kernel(const float* __restrict__ x, long long n, in
   }
 }
 
-// avg = (avg * w_avg + cur * w_cur) * scale, fp64 accumulator, every rounding step of the
-// reference's in-place sequence kept (v *= w1; v += cur * w2; v *= scale): an fp32 `cur` is
-// multiplied in fp32 (tensor * python float keeps the tensor dtype), an fp64 one in fp64.
+// avg = (avg * w_avg + cur * w_cur) * scale with every rounding step of the reference's in-place
+// sequence (v *= w1; v += cur * w2; v *= scale) as torch evaluates it:
+//   fp64 accumulator (model_avg as created, finetune.py:902): products / sum in fp64; an fp32 `cur`
+//     is first multiplied in fp32 (tensor * python float keeps the tensor dtype);
+//   fp32 accumulator (model_avg after the first save_checkpoint, which calls
+//     model_avg.to(torch.float32) in place, checkpoint.py:94-95): scalars are cast to fp32; adding an
+//     fp64 `cur` term promotes the sum to fp64 and rounds the result back to fp32.
 F2G_KERNEL void average_update_kernel(const F2GAvgTensor* __restrict__ tab, const int* __restrict__ chunks,
                                       double w_avg, double w_cur, double scale) {
   const int ti = chunks[2 * blockIdx.x], ci = chunks[2 * blockIdx.x + 1];
   const F2GAvgTensor t = tab[ti];
   const long long base = (long long)ci * AVG_CHUNK;
   const long long end = min(base + (long long)AVG_CHUNK, t.numel);
-  const float w_cur_f = (float)w_cur;
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-    double term;
-    if (t.cur_is_f64)
-      term = simt_dmul(reinterpret_cast<const double*>(t.cur)[i], w_cur);
-    else
-      term = (double)simt_fmul(reinterpret_cast<const float*>(t.cur)[i], w_cur_f);
-    double v = simt_dmul(t.avg[i], w_avg);
-    v = simt_dadd(v, term);
-    t.avg[i] = simt_dmul(v, scale);
+  const float w_avg_f = (float)w_avg, w_cur_f = (float)w_cur, scale_f = (float)scale;
+  if (!t.avg_is_f32) {
+    double* __restrict__ avg = reinterpret_cast<double*>(t.avg);
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+      double term;
+      if (t.cur_is_f64)
+        term = simt_dmul(reinterpret_cast<const double*>(t.cur)[i], w_cur);
+      else
+        term = (double)simt_fmul(reinterpret_cast<const float*>(t.cur)[i], w_cur_f);
+      double v = simt_dmul(avg[i], w_avg);
+      v = simt_dadd(v, term);
+      avg[i] = simt_dmul(v, scale);
+    }
+  } else {
+    float* __restrict__ avg = reinterpret_cast<float*>(t.avg);
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+      float v = simt_fmul(avg[i], w_avg_f);
+      if (t.cur_is_f64)
+        v = (float)simt_dadd((double)v, simt_dmul(reinterpret_cast<const double*>(t.cur)[i], w_cur));
+      else
+        v = simt_fadd(v, simt_fmul(reinterpret_cast<const float*>(t.cur)[i], w_cur_f));
+      avg[i] = simt_fmul(v, scale_f);
+    }
   }
 }
 

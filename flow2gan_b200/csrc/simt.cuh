@@ -31,6 +31,7 @@ F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v));
 }
 F2G_SIMT_DEV float simt_fmul(float a, float b) { return __fmul_rn(a, b); }
+F2G_SIMT_DEV float simt_fadd(float a, float b) { return __fadd_rn(a, b); }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return __dmul_rn(a, b); }
 F2G_SIMT_DEV double simt_dadd(double a, double b) { return __dadd_rn(a, b); }
 F2G_SIMT_DEV int simt_rint(float v) { return __float2int_rn(v); }
@@ -83,6 +84,7 @@ F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {
   if (v > *dst) *dst = v;
 }
 F2G_SIMT_DEV float simt_fmul(float a, float b) { return a * b; }
+F2G_SIMT_DEV float simt_fadd(float a, float b) { return a + b; }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return a * b; }
 F2G_SIMT_DEV double simt_dadd(double a, double b) { return a + b; }
 F2G_SIMT_DEV int simt_rint(float v) { return (int)lrintf(v); }   // default mode: nearest-even

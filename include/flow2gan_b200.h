@@ -387,16 +387,17 @@ int f2g_gain_resample(const float* x, long long n_in, const float* stats, float 
  * (flow2gan/bin/infer.py:208-212, bin/infer_dir.py:237); clamp != 0 bounds x to [-1, 1] first. */
 int f2g_pcm16_encode(const float* x, long long n, int clamp, short* out, void* stream);
 
-/* avg = (avg * w_avg + cur * w_cur) * scale on fp64 accumulators, every tensor of a model in one
- * launch (chunks: int pairs {tensor, 4096-element chunk}); replaces average_state_dict as used by
- * update_averaged_model / update_ema_model / average_checkpoints_with_averaged_model
+/* avg = (avg * w_avg + cur * w_cur) * scale, every tensor of a model in one launch (chunks: int
+ * pairs {tensor, 4096-element chunk}), with the rounding sequence of the reference's in-place
+ * torch ops for each dtype pair; replaces average_state_dict as used by update_averaged_model /
+ * update_ema_model / average_checkpoints_with_averaged_model
  * (flow2gan/checkpoint.py:378-409,411-441,443-531). */
 typedef struct F2GAvgTensor {
-  double* avg;
+  void* avg;       /* accumulator: fp64 (model_avg as created) or fp32 (after save_checkpoint's in-place downcast) */
   const void* cur; /* fp32 (model parameters / buffers) or fp64 (another averaged model) */
   long long numel;
   int cur_is_f64;
-  int reserved;
+  int avg_is_f32;
 } F2GAvgTensor;
 int f2g_average_update(const F2GAvgTensor* tab_dev, const int* chunks_dev, int n_chunks, double w_avg,
                        double w_cur, double scale, void* stream);

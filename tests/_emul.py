@@ -21,7 +21,7 @@ _lib = None
 
 class AvgTensor(C.Structure):
     _fields_ = [("avg", C.c_void_p), ("cur", C.c_void_p), ("numel", C.c_longlong),
-                ("cur_is_f64", C.c_int), ("reserved", C.c_int)]
+                ("cur_is_f64", C.c_int), ("avg_is_f32", C.c_int)]
 
 
 def available() -> bool:
@@ -87,13 +87,13 @@ def pcm16_encode(x: np.ndarray, clamp: bool):
 
 
 def average_update(pairs, w_avg: float, w_cur: float, scale: float, chunk: int = 4096):
-    """pairs: [(avg float64 ndarray (updated in place), cur float32|float64 ndarray)]"""
+    """pairs: [(avg float64|float32 ndarray (updated in place), cur float32|float64 ndarray)]"""
     tab = (AvgTensor * len(pairs))()
     chunks = []
     for i, (a, c) in enumerate(pairs):
-        assert a.dtype == np.float64 and a.flags.c_contiguous and c.flags.c_contiguous
+        assert a.dtype in (np.float64, np.float32) and a.flags.c_contiguous and c.flags.c_contiguous
         tab[i].avg, tab[i].cur, tab[i].numel = a.ctypes.data, c.ctypes.data, a.size
-        tab[i].cur_is_f64 = int(c.dtype == np.float64)
+        tab[i].cur_is_f64, tab[i].avg_is_f32 = int(c.dtype == np.float64), int(a.dtype == np.float32)
         for ci in range((a.size + chunk - 1) // chunk):
             chunks += [i, ci]
     ch = np.asarray(chunks, dtype=np.int32)

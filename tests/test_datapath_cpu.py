@@ -22,6 +22,7 @@ from oracle import datapath_oracle as DO
 sys.path.insert(0, GOLDEN)
 G = torch.load(os.path.join(GOLDEN, "ref_datapath.pt"), weights_only=False)
 needs_gxx = pytest.mark.skipif(not _emul.available(), reason="g++ not available")
+AVG_TAGS = ["running_fp32", "ema_fp32", "interval_fp64", "running_fp32_acc32", "interval_fp64_acc32"]
 
 
 # ------------------------------------------------------------------------------------ oracle
@@ -29,24 +30,25 @@ needs_gxx = pytest.mark.skipif(not _emul.available(), reason="g++ not available"
 def test_oracle_resample_matches_torchaudio_golden(case):
     y = DO.resample(case["x"][None], case["orig"], case["new"])[0]
     assert y.shape == case["y"].shape
-    assert torch.allclose(y, case["y"], rtol=0, atol=2e-7), float((y - case["y"]).abs().max())
+    # conv1d's fp32 summation order depends on the CPU backend's blocking / thread split
+    assert torch.allclose(y, case["y"], rtol=0, atol=1e-6), float((y - case["y"]).abs().max())
 
 
 def test_oracle_resample_matches_torchaudio_live():
     AF = pytest.importorskip("torchaudio.functional")
     x = torch.randn(2, 3001, generator=torch.Generator().manual_seed(3)) * 0.2
     for o, n in ((44100, 24000), (32000, 24000), (24000, 24000)):
-        assert torch.equal(DO.resample(x, o, n), AF.resample(x, orig_freq=o, new_freq=n))
+        assert torch.allclose(DO.resample(x, o, n), AF.resample(x, orig_freq=o, new_freq=n), rtol=0, atol=1e-6)
 
 
 def _avg_case(tag):
-    from make_golden_datapath import avg_inputs, clone_sd
+    from make_golden_datapath import avg_inputs, clone_sd, to_f32
     avg, cur32, cur64 = avg_inputs()
     g = next(a for a in G["avg"] if a["tag"] == tag)
-    return clone_sd(avg), (cur64 if "fp64" in tag else cur32), g
+    return (to_f32(avg) if tag.endswith("_acc32") else clone_sd(avg)), (cur64 if "fp64" in tag else cur32), g
 
 
-@pytest.mark.parametrize("tag", ["running_fp32", "ema_fp32", "interval_fp64"])
+@pytest.mark.parametrize("tag", AVG_TAGS)
 def test_oracle_average_state_dict_matches_reference(tag):
     avg, cur, g = _avg_case(tag)
     DO.average_state_dict(avg, cur, g["w1"], g["w2"], g["scale"])
@@ -230,7 +232,7 @@ def test_emulated_pcm16_encode_bit_exact():
 
 
 @needs_gxx
-@pytest.mark.parametrize("tag", ["running_fp32", "ema_fp32", "interval_fp64"])
+@pytest.mark.parametrize("tag", AVG_TAGS)
 def test_emulated_average_update_bit_exact_vs_reference(tag):
     avg, cur, g = _avg_case(tag)
     keys = [k for k in ("w1", "b1", "s", "tail")]
@@ -244,8 +246,8 @@ def test_emulated_average_update_bit_exact_vs_reference(tag):
 @needs_gxx
 def test_emulated_average_update_ragged_chunks():
     rng = np.random.default_rng(2)
-    sizes = [1, 4095, 4096, 4097, 10000, 3]
-    avg = [rng.standard_normal(s) for s in sizes]
+    sizes = [1, 4095, 4096, 4097, 10000, 3, 5000, 4098]
+    avg = [rng.standard_normal(s).astype(np.float32 if i >= 6 else np.float64) for i, s in enumerate(sizes)]
     cur = [rng.standard_normal(s).astype(np.float32 if i % 2 else np.float64) for i, s in enumerate(sizes)]
     sd1 = {str(i): torch.from_numpy(a.copy()) for i, a in enumerate(avg)}
     sd2 = {str(i): torch.from_numpy(c.copy()) for i, c in enumerate(cur)}
@@ -311,7 +313,7 @@ def test_host_layer_dry_run_collate_and_save(emulated_lib, tmp_path):
 
 
 @needs_gxx
-@pytest.mark.parametrize("tag", ["running_fp32", "ema_fp32", "interval_fp64"])
+@pytest.mark.parametrize("tag", AVG_TAGS)
 def test_host_layer_dry_run_average_state_dict(emulated_lib, tag):
     import _datapath_cases as DC
     DC.case_average_state_dict("cpu", tag)

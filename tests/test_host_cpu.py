@@ -67,3 +67,59 @@ def test_no_cpu_fallback():
     from flow2gan_b200.modules import LogMelSpectrogram
     with pytest.raises((RuntimeError, AssertionError)):
         LogMelSpectrogram()(torch.zeros(1, 4000))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/flow2gan"), reason="reference not mounted")
+def test_checkpoint_files_interoperate_with_reference(tmp_path):
+    """Files written by flow2gan_b200.checkpoint.save_checkpoint load with the reference's
+    load_checkpoint and vice versa (same top-level keys, DDP prefix handling, params passthrough,
+    the reference's in-place fp32 downcast of model_avg)."""
+    import copy
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    import_reference()
+    import flow2gan.checkpoint as RC
+    from flow2gan_b200 import checkpoint as MC
+    from make_golden_datapath import toy_model
+    m = toy_model()
+    avg = copy.deepcopy(m).to(torch.float64)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)
+    m.head.weight.sum().backward()
+    opt.step()
+    sched = torch.optim.lr_scheduler.StepLR(opt, 3)
+    params = {"batch_idx_train": 77, "best_train_loss": 0.5}
+    mine, ref = tmp_path / "mine.pt", tmp_path / "ref.pt"
+    MC.save_checkpoint(mine, m, model_avg=avg, params=params, optimizer=opt, scheduler=sched, optimizer_disc=opt)
+    assert next(avg.parameters()).dtype == torch.float32            # the reference's in-place downcast
+    avg = avg.to(torch.float64)
+    RC.save_checkpoint(ref, m, model_avg=avg, params=params, optimizer=opt, scheduler=sched, optimizer_disc=opt)
+    a = torch.load(mine, weights_only=False)
+    b = torch.load(ref, weights_only=False)
+    assert list(a.keys()) == list(b.keys())
+    for k in ("model", "model_avg"):
+        assert list(a[k]) == list(b[k]) and all(torch.equal(a[k][n], b[k][n]) and a[k][n].dtype == b[k][n].dtype
+                                                for n in a[k])
+    assert a["batch_idx_train"] == 77 and a["optimizer"]["param_groups"] == b["optimizer"]["param_groups"]
+    # cross loading, both directions, incl. a DDP-prefixed file
+    for saver_file, loader in ((mine, RC.load_checkpoint), (ref, MC.load_checkpoint)):
+        m2, avg2 = toy_model(), copy.deepcopy(toy_model()).to(torch.float64)
+        with torch.no_grad():
+            for p in m2.parameters():
+                p.zero_()
+        opt2 = torch.optim.SGD(m2.parameters(), lr=0.3, momentum=0.9)
+        rest = loader(saver_file, m2, model_avg=avg2, optimizer=opt2)
+        assert rest["batch_idx_train"] == 77 and "optimizer" not in rest and "model_avg" not in rest
+        assert all(torch.equal(x, y) for x, y in zip(m.state_dict().values(), m2.state_dict().values()))
+        assert opt2.param_groups[0]["lr"] == 0.1
+    ddp = tmp_path / "ddp.pt"
+    torch.save({"model": {"module." + k: v for k, v in m.state_dict().items()}}, ddp)
+    m3 = toy_model()
+    with torch.no_grad():
+        m3.gain.fill_(5.0)
+    MC.load_checkpoint(ddp, m3)
+    assert all(torch.equal(x, y) for x, y in zip(m.state_dict().values(), m3.state_dict().values()))
+    avg_keep = copy.deepcopy(m).to(torch.float64)
+    MC.save_checkpoint(tmp_path / "keep.pt", m, model_avg=avg_keep, downcast_avg_in_place=False)
+    assert next(avg_keep.parameters()).dtype == torch.float64
+    assert torch.load(tmp_path / "keep.pt", weights_only=False)["model_avg"]["gain"].dtype == torch.float32

@@ -14,6 +14,7 @@ from _cases import GOLDEN, rel_rms
 from oracle import datapath_oracle as DO
 
 pytestmark = pytest.mark.gpu
+AVG_TAGS = ["running_fp32", "ema_fp32", "interval_fp64", "running_fp32_acc32", "interval_fp64_acc32"]
 
 
 def test_load_wav_reproduces_reference_mel_fixture():
@@ -41,7 +42,7 @@ def test_pcm16_encode_and_save_wav_round_trip(tmp_path):
     DC.case_encode_save_round_trip("cuda", tmp_path)
 
 
-@pytest.mark.parametrize("tag", ["running_fp32", "ema_fp32", "interval_fp64"])
+@pytest.mark.parametrize("tag", AVG_TAGS)
 def test_average_state_dict_bit_exact_vs_reference(tag):
     DC.case_average_state_dict("cuda", tag)
     from flow2gan_b200.averaging import average_state_dict
