@@ -112,7 +112,7 @@ class ClockSampler:
 def build_model(device):
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator
-    from oracle.synth import synth_state_dict
+    from _synth import synth_state_dict
     torch.manual_seed(0)
     m = MelAudioGenerator(**get_generator_config(MODEL))
     spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
@@ -122,7 +122,7 @@ def build_model(device):
 
 def cpu_oracle_rate(n_timesteps: int, iters: int, warmup: int = 1):
     from oracle import flow2gan_oracle as O
-    from oracle.synth import synth_state_dict
+    from _synth import synth_state_dict
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator
     ncpu = os.cpu_count() or 1
@@ -166,7 +166,7 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
     from flow2gan_b200.gan import GAN
     from flow2gan_b200.generator import MelAudioGenerator
     from flow2gan_b200.trainer import GANTrainer
-    from oracle.synth import synth_state_dict
+    from _synth import synth_state_dict
     torch.manual_seed(0)
     gen = MelAudioGenerator(**get_generator_config(MODEL))
     gen.branch_dropout = 0.0

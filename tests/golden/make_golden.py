@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from _cases import audio_input, mel_input, noise_input  # noqa: E402
-from oracle.synth import synth_state_dict  # noqa: E402
+from _synth import synth_state_dict  # noqa: E402
 
 
 def import_reference():

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from _cases import GOLDEN, rel_rms
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 from test_train_gpu import _assert_grads, _grad_errors
 
 pytestmark = pytest.mark.gpu

@@ -7,7 +7,7 @@ import torch
 
 from _cases import GOLDEN, rel_rms
 from oracle import flow2gan_oracle as O
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 
 torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
 

@@ -31,7 +31,7 @@ def test_streaming_matches_oracle_chunk_by_chunk():
     from flow2gan_b200.generator import MelAudioGenerator
     from flow2gan_b200.streaming import infer_audio, streaming_infer_audio
     from oracle import flow2gan_oracle as O
-    from oracle.synth import synth_state_dict
+    from _synth import synth_state_dict
     torch.manual_seed(0)
     m = MelAudioGenerator(**get_generator_config("mel_24k_base"))
     sd = synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 99)

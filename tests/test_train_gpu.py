@@ -14,7 +14,7 @@ import torch
 
 from _cases import GOLDEN, audio_input, mel_input, noise_input, rel_rms
 from oracle import flow2gan_oracle as O
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 
 pytestmark = pytest.mark.gpu
 

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from _cases import audio_input, rel_rms
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 
 pytestmark = pytest.mark.gpu
 B, T = 2, 8192

@@ -83,7 +83,7 @@ def test_pretrain_step_and_model_average():
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator
     from flow2gan_b200.pretrainer import FMTrainer
-    from oracle.synth import synth_state_dict
+    from _synth import synth_state_dict
     g = torch.load(os.path.join(GOLDEN, "ref_fm_loss_24k.pt"), weights_only=False)
     m = MelAudioGenerator(**get_generator_config(g["model_name"]))
     m.load_state_dict(synth_state_dict(g["sd_spec"], g["sd_seed"]), strict=False)

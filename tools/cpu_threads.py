@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 from oracle import flow2gan_oracle as O
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 from flow2gan_b200 import get_generator_config
 from flow2gan_b200.generator import MelAudioGenerator
 m = MelAudioGenerator(**get_generator_config("mel_24k_base"))

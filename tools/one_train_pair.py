@@ -8,7 +8,7 @@ from flow2gan_b200 import get_gan_config, get_generator_config
 from flow2gan_b200.gan import GAN
 from flow2gan_b200.generator import MelAudioGenerator
 from flow2gan_b200.trainer import GANTrainer
-from oracle.synth import synth_state_dict
+from _synth import synth_state_dict
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 gen = MelAudioGenerator(**get_generator_config(bench.MODEL)); gen.branch_dropout = 0.0
