@@ -9,7 +9,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libflow2gan_b200.so")
-SOURCES = ["api.cu", "gemm_tf32.cu", "gemm_pair.cu", "spectral.cu", "blocks.cu", "optim.cu", "train.cu", "conv.cu", "datapath.cu"]
+SOURCES = ["api.cu", "gemm_tf32.cu", "gemm_pair.cu", "spectral.cu", "blocks.cu", "optim.cu", "train.cu", "conv.cu", "datapath.cu", "losses.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

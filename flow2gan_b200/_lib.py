@@ -19,6 +19,7 @@ ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_SILU = 0, 1, 2, 3
 SPEC_PACKED, SPEC_MAG, SPEC_POWER, SPEC_COMPLEX = 0, 1, 2, 3
 GEMM_MAX_PROBLEMS = 8
 PCM_F32, PCM_S16, PCM_S24, PCM_S32 = 1, 16, 24, 32
+LOSS_L1, LOSS_HINGE = 0, 1
 
 _fp = C.c_void_p
 _i = C.c_int
@@ -85,6 +86,12 @@ class F2GAvgTensor(C.Structure):
     _fields_ = [("avg", _fp), ("cur", _fp), ("numel", _ll), ("cur_is_f64", _i), ("avg_is_f32", _i)]
 
 
+class F2GLossTerm(C.Structure):
+    _fields_ = [("a", _fp), ("b", _fp), ("grad", _fp), ("numel", _ll), ("stride_a", _ll * 4),
+                ("stride_b", _ll * 4), ("dims", _i * 4), ("scale", _f), ("sign", _f), ("mode", _i),
+                ("reserved", _i)]
+
+
 class F2GAdamHyper(C.Structure):
     _fields_ = [("lr", _f), ("scalar_lr_scale", _f), ("beta1", _f), ("beta2", _f), ("eps", _f),
                 ("param_min_rms", _f), ("param_max_rms", _f), ("scalar_max", _f),
@@ -134,6 +141,7 @@ _SIGS = {
     "f2g_gain_resample": ([_fp, _ll, _fp, _f, _i, _i, _i, _fp, _fp, _ll, _fp], _i),
     "f2g_pcm16_encode": ([_fp, _ll, _i, _fp, _fp], _i),
     "f2g_average_update": ([_fp, _fp, _i, C.c_double, C.c_double, C.c_double, _fp], _i),
+    "f2g_loss_terms": ([C.POINTER(F2GLossTerm), _i, _i, _fp, _fp, _fp], _i),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -159,7 +167,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 5:
+        if lib.f2g_abi_version() != 6:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -487,3 +495,33 @@ def average_update(tab_u8, chunks_i32, n_chunks, w_avg, w_cur, scale):
     assert chunks_i32.is_cuda and chunks_i32.dtype == torch.int32
     _check(lib().f2g_average_update(tab_u8.data_ptr(), chunks_i32.data_ptr(), n_chunks, float(w_avg),
                                     float(w_cur), float(scale), stream()))
+
+
+# ---------------------------------------------------------------------------------------
+# fused multi-tensor loss reductions (csrc/losses.cu)
+# ---------------------------------------------------------------------------------------
+def loss_term(mode: int, a: torch.Tensor, b: Optional[torch.Tensor], grad: Optional[torch.Tensor],
+              sign: float = 0.0) -> F2GLossTerm:
+    """Descriptor of one term over the (<= 4-D, arbitrarily strided) tensor `a` (and `b`, same shape)."""
+    assert a.dim() <= 4 and a.numel() > 0, a.shape
+    pad = 4 - a.dim()
+    t = F2GLossTerm()
+    t.a, t.b, t.grad = ptr(a), ptr(b), ptr(grad)
+    t.numel = a.numel()
+    dims = [1] * pad + list(a.shape)
+    sa = [0] * pad + list(a.stride())
+    sb = [0] * pad + list(b.stride()) if b is not None else [0] * 4
+    if b is not None:
+        assert b.shape == a.shape, (a.shape, b.shape)
+    if grad is not None:
+        assert grad.is_contiguous() and grad.numel() == a.numel()
+    for k in range(4):
+        t.dims[k], t.stride_a[k], t.stride_b[k] = dims[k], sa[k], sb[k]
+    t.scale, t.sign, t.mode = 1.0 / a.numel(), float(sign), mode
+    return t
+
+
+def loss_terms(terms: Sequence[F2GLossTerm], backward: bool, out: Optional[torch.Tensor],
+               gout: Optional[torch.Tensor]) -> None:
+    arr = (F2GLossTerm * len(terms))(*terms)
+    _check(lib().f2g_loss_terms(arr, len(terms), int(backward), ptr(out), ptr(gout), stream()))

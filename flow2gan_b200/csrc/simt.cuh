@@ -14,8 +14,11 @@
 // ------------------------------------------------------------------------------------ CUDA
 #include "common.cuh"
 
+#include <string.h>
+
 #define F2G_KERNEL __global__
 #define F2G_SIMT_DEV __device__ __forceinline__
+#define F2G_GRID_CONSTANT __grid_constant__
 #define F2G_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 
 namespace f2g {
@@ -35,6 +38,14 @@ F2G_SIMT_DEV float simt_fadd(float a, float b) { return __fadd_rn(a, b); }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return __dmul_rn(a, b); }
 F2G_SIMT_DEV double simt_dadd(double a, double b) { return __dadd_rn(a, b); }
 F2G_SIMT_DEV int simt_rint(float v) { return __float2int_rn(v); }
+inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(p, v, n, s);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
 }  // namespace f2g
 
 #else
@@ -47,6 +58,7 @@ F2G_SIMT_DEV int simt_rint(float v) { return __float2int_rn(v); }
 
 #define F2G_KERNEL static
 #define F2G_SIMT_DEV static inline
+#define F2G_GRID_CONSTANT
 #define __restrict__ __restrict
 
 typedef void* cudaStream_t;
@@ -70,7 +82,7 @@ static f2g_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace f2g {
 enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
-static char g_emul_err[512];
+inline char g_emul_err[512];       // one buffer for every translation unit of the emulated library
 static inline void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -88,9 +100,13 @@ F2G_SIMT_DEV float simt_fadd(float a, float b) { return a + b; }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return a * b; }
 F2G_SIMT_DEV double simt_dadd(double a, double b) { return a + b; }
 F2G_SIMT_DEV int simt_rint(float v) { return (int)lrintf(v); }   // default mode: nearest-even
+static inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t) {
+  memset(p, v, n);
+  return 0;
+}
 }  // namespace f2g
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
-extern "C" const char* f2g_emul_last_error(void) { return f2g::g_emul_err; }
+extern "C" __attribute__((weak)) const char* f2g_emul_last_error(void) { return f2g::g_emul_err; }
 #endif
 
 // global thread id / stride of a 1-D launch (64-bit: waveforms of hours still index correctly)

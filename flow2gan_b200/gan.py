@@ -2,14 +2,20 @@
 tuples and train()/eval() side effects (flow2gan/models/gan.py:30-166)."""
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor, nn
 
 from .discriminators import MultiPeriodDiscriminator, MultiResolutionDiscriminator
-from .losses import mel_recon_loss
+from .losses import hinge_terms, l1_terms, mel_recon_loss
 from .modules import MelSpectrogram
+
+# F2G_FUSED_LOSSES=1: hinge / feature-matching / mel L1 reductions through the multi-tensor kernels of
+# csrc/losses.cu (one launch per <= 24 terms each way) instead of element-wise torch ops per term.
+# Off by default until the round-2 GPU parity run has covered it (tests/test_zz_losses_gpu.py).
+FUSED_LOSSES = os.environ.get("F2G_FUSED_LOSSES", "0") == "1"
 
 
 class GAN(nn.Module):
@@ -26,6 +32,9 @@ class GAN(nn.Module):
 
     @staticmethod
     def discriminator_loss(score_real: List[Tensor], score_fake: List[Tensor]):
+        if FUSED_LOSSES:
+            return hinge_terms(list(score_real) + list(score_fake),
+                               [-1.0] * len(score_real) + [1.0] * len(score_fake))
         loss = 0
         for s_real, s_fake in zip(score_real, score_fake):
             loss = loss + torch.mean(torch.clamp(1 - s_real, min=0)) + torch.mean(torch.clamp(1 + s_fake, min=0))
@@ -33,6 +42,8 @@ class GAN(nn.Module):
 
     @staticmethod
     def generator_loss(score_fake: List[Tensor]):
+        if FUSED_LOSSES:
+            return hinge_terms(list(score_fake), [-1.0] * len(score_fake))
         loss = 0
         for s_fake in score_fake:
             loss = loss + torch.mean(torch.clamp(1 - s_fake, min=0))
@@ -40,6 +51,10 @@ class GAN(nn.Module):
 
     @staticmethod
     def feature_matching_loss(fmap_real: List[List[Tensor]], fmap_fake: List[List[Tensor]]):
+        if FUSED_LOSSES:
+            for f_real, f_fake in zip(fmap_real, fmap_fake):
+                assert isinstance(f_real, list) and isinstance(f_fake, list)
+            return l1_terms([r for fr in fmap_real for r in fr], [f for ff in fmap_fake for f in ff])
         loss = 0
         for f_real, f_fake in zip(fmap_real, fmap_fake):
             assert isinstance(f_real, list) and isinstance(f_fake, list)
@@ -48,7 +63,7 @@ class GAN(nn.Module):
         return loss
 
     def mel_recon_loss(self, real: Tensor, fake: Tensor):
-        return mel_recon_loss(self.mel_recon_modules, real, fake)
+        return mel_recon_loss(self.mel_recon_modules, real, fake, fused=FUSED_LOSSES)
 
     def forward(self, cond: Tensor, audio: Tensor, audio_lens: Optional[Tensor] = None,
                 n_timesteps: int = 1, train_disc: bool = True, noise: Optional[Tensor] = None):

@@ -60,13 +60,82 @@ def spectral_scaled_loss(model, pred: Tensor, ref: Tensor, audio_lens: Tensor) -
     return (es * scale * mask).sum() / (mask.sum() * es.shape[2])
 
 
-def mel_recon_loss(mel_modules, real: Tensor, fake: Tensor) -> Tensor:
+def mel_recon_loss(mel_modules, real: Tensor, fake: Tensor, fused: bool = False) -> Tensor:
     """GAN.mel_recon_loss (gan.py:89-99): sum_k L1(log-mel_k(real), log-mel_k(fake))."""
     loss = 0
+    rs, fs = [], []
     for m in mel_modules:
         fb = m.mel_scale.fb
         with torch.no_grad():
             r = filter_spec_rows(real, fb, m.n_fft, m.hop_length, L.SPEC_MAG, 1e-7)
         f = filter_spec_rows(fake, fb, m.n_fft, m.hop_length, L.SPEC_MAG, 1e-7)
-        loss = loss + torch.nn.functional.l1_loss(r, f)
-    return loss
+        if fused:
+            rs.append(r)
+            fs.append(f)
+        else:
+            loss = loss + torch.nn.functional.l1_loss(r, f)
+    return l1_terms(rs, fs) if fused else loss
+
+
+# ---------------------------------------------------------------------------------------------
+# fused multi-tensor reductions of GAN.forward's loss terms (csrc/losses.cu): one launch per <= 24
+# terms each way instead of 3-4 element-wise torch launches per term and direction
+# ---------------------------------------------------------------------------------------------
+class _L1TermsFn(torch.autograd.Function):
+    """sum_i mean|ref_i - x_i|, differentiable w.r.t. the x_i (refs are constants)."""
+
+    @staticmethod
+    def forward(ctx, n: int, *tensors: Tensor):
+        refs, xs = tensors[:n], tensors[n:]
+        out = torch.empty(1, device=xs[0].device, dtype=torch.float32)
+        L.loss_terms([L.loss_term(L.LOSS_L1, r, x, None) for r, x in zip(refs, xs)], False, out, None)
+        ctx.save_for_backward(*tensors)
+        ctx.n = n
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        n = ctx.n
+        refs, xs = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        grads = [torch.empty(x.shape, device=x.device, dtype=torch.float32) for x in xs]
+        gout = g.reshape(1).float().contiguous()
+        L.loss_terms([L.loss_term(L.LOSS_L1, r, x, d) for r, x, d in zip(refs, xs, grads)], True, None, gout)
+        return (None,) + (None,) * n + tuple(grads)
+
+
+class _HingeTermsFn(torch.autograd.Function):
+    """sum_i mean(clamp(1 + sign_i * s_i, min=0)), differentiable w.r.t. the scores."""
+
+    @staticmethod
+    def forward(ctx, signs, *scores: Tensor):
+        out = torch.empty(1, device=scores[0].device, dtype=torch.float32)
+        L.loss_terms([L.loss_term(L.LOSS_HINGE, s, None, None, sg) for s, sg in zip(scores, signs)], False, out, None)
+        ctx.save_for_backward(*scores)
+        ctx.signs = tuple(signs)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        scores = ctx.saved_tensors
+        grads = [torch.empty(s.shape, device=s.device, dtype=torch.float32) for s in scores]
+        gout = g.reshape(1).float().contiguous()
+        L.loss_terms([L.loss_term(L.LOSS_HINGE, s, None, d, sg) for s, d, sg in zip(scores, grads, ctx.signs)],
+                     True, None, gout)
+        return (None,) + tuple(grads)
+
+
+def _as4d(t: Tensor) -> Tensor:
+    return t if t.dim() <= 4 else t.reshape(-1, *t.shape[-3:])
+
+
+def l1_terms(refs, xs) -> Tensor:
+    """sum_i l1_loss(refs[i].detach(), xs[i]) (feature_matching_loss gan.py:72-87, mel_recon_loss :89-99)."""
+    refs = [_as4d(r.detach().float()) for r in refs]
+    xs = [_as4d(x.float()) for x in xs]
+    return _L1TermsFn.apply(len(refs), *refs, *xs)
+
+
+def hinge_terms(scores, signs) -> Tensor:
+    """sum_i mean(clamp(1 + signs[i] * scores[i], min=0)) (discriminator_loss gan.py:57-63 with signs
+    -1 for real / +1 for fake scores; generator_loss :65-70 with -1 for fake scores)."""
+    return _HingeTermsFn.apply(tuple(float(s) for s in signs), *[_as4d(s.float()) for s in scores])

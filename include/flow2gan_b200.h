@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 5
+#define F2G_ABI_VERSION 6
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -401,6 +401,36 @@ typedef struct F2GAvgTensor {
 } F2GAvgTensor;
 int f2g_average_update(const F2GAvgTensor* tab_dev, const int* chunks_dev, int n_chunks, double w_avg,
                        double w_cur, double scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-tensor loss reductions of GAN.forward (flow2gan/models/gan.py:57-99):
+ *   F2G_LOSS_L1    term = scale * sum |a - b|              (feature matching :72-87, a = real.detach();
+ *                                                          log-mel reconstruction :89-99); gradient w.r.t. b
+ *   F2G_LOSS_HINGE term = scale * sum clamp(1 + sign*a, 0) (discriminator_loss :57-63, generator_loss
+ *                                                          :65-70; sign = -1 for real scores in the D loss and
+ *                                                          for fake scores in the G loss, +1 for fake scores in
+ *                                                          the D loss); gradient w.r.t. a
+ * with scale = 1 / numel (torch.mean).  `terms` is a HOST array (descriptors travel as kernel
+ * parameters, 24 per launch); tensors are addressed through 4-D dims / element strides (permuted or
+ * channel-sliced views).  backward = 0: out[0] = sum of all terms.  backward = 1: every term's
+ * `grad` (contiguous, logical order) = gout[0] * d(term)/d(input).
+ * ------------------------------------------------------------------------------------- */
+enum { F2G_LOSS_L1 = 0, F2G_LOSS_HINGE = 1 };
+typedef struct F2GLossTerm {
+  const float* a;
+  const float* b;
+  float* grad;
+  long long numel;
+  long long stride_a[4];
+  long long stride_b[4];
+  int dims[4];
+  float scale;
+  float sign;
+  int mode;
+  int reserved;
+} F2GLossTerm;
+int f2g_loss_terms(const F2GLossTerm* terms, int n_terms, int backward, float* out, const float* gout,
+                   void* stream);
 
 #ifdef __cplusplus
 }

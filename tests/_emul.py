@@ -31,8 +31,8 @@ def available() -> bool:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        srcs = [os.path.join(CSRC, f) for f in ("datapath.cu", "simt.cuh")] + \
-               [os.path.join(ROOT, "include", "flow2gan_b200.h")]
+        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu")]
+        srcs = cus + [os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
         h = hashlib.sha256()
         for s in srcs:
             h.update(open(s, "rb").read())
@@ -40,13 +40,14 @@ def lib() -> C.CDLL:
         so = os.path.join(OUT, f"libf2g_datapath_emul_{h.hexdigest()[:12]}.so")
         if not os.path.exists(so):
             subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2G_HOST_EMUL",
-                                   "-shared", "-fPIC", srcs[0], "-o", so])
+                                   "-shared", "-fPIC", *cus, "-o", so])
         l = C.CDLL(so)
         vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
         l.f2g_pcm_decode.argtypes = [vp, i, i, ll, ll, vp, vp, vp]
         l.f2g_gain_resample.argtypes = [vp, ll, vp, f, i, i, i, vp, vp, ll, vp]
         l.f2g_pcm16_encode.argtypes = [vp, ll, i, vp, vp]
         l.f2g_average_update.argtypes = [vp, vp, i, d, d, d, vp]
+        l.f2g_loss_terms.argtypes = [vp, i, i, vp, vp, vp]
         _lib = l
     return _lib
 

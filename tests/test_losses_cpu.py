@@ -1,0 +1,62 @@
+"""CPU checks of the fused multi-tensor loss reductions: csrc/losses.cu compiled for the host from the
+same source (tests/_emul.py) behind the product's autograd wrappers (flow2gan_b200/losses.py,
+gan.py), against torch autograd of the reference's expressions (flow2gan/models/gan.py:57-99)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import _emul
+import _losses_cases as LC
+
+pytestmark = pytest.mark.skipif(not _emul.available(), reason="g++ not available")
+
+
+@pytest.fixture
+def emulated_losses(monkeypatch):
+    from flow2gan_b200 import _lib as L
+    e = _emul.lib()
+
+    def loss_terms(terms, backward, out, gout):
+        arr = (L.F2GLossTerm * len(terms))(*terms)
+        rc = e.f2g_loss_terms(C.cast(arr, C.c_void_p), len(terms), int(backward),
+                              None if out is None else C.c_void_p(out.data_ptr()),
+                              None if gout is None else C.c_void_p(gout.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError("flow2gan_b200 native call failed (rc=%d): %s" % (rc, _emul.last_error()))
+
+    monkeypatch.setattr(L, "ptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(L, "loss_terms", loss_terms)
+    return L
+
+
+def test_l1_terms(emulated_losses):
+    LC.case_l1_terms("cpu")
+    LC.case_l1_terms_strided_grad_flow("cpu")
+
+
+def test_hinge_terms(emulated_losses):
+    LC.case_hinge_terms("cpu")
+
+
+def test_gan_loss_methods(emulated_losses, monkeypatch):
+    LC.case_gan_loss_methods("cpu", monkeypatch)
+
+
+def test_malformed_terms_are_refused(emulated_losses):
+    L = emulated_losses
+    x = torch.zeros(4, 4)
+    t = L.loss_term(L.LOSS_L1, x, x, None)
+    t.dims[0] = 3                                   # dims no longer multiply to numel
+    with pytest.raises(RuntimeError, match="dims do not multiply"):
+        L.loss_terms([t], False, torch.zeros(1), None)
+    t = L.loss_term(L.LOSS_HINGE, x, None, None, 1.0)
+    with pytest.raises(RuntimeError, match="malformed"):
+        L.loss_terms([t], True, None, torch.ones(1))         # backward without a grad buffer
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less box")
+def test_no_cpu_fallback():
+    from flow2gan_b200.losses import hinge_terms
+    with pytest.raises((RuntimeError, AssertionError)):
+        hinge_terms([torch.zeros(3)], [1.0])
