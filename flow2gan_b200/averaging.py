@@ -118,3 +118,30 @@ def average_checkpoints_with_averaged_model(filename_start: str, filename_end: s
     avg = sd_end["model_avg"]
     average_state_dict(avg, sd_start["model_avg"], 1.0, weight_start / weight_end, weight_end)
     return avg
+
+
+def average_checkpoints(filenames, device: torch.device = torch.device("cuda")) -> Dict[str, Tensor]:
+    """Plain mean of the `model` entries of several checkpoints (checkpoint.py:171-212, used by
+    bin/save_averaged_model.py:148-157).  The running sums are one `f2g_average_update` launch per
+    checkpoint (v * 1 + cur * 1 is the reference's fp32 `avg[k] += state_dict[k]` bit for bit); the
+    final division keeps torch's true-division rounding (one multi-tensor op)."""
+    n = len(filenames)
+    avg = torch.load(filenames[0], map_location=device, weights_only=False)["model"]
+    keys = unique_float_keys(avg)
+    seen, int_keys = set(), []
+    for k, v in avg.items():
+        if v.data_ptr() not in seen:
+            seen.add(v.data_ptr())
+            if not torch.is_floating_point(v):
+                int_keys.append(k)
+    for i in range(1, n):
+        sd = torch.load(filenames[i], map_location=device, weights_only=False)["model"]
+        average_state_dict(avg, sd, 1.0, 1.0)
+        for k in int_keys:
+            avg[k] += sd[k]
+    floats = [avg[k] for k in keys if avg[k].numel() > 0]
+    if floats:
+        torch._foreach_div_(floats, n)
+    for k in int_keys:
+        avg[k] //= n
+    return avg

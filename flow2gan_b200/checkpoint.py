@@ -13,8 +13,8 @@ from typing import Any, Dict, Optional
 import torch
 from torch import nn
 
-from .averaging import (average_checkpoints_with_averaged_model, average_state_dict,  # noqa: F401
-                        update_averaged_model, update_ema_model)
+from .averaging import (average_checkpoints, average_checkpoints_with_averaged_model,  # noqa: F401
+                        average_state_dict, update_averaged_model, update_ema_model)
 
 
 def _unwrap(model: nn.Module) -> nn.Module:

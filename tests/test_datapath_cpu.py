@@ -323,6 +323,7 @@ def test_host_layer_dry_run_average_state_dict(emulated_lib, tag):
 def test_host_layer_dry_run_model_average_helpers(emulated_lib, tmp_path):
     import _datapath_cases as DC
     DC.case_model_average_helpers("cpu", tmp_path)
+    DC.case_average_checkpoints("cpu", tmp_path)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less box")

@@ -52,6 +52,7 @@ def test_average_state_dict_bit_exact_vs_reference(tag):
 
 def test_model_average_helpers(tmp_path):
     DC.case_model_average_helpers("cuda", tmp_path)
+    DC.case_average_checkpoints("cuda", tmp_path)
 
 
 def test_large_waveform_streams():
