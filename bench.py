@@ -15,6 +15,7 @@ configuration).  Prints ONE JSON line (rank 0).
                (pwconv1/pwconv2): sum(2*M*N*K) of its launches in one step / their time when
                replayed back to back from a CUDA graph (CUDA events), against the measured dense
                bf16/fp16 tensor peak; `roofline_other` = the remaining TF32 GEMM launches;
+               `roofline_hbm` = the block-prologue launches (dominant HBM-bound kernel) the same way;
                `traffic` = dram bytes per launch from the committed ncu capture (profiles/).
   cpu_baseline / --impl reference : the oracle port (oracle/flow2gan_oracle.py, a functional
                restatement of the reference's PyTorch path; the reference itself is Python and
@@ -314,27 +315,28 @@ def run_ours(args):
         # The step's GEMM launches (same descriptors, same buffers) are re-issued alone, back to
         # back, from a CUDA graph so that no host submission latency sits between the two events:
         # achieved = sum(2MNK) / (event time / launches) -- the in-step average launch duration.
-        roof = roof_other = None
+        roof = roof_other = roof_hbm = None
         if rank == 0:
-            L.PROFILE = []
+            L.PROFILE, L.PROFILE_PRE = [], []
             plan.x_audio.copy_(noise)
             plan._run(n, False)
             torch.cuda.synchronize()
             rec, L.PROFILE = L.PROFILE, None
+            rec_pre, L.PROFILE_PRE = L.PROFILE_PRE, None
             pk, how = peaks()
 
-            def replay_timed(sub):
-                """GEMM launches `sub` re-issued alone, back to back, from a CUDA graph on a side
+            def replay_timed(sub, issue=L.gemm_replay):
+                """Launches `sub` re-issued alone, back to back, from a CUDA graph on a side
                 stream (no host submission latency between the two events)."""
                 side = torch.cuda.Stream()
                 with torch.cuda.stream(side):
-                    for arr, cnt, _, _ in sub:
-                        L.gemm_replay(arr, cnt)
+                    for r in sub:
+                        issue(r[0], r[1])
                     side.synchronize()
                     gg = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gg, stream=side):
-                        for arr, cnt, _, _ in sub:
-                            L.gemm_replay(arr, cnt)
+                        for r in sub:
+                            issue(r[0], r[1])
                     reps = 10
                     for _ in range(3):
                         gg.replay()
@@ -370,6 +372,24 @@ def run_ours(args):
             else:
                 roof = roof_entry(t32, "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32)",
                                   pk["bf16_tflops"] / 2.0, "bf16_tflops (burst)/2 -- TF32 issues at half the bf16 rate")
+            # The generator's dominant HBM-bound kernel: the block prologue (mask -> dwconv7 -> BiasNorm ->
+            # + cond -> x(1 + time scale) -> fp16), 19 % of the step.  Algorithmic bytes = residual
+            # stream read (fp32) + prologue output written (6 B per row x channel).
+            try:
+                if rec_pre:
+                    by = sum(r[2] for r in rec_pre)
+                    ms = replay_timed(rec_pre, issue=L.block_pre_replay)
+                    ach = by / (ms * 1e-3) / 1e9
+                    roof_hbm = {"bound": "hbm", "kernel": "block_pre_kernel (grouped ConvNeXt block prologue)",
+                                "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                                "traffic": None, "launches_timed": len(rec_pre),
+                                "bytes_per_launch_avg": by / len(rec_pre), "us_per_launch_avg": ms * 1e3 / len(rec_pre),
+                                "how": "the step's launches of this kernel replayed back to back from a CUDA graph, "
+                                       "CUDA events on the launching stream; inputs stay L2-resident between "
+                                       "replays, so this is the kernel's own ceiling, not a DRAM measurement",
+                                "peak_source": f"{how}: hbm_gbs"}
+            except Exception as e:                      # never lose the headline line to the extra leg
+                roof_hbm = {"error": repr(e)[:200]}
             roof["step_ref_equiv_tflops"] = REF_FLOPS[n] * K / (ms_total * 1e-3) / 1e12
             tr_path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
             if os.path.exists(tr_path):       # dram__bytes_{read,write}.sum of the same launches (ncu --set full)
@@ -407,6 +427,8 @@ def run_ours(args):
     }
     if roof_other is not None:
         line["roofline_other"] = roof_other
+    if roof_hbm is not None:
+        line["roofline_hbm"] = roof_hbm
     if train is not None:
         line["gan_train"] = train
     if cpu_rate is not None:

@@ -148,6 +148,7 @@ _lib: Optional[C.CDLL] = None
 _device_ok = False
 COUNT = 0            # native launches issued through this module (bench.py's gpu_launches)
 PROFILE = None       # when a list: gemm_group appends (descriptor array, n, flops, fp16 operands?)
+PROFILE_PRE = None   # when a list: block_pre_group appends (descriptor array, n, algorithmic bytes)
 
 
 def exported_symbols() -> Sequence[str]:
@@ -334,6 +335,14 @@ def block_pre_group(descs, zero: Optional[torch.Tensor] = None) -> None:
     arr = (F2GBlockPre * n)(*descs)
     if zero is not None:
         arr[0].zero_ptr, arr[0].zero_n = ptr(zero), zero.numel()
+    if PROFILE_PRE is not None:  # bench.py: x read (fp32) + prologue output written (fp16 / fp32), per row x channel
+        PROFILE_PRE.append((arr, n, sum(float(d.B) * d.T * d.C * (4 + (2 if d.out_f16 else 4)) for d in descs)))
+    _check(lib().f2g_block_pre_group(arr, n, stream()))
+
+
+def block_pre_replay(arr, n) -> None:
+    """Re-issue a recorded grouped prologue launch (bench.py HBM-roofline leg; the launch only reads
+    the residual stream and rewrites its own output, so replaying it is idempotent)."""
     _check(lib().f2g_block_pre_group(arr, n, stream()))
 
 
