@@ -1,0 +1,165 @@
+"""Offline model of the CTA-pair GEMM tile schedule (csrc/gemm_pair.cu::pick_bn / build_schedule):
+replays the host-side LPT assignment for a grouped / chained launch and simulates the per-pair
+timelines (tile cost = the kernel's own byte model: k-blocks x (256 + bn) + 8 x bn; a consumer tile
+starts only when every producer tile of its 256-row block is done), to compare N-tile choices
+before spending GPU time.  Usage: python tools/sched_sim.py"""
+from __future__ import annotations
+
+import heapq
+import itertools
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+PAIRS = 74
+
+
+@dataclass
+class Problem:
+    name: str
+    M: int
+    N: int
+    K: int
+    f16: bool = True
+    wait: Optional[int] = None     # index of the producer problem (chained consumer)
+    bn: int = 0
+
+
+def pick_bn(N: int, step: int = 32) -> int:
+    best, best_cost = 256, -1
+    for bn in range(256, step - 1, -step):
+        tiles = -(-N // bn)
+        cost = tiles * (256 + bn)
+        if best_cost < 0 or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+def tiles_of(p: Problem) -> Tuple[int, int, int, int]:
+    kelem = 64 if p.f16 else 32
+    kb = -(-p.K // kelem)
+    mt, nt = -(-p.M // 256), -(-p.N // p.bn)
+    return mt, nt, kb, kb * (256 + p.bn) + 8 * p.bn
+
+
+def simulate(problems: Sequence[Problem], pairs: int = PAIRS, fixed: float = 0.0):
+    """-> (makespan, ideal, per-phase info).  `fixed` = per-tile overhead in cost units."""
+    order = sorted(range(len(problems)), key=lambda i: (problems[i].wait is not None, -problems[i].K))
+    tiles = []        # (cost, phase, problem index, m tile)
+    for oi in order:
+        p = problems[oi]
+        mt, nt, kb, c = tiles_of(p)
+        for m in range(mt):
+            for n in range(nt):
+                tiles.append((c, int(p.wait is not None), oi, m))
+    # LPT: phase-0 tiles before phase-1 tiles, decreasing cost inside a phase, cumulative loads
+    idx = sorted(range(len(tiles)), key=lambda i: (tiles[i][1], -tiles[i][0], i))
+    heap = [(0, q) for q in range(pairs)]
+    heapq.heapify(heap)
+    lists: List[List[int]] = [[] for _ in range(pairs)]
+    for i in idx:
+        load, q = heapq.heappop(heap)
+        lists[q].append(i)
+        heapq.heappush(heap, (load + tiles[i][0], q))
+    # timeline with producer -> consumer row-tile dependencies
+    done_at = {}                                   # (problem, m) -> completion time of all its N tiles
+    remaining = {}
+    for c, ph, oi, m in tiles:
+        remaining[(oi, m)] = remaining.get((oi, m), 0) + 1
+    t = [0.0] * pairs
+    pos = [0] * pairs
+    finished_tiles = 0
+    total = len(tiles)
+    row_done = {}
+    while finished_tiles < total:
+        progressed = False
+        # advance the pair whose next tile can start earliest
+        best = None
+        for q in range(pairs):
+            if pos[q] >= len(lists[q]):
+                continue
+            c, ph, oi, m = tiles[lists[q][pos[q]]]
+            start = t[q]
+            w = problems[oi].wait
+            if w is not None:
+                key = (w, m)
+                if remaining.get(key, 0) > 0:
+                    continue                        # producer row block not finished yet
+                start = max(start, row_done[key])
+            if best is None or start < best[0]:
+                best = (start, q)
+        if best is None:
+            raise RuntimeError("deadlock in the simulated schedule")
+        start, q = best
+        c, ph, oi, m = tiles[lists[q][pos[q]]]
+        t[q] = start + c + fixed
+        pos[q] += 1
+        finished_tiles += 1
+        remaining[(oi, m)] -= 1
+        row_done[(oi, m)] = max(row_done.get((oi, m), 0.0), t[q])
+    total_cost = sum(x[0] + fixed for x in tiles)
+    return max(t), total_cost / pairs, len(tiles)
+
+
+def decoder_depth(bns: Optional[Sequence[int]] = None) -> List[Problem]:
+    """One chained pwconv1 -> pwconv2 launch of the three branches at the bench shape."""
+    rows, chans = (1520, 3024, 6032), (768, 512, 384)
+    ps = [Problem(f"pw1.b{i}", r, 3 * c, c) for i, (r, c) in enumerate(zip(rows, chans))]
+    ps += [Problem(f"pw2.b{i}", r, c, 3 * c, wait=i) for i, (r, c) in enumerate(zip(rows, chans))]
+    for i, p in enumerate(ps):
+        p.bn = bns[i] if bns else pick_bn(p.N)
+    return ps
+
+
+def main():
+    base = decoder_depth()
+    mk, ideal, n = simulate(base)
+    print("baseline bn", [p.bn for p in base], "tiles", n, "makespan %.0f ideal %.0f eff %.3f" % (mk, ideal, ideal / mk))
+    best = (mk, [p.bn for p in base])
+    cands = (128, 192, 256)          # (96 ... 256 in 32-column steps takes ~7 min and finds the same optimum)
+    results = []
+    for bns in itertools.product(cands, repeat=6):
+        ps = decoder_depth(bns)
+        m2, i2, n2 = simulate(ps)
+        results.append((m2, i2, n2, bns))
+    results.sort()
+    for m2, i2, n2, bns in results[:12]:
+        print("bn", bns, "tiles", n2, "makespan %.0f (%.1f%% vs baseline) ideal %.0f eff %.3f" %
+              (m2, 100 * (m2 / mk - 1), i2, i2 / m2))
+
+
+if __name__ == "__main__":
+    main()
+
+
+def lpt_makespan(problems: Sequence[Problem], pairs: int = PAIRS) -> float:
+    """Max pair load of the LPT assignment alone (what a host-side tuner can afford per launch)."""
+    order = sorted(range(len(problems)), key=lambda i: (problems[i].wait is not None, -problems[i].K))
+    costs = []
+    for oi in order:
+        p = problems[oi]
+        mt, nt, kb, c = tiles_of(p)
+        costs += [(int(p.wait is not None), c)] * (mt * nt)
+    costs.sort(key=lambda x: (x[0], -x[1]))
+    heap = [0] * pairs
+    heapq.heapify(heap)
+    for _, c in costs:
+        heapq.heappush(heap, heapq.heappop(heap) + c)
+    return float(max(heap))
+
+
+def tune_greedy(problems: List[Problem], pairs: int = PAIRS, floor: int = 96) -> List[int]:
+    """Coordinate descent over the N tiles (32-column steps down from the byte-optimal choice)
+    minimising the LPT makespan -- the rule proposed for gemm_pair.cu (F2G_PAIR_TUNE)."""
+    best = lpt_makespan(problems, pairs)
+    improved = True
+    while improved:
+        improved = False
+        for p in problems:
+            keep = p.bn
+            for bn in range(keep - 32, floor - 1, -32):
+                p.bn = bn
+                m = lpt_makespan(problems, pairs)
+                if m < best * 0.995:
+                    best, keep, improved = m, bn, True
+            p.bn = keep
+    return [p.bn for p in problems]
