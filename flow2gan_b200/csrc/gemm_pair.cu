@@ -857,7 +857,15 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   {
     static const int fill = getenv("F2G_PAIR_FILL") ? atoi(getenv("F2G_PAIR_FILL")) : 1;
     const int step = b_mn ? 64 : 32;
-    for (int oi = 0; oi < n; ++oi) bns[oi] = pick_bn(descs[order[oi]].N, b_mn != 0);
+    // F2G_PAIR_BN_HINT=1 (experiment, off by default): chained consumer problems take the caller's
+    // N tile (F2GGemm::bn) instead of the byte-optimal one -- narrower tiles for the problems the LPT
+    // schedule places last shorten the tail of the launch (tools/sched_sim.py: -5 % modelled).
+    static const int bn_hint = getenv("F2G_PAIR_BN_HINT") ? atoi(getenv("F2G_PAIR_BN_HINT")) : 0;
+    for (int oi = 0; oi < n; ++oi) {
+      const F2GGemm& d = descs[order[oi]];
+      bns[oi] = pick_bn(d.N, b_mn != 0);
+      if (bn_hint && d.wait_counter && d.bn >= 64 && d.bn <= 256 && d.bn % step == 0) bns[oi] = d.bn;
+    }
     for (int round = 0; fill && round < 3; ++round) {
       long tl = 0;
       for (int oi = 0; oi < n; ++oi) {

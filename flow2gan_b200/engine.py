@@ -162,8 +162,12 @@ def _g1(bw: _BlockW, a, h, M, bn=None, done=None):
                        act=L.ACT_PRELU, round_tf32=1)
 
 
+# F2G_PAIR_BN_HINT=1 (experiment): N tile of the chained pwconv2 problems by output width
+_TAIL_BN = {768: 256, 512: 192, 384: 128} if os.environ.get("F2G_PAIR_BN_HINT", "0") == "1" else {}
+
+
 def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0, wait=None):
-    bn = bn or BN_G2
+    bn = bn or (_TAIL_BN.get(bw.C) if wait is not None else None) or BN_G2
     b = bw.blk
     f16 = h.dtype == torch.float16        # h (fp16) x W2 (fp16) -> x (fp32 residual stream, in place)
     return L.gemm_desc(h.data_ptr(), (bw.half()[1] if f16 else bw.W2).data_ptr(), x.data_ptr(), M, bw.C,
