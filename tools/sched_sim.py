@@ -163,3 +163,66 @@ def tune_greedy(problems: List[Problem], pairs: int = PAIRS, floor: int = 96) ->
                     best, keep, improved = m, bn, True
             p.bn = keep
     return [p.bn for p in problems]
+
+
+def lpt_refined(problems: Sequence[Problem], pairs: int = PAIRS, iters: int = 4096):
+    """LPT followed by the move / swap refinement proposed for build_schedule (F2G_PAIR_REFINE):
+    repeatedly relieve the most loaded pair by moving one tile to, or swapping one tile with, the
+    least loaded pair.  Returns (makespan before, makespan after) of the LOADS only.  Negative
+    result kept for the record: on the chained decoder launch the loads improve 41 728 -> 36 864, but
+    the dependency-aware timeline of that assignment is 49 920 -- moving producer tiles unbalances the
+    producer phase and consumers stall on other pairs' producers.  Restricting the moves to consumer
+    tiles finds nothing; assigning consumer tiles first and filling with producer tiles gives 40 704
+    (-2.5 %).  What helps is narrower N tiles for the problems scheduled last (main())."""
+    order = sorted(range(len(problems)), key=lambda i: (problems[i].wait is not None, -problems[i].K))
+    costs = []
+    for oi in order:
+        p = problems[oi]
+        mt, nt, kb, c = tiles_of(p)
+        costs += [(int(p.wait is not None), c)] * (mt * nt)
+    costs.sort(key=lambda x: (x[0], -x[1]))
+    load = [0] * pairs
+    own = []
+    heap = [(0, q) for q in range(pairs)]
+    heapq.heapify(heap)
+    for _, c in costs:
+        l, q = heapq.heappop(heap)
+        own.append(q)
+        load[q] += c
+        heapq.heappush(heap, (l + c, q))
+    before = max(load)
+    for _ in range(iters):
+        hi = max(range(pairs), key=lambda q: load[q])
+        lo = min(range(pairs), key=lambda q: load[q])
+        gap = load[hi] - load[lo]
+        best = None                                   # (new pair max, tile on hi, tile on lo or None)
+        for i, q in enumerate(own):
+            if q != hi:
+                continue
+            c = costs[i][1]
+            if c < gap:                               # move
+                m = max(load[hi] - c, load[lo] + c)
+                if best is None or m < best[0]:
+                    best = (m, i, None)
+            for j, q2 in enumerate(own):              # swap
+                if q2 != lo:
+                    continue
+                d = c - costs[j][1]
+                if 0 < d < gap:
+                    m = max(load[hi] - d, load[lo] + d)
+                    if best is None or m < best[0]:
+                        best = (m, i, j)
+        if best is None or best[0] >= load[hi]:
+            break
+        _, i, j = best
+        c = costs[i][1]
+        if j is None:
+            own[i] = lo
+            load[hi] -= c
+            load[lo] += c
+        else:
+            d = c - costs[j][1]
+            own[i], own[j] = lo, hi
+            load[hi] -= d
+            load[lo] += d
+    return before, max(load)
