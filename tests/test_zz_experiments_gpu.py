@@ -1,0 +1,49 @@
+"""Opt-in experiment switches keep the results: each switch is read once per process (module import /
+first launch), so every arm runs in its own interpreter on the same seeded case and the outputs are
+compared here.  Named test_zz_* to run after the hot-path suites under `-x`."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from _cases import ROOT
+
+pytestmark = pytest.mark.gpu
+
+_ARM = r'''
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from _cases import mel_input, noise_input
+from _synth import synth_state_dict
+from flow2gan_b200 import get_generator_config
+from flow2gan_b200.generator import MelAudioGenerator
+torch.manual_seed(0)
+m = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+m.load_state_dict(synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 99), strict=False)
+m = m.cuda().eval()
+with torch.no_grad():
+    out = m.infer(mel_input(16, 100, 94, seed=0).cuda(), n_timesteps=2, noise=noise_input(16, 24064, seed=1).cuda())
+torch.save(out.cpu(), {out!r})
+'''
+
+
+def _run_arm(tmp_path, name, env):
+    out = str(tmp_path / f"{name}.pt")
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _ARM.format(root=ROOT, out=out)], env=e, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(out)
+
+
+def test_pair_bn_hint_keeps_inference_output(tmp_path):
+    """F2G_PAIR_BN_HINT=1 only changes the N-tile width of the chained pwconv2 problems: every output
+    element still accumulates its K products in the same order."""
+    base = _run_arm(tmp_path, "base", {"F2G_PAIR_BN_HINT": "0"})
+    hint = _run_arm(tmp_path, "hint", {"F2G_PAIR_BN_HINT": "1"})
+    assert torch.isfinite(base).all() and base.shape == (16, 24064)
+    rel = float((base - hint).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
+    assert rel < 1e-6, rel
