@@ -13,7 +13,7 @@ What is restructured relative to the reference (results stay equal, see DESIGN.m
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor

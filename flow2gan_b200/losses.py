@@ -5,8 +5,6 @@ triangular filters [+ safe_log]) as one fused kernel each way, and the reduction
 The scalar reductions over the (small) filterbank tensors are plain element-wise torch ops."""
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 from torch import Tensor
 

@@ -12,7 +12,7 @@ SIMT kernels from csrc/train.cu / csrc/spectral.cu.
 from __future__ import annotations
 
 import random
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 from torch import Tensor
