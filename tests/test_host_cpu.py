@@ -123,3 +123,51 @@ def test_checkpoint_files_interoperate_with_reference(tmp_path):
     MC.save_checkpoint(tmp_path / "keep.pt", m, model_avg=avg_keep, downcast_avg_in_place=False)
     assert next(avg_keep.parameters()).dtype == torch.float64
     assert torch.load(tmp_path / "keep.pt", weights_only=False)["model_avg"]["gain"].dtype == torch.float32
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/flow2gan"), reason="reference not mounted")
+def test_optimizer_host_logic_matches_reference_in_place():
+    """ScaledAdam's four accepted parameter forms (optim.py:340-445) yield the reference's param_groups /
+    parameters_names; Eden2 follows the reference's lr trajectory through warm-up and decay; the
+    scheduler state_dict round-trips.  Host logic only: no optimizer step is taken (that needs the GPU)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    import_reference()
+    import flow2gan.optim as RO
+    import flow2gan_b200.optim as MO
+    from make_golden_datapath import toy_model
+
+    def forms(m):
+        named = list(m.named_parameters())
+        half = len(named) // 2
+        return [
+            [p for _, p in named],
+            named,
+            [{"params": [p for _, p in named[:half]], "lr": 0.01}, {"params": [p for _, p in named[half:]]}],
+            [{"named_params": named[:half], "lr": 0.01}, {"named_params": named[half:], "lr": 0.002}],
+        ]
+
+    for fa, fb in zip(forms(toy_model()), forms(toy_model())):
+        a = RO.ScaledAdam(fa, lr=0.045, clipping_scale=2.0)
+        b = MO.ScaledAdam(fb, lr=0.045, clipping_scale=2.0)
+        assert a.parameters_names == b.parameters_names
+        assert a.show_dominant_parameters == b.show_dominant_parameters
+        assert len(a.param_groups) == len(b.param_groups)
+        for ga, gb in zip(a.param_groups, b.param_groups):
+            assert [tuple(p.shape) for p in ga["params"]] == [tuple(p.shape) for p in gb["params"]]
+            for k in ga:
+                if k != "params":
+                    assert ga[k] == gb[k], k
+        sa = RO.Eden2(a, lr_batches=50, warmup_batches=20, warmup_start=0.1)
+        sb = MO.Eden2(b, lr_batches=50, warmup_batches=20, warmup_start=0.1)
+        for step in list(range(1, 30)) + [100, 1000]:
+            sa.step_batch(step)
+            sb.step_batch(step)
+            assert sa.get_last_lr() == sb.get_last_lr(), step
+            assert [g["lr"] for g in a.param_groups] == [g["lr"] for g in b.param_groups]
+        sb2 = MO.Eden2(MO.ScaledAdam(forms(toy_model())[1], lr=0.045), lr_batches=50, warmup_batches=20)
+        sb2.load_state_dict(sa.state_dict())
+        assert sb2.batch == 1000 and sb2.state_dict() == sb.state_dict()
+    with pytest.raises(ValueError):
+        MO.ScaledAdam([], lr=0.1)
