@@ -171,3 +171,43 @@ def test_optimizer_host_logic_matches_reference_in_place():
         assert sb2.batch == 1000 and sb2.state_dict() == sb.state_dict()
     with pytest.raises(ValueError):
         MO.ScaledAdam([], lr=0.1)
+
+
+def test_gan_state_dict_layout_matches_reference_spec():
+    """GAN(generator, ...) rebuilds the reference's module tree: same 666 state_dict keys and shapes as
+    the reference GAN the golden file was generated from (checkpoints load with strict=False, so a
+    silent key mismatch would just skip weights)."""
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.gan import GAN
+    from flow2gan_b200.generator import MelAudioGenerator
+    g = torch.load(os.path.join(GOLDEN, "ref_gan_24k.pt"), weights_only=False)
+    gan = GAN(MelAudioGenerator(**get_generator_config("mel_24k_base")), **get_gan_config("gan_multi_scale_mel_recon"))
+    mine = [(k, tuple(v.shape)) for k, v in gan.state_dict().items()]
+    assert mine == [(k, tuple(s)) for k, s in g["sd_spec"]]
+    n_gen = sum(p.numel() for p in gan.generator.parameters())
+    n_disc = sum(p.numel() for p in gan.discriminator.parameters())
+    assert (n_gen, n_disc) == (78949542, 42503752)              # SURVEY.md section 8(e)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/flow2gan"), reason="reference not mounted")
+def test_configs_and_filterbanks_match_reference_in_place():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    import_reference()
+    import flow2gan.models.config as RC
+    import flow2gan_b200.config as MC
+    for name in ("mel_24k_base", "mel_44k_128band_512x_base"):
+        assert dict(RC.get_generator_config(name)) == dict(MC.get_generator_config(name)), name
+    assert dict(RC.get_gan_config("gan_multi_scale_mel_recon")) == dict(MC.get_gan_config("gan_multi_scale_mel_recon"))
+    assert RC.HF_MODEL_NAMES == MC.HF_MODEL_NAMES and RC.HF_REPO == MC.HF_REPO
+    for bad in ("nope", ""):
+        with pytest.raises(ValueError):
+            MC.get_generator_config(bad)
+    import torchaudio
+    from flow2gan_b200.modules import linear_fbanks, melscale_fbanks
+    for n_fft, n_mels in zip((32, 64, 128, 256, 512, 1024, 2048), (5, 10, 20, 40, 80, 160, 320)):
+        ref = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, 12000.0, n_mels, 24000, norm=None, mel_scale="htk")
+        assert torch.equal(melscale_fbanks(n_fft // 2 + 1, n_mels, 24000), ref), n_fft
+    ref = torchaudio.functional.linear_fbanks(513, 0.0, 12000.0, 256, 24000)
+    assert torch.equal(linear_fbanks(513, 256, 24000), ref)
