@@ -211,3 +211,23 @@ def test_configs_and_filterbanks_match_reference_in_place():
         assert torch.equal(melscale_fbanks(n_fft // 2 + 1, n_mels, 24000), ref), n_fft
     ref = torchaudio.functional.linear_fbanks(513, 0.0, 12000.0, 256, 24000)
     assert torch.equal(linear_fbanks(513, 256, 24000), ref)
+
+
+def test_branch_dropout_draws_follow_reference_order():
+    """generator.py:145-162: randint (branch to drop) then rand (apply with prob. p), mask rescaled by
+    nb / (nb - 1); ours additionally folds the branch mean (1 / nb) into the weights."""
+    from types import SimpleNamespace
+    from flow2gan_b200.train import _branch_dropout_weight
+    m = SimpleNamespace(num_branches=3, training=True, branch_dropout=0.5)
+    torch.manual_seed(11)
+    w = _branch_dropout_weight(m, 64, torch.device("cpu"))
+    torch.manual_seed(11)
+    idx = torch.randint(0, 3, (64,))
+    mask = torch.ones(64, 3)
+    mask[torch.arange(64), idx] = 0.0
+    mask = mask * (3 / 2)
+    want = torch.where(torch.rand(64, 1) < 0.5, mask, torch.ones_like(mask))
+    assert torch.equal(w, want / 3)
+    assert 10 < int((w == 0).sum()) < 54 and torch.allclose(w.sum(1), torch.ones(64))
+    m.training = False
+    assert _branch_dropout_weight(m, 64, torch.device("cpu")) is None
