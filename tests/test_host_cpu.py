@@ -231,3 +231,30 @@ def test_branch_dropout_draws_follow_reference_order():
     assert 10 < int((w == 0).sum()) < 54 and torch.allclose(w.sum(1), torch.ones(64))
     m.training = False
     assert _branch_dropout_weight(m, 64, torch.device("cpu")) is None
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/flow2gan"), reason="reference not mounted")
+def test_limit_param_value_flip_matches_reference_in_place():
+    """train._limit_flip / _limit_apply == LimitParamValue.backward (modules.py:236-256) on random
+    gradients with parameters below, inside and above the range; the graph-mode device flag gives the
+    same result as the eager Python flag."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    import_reference()
+    from flow2gan.models.modules import LimitParamValue
+    from flow2gan_b200.train import _limit_apply, _limit_flip
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(4000, generator=g) * 1.5)
+    grad = torch.randn(4000, generator=g)
+    grad[::7] = 0.0
+    for lo, hi in ((0.5, 1.0), (-1.5, 1.5)):
+        xr = x.clone().requires_grad_(True)
+        LimitParamValue.apply(xr, lo, hi).backward(grad.clone())
+        got = _limit_flip(grad.clone(), x, lo, hi)
+        assert torch.equal(got, xr.grad)
+        assert torch.equal(_limit_apply(True, grad, x, lo, hi), got)
+        assert torch.equal(_limit_apply(False, grad, x, lo, hi), grad)
+        assert torch.equal(_limit_apply(torch.tensor(1.0), grad, x, lo, hi), got)
+        assert torch.equal(_limit_apply(torch.tensor(0.0), grad, x, lo, hi), grad)
+        assert int((got != grad).sum()) > 100
