@@ -275,3 +275,99 @@ def save_wav(path: str, audio: Tensor, sampling_rate: int, clamp: bool = True) -
     with open(path, "wb") as f:
         f.write(wav_header_pcm16(pcm.numel(), sampling_rate))
         f.write(pcm.numpy().tobytes())
+
+
+# ---------------------------------------------------------------------------------------------
+# dataset-shaped front (flow2gan/dataset.py:31-46,96-175) over plain wav paths
+# ---------------------------------------------------------------------------------------------
+class RecordingDataset:
+    """`LhotseRecordingDataset` without lhotse: items are wav paths (or bytes).  `__getitem__` returns
+    `(audio (T,) fp32 on the device at `sampling_rate`, silence flag, file name)` with the reference's
+    segment policy -- whole file when `duration` is None, the first `duration` seconds in validation,
+    a uniformly drawn segment in training, redrawn up to `max_load_times` while it is silent -- and
+    its effects: sox `norm` at -3 dB (validation) or U(-1, -6) dB (training), then resampling.  The
+    random draws come from numpy's global generator in the reference's order (offset(s), then gain)."""
+
+    def __init__(self, recordings: Sequence[Union[str, bytes]], sampling_rate: int = 24000,
+                 root_path: Optional[str] = None, train: bool = False, duration: Optional[float] = None,
+                 apply_effects: bool = True, max_load_times: int = 1, min_rms: float = 0.005,
+                 device: Union[str, torch.device] = "cuda"):
+        self.recordings = list(recordings)
+        self.sampling_rate = sampling_rate
+        self.root_path = root_path
+        self.train = train
+        self.duration = duration
+        self.apply_effects = apply_effects
+        self.max_load_times = max_load_times
+        self.min_rms = min_rms
+        self.device = torch.device(device)
+
+    def __len__(self) -> int:
+        return len(self.recordings)
+
+    def _name(self, src) -> str:
+        import os
+        if not isinstance(src, str):
+            return "<bytes>"
+        return os.path.relpath(src, self.root_path) if self.root_path is not None else src
+
+    def __getitem__(self, index: int) -> Tuple[Tensor, Tensor, str]:
+        import numpy as np
+        src = self.recordings[index]
+        if isinstance(src, str):
+            with open(src, "rb") as f:
+                src_bytes = f.read()
+        else:
+            src_bytes = bytes(src)
+        info = parse_wav_header(src_bytes)
+        offsets = [0.0]
+        duration = None
+        if self.duration is not None:
+            duration = min(self.duration, info.duration)
+            if self.train:
+                offsets = []            # drawn lazily: one np.random.uniform per attempt (dataset.py:146-152)
+        seg = mono = stats = silence = None
+        attempts = 1 if not (self.train and self.duration is not None) else max(1, self.max_load_times)
+        for k in range(attempts):
+            off = offsets[k] if offsets else float(np.random.uniform(0, info.duration - duration))
+            seg = _open_segment(src_bytes, None, off, duration)
+            mono, silence, stats = _decode_only(seg, self.min_rms, self.device)
+            if k + 1 < attempts and not bool(silence):          # host decision only when a redraw is possible
+                break
+        y = mono
+        gain_db = None
+        if self.apply_effects:
+            gain_db = float(f"{np.random.uniform(-1, -6):.2f}") if self.train else -3.0    # dataset.py:165-167
+        if gain_db is not None or info.sampling_rate != self.sampling_rate:
+            y = gain_resample(mono, info.sampling_rate, self.sampling_rate, stats, gain_db)
+        return y, silence, self._name(self.recordings[index])
+
+
+def _decode_only(seg: _Segment, min_rms: float, dev: torch.device) -> Tuple[Tensor, Tensor, Tensor]:
+    info, n = seg.info, seg.n
+    if n == 0:
+        z = torch.zeros(2, device=dev)
+        return torch.empty(0, device=dev), torch.ones((), device=dev, dtype=torch.bool), z
+    fb = info.bytes_per_sample * info.channels
+    lo = info.data_offset + seg.first * fb
+    host = torch.frombuffer(bytearray(seg.buf[lo: lo + n * fb]), dtype=torch.uint8)
+    payload = host.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else host
+    mono, stats = decode_segment(payload, info, 0, n)
+    return mono, torch.sqrt(stats[0] / n) < min_rms, stats
+
+
+def pad_seq_collate_fn(data, filter_silence: bool = True) -> Tuple[Tensor, Tensor, List[str]]:
+    """dataset.py:31-46 on device items: drop silent items (keep the first if all are), zero-pad to the
+    longest, int32 lengths, file names."""
+    if filter_silence and data:
+        flags = torch.stack([torch.as_tensor(x[1]).reshape(()).to(data[0][0].device) for x in data]).cpu().tolist()
+        kept = [x for x, f in zip(data, flags) if not f] or list(data[0:1])
+    else:
+        kept = list(data)
+    dev = kept[0][0].device
+    tmax = max(x[0].numel() for x in kept)
+    audios = torch.zeros(len(kept), tmax, device=dev, dtype=torch.float32)
+    for r, x in enumerate(kept):
+        audios[r, : x[0].numel()].copy_(x[0])
+    lens = torch.tensor([x[0].numel() for x in kept], dtype=torch.int32)
+    return audios, lens, [x[2] for x in kept]

@@ -313,6 +313,12 @@ def test_host_layer_dry_run_collate_and_save(emulated_lib, tmp_path):
 
 
 @needs_gxx
+def test_host_layer_dry_run_recording_dataset(emulated_lib, tmp_path):
+    import _datapath_cases as DC
+    DC.case_recording_dataset("cpu", tmp_path)
+
+
+@needs_gxx
 @pytest.mark.parametrize("tag", AVG_TAGS)
 def test_host_layer_dry_run_average_state_dict(emulated_lib, tag):
     import _datapath_cases as DC

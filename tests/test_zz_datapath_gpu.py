@@ -38,6 +38,10 @@ def test_norm_gain_resample_and_collate():
     DC.case_norm_resample_collate("cuda")
 
 
+def test_recording_dataset_policy(tmp_path):
+    DC.case_recording_dataset("cuda", tmp_path)
+
+
 def test_pcm16_encode_and_save_wav_round_trip(tmp_path):
     DC.case_encode_save_round_trip("cuda", tmp_path)
 
