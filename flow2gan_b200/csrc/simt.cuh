@@ -61,6 +61,13 @@ inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 #define F2G_GRID_CONSTANT
 #define __restrict__ __restrict
 
+// -DF2G_EMUL_REVERSE runs blocks and threads in descending order: results must not depend on it
+#ifdef F2G_EMUL_REVERSE
+#define F2G_EMUL_ORDER(i, n) ((n) - 1u - (i))
+#else
+#define F2G_EMUL_ORDER(i, n) (i)
+#endif
+
 typedef void* cudaStream_t;
 struct f2g_dim3 {
   unsigned x, y, z;
@@ -74,8 +81,8 @@ static f2g_dim3 threadIdx, blockIdx, blockDim, gridDim;
     blockDim = {(unsigned)(block), 1, 1};                                       \
     for (unsigned b_ = 0; b_ < gridDim.x; ++b_)                                 \
       for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                            \
-        blockIdx = {b_, 0, 0};                                                  \
-        threadIdx = {t_, 0, 0};                                                 \
+        blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                       \
+        threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                     \
         kernel(__VA_ARGS__);                                                    \
       }                                                                         \
   } while (0)

@@ -17,6 +17,7 @@ CSRC = os.path.join(ROOT, "flow2gan_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_build")
 
 _lib = None
+REVERSE = os.environ.get("F2G_EMUL_REVERSE", "0") == "1"      # run blocks / threads in descending order
 
 
 class AvgTensor(C.Structure):
@@ -37,10 +38,10 @@ def lib() -> C.CDLL:
         for s in srcs:
             h.update(open(s, "rb").read())
         os.makedirs(OUT, exist_ok=True)
-        so = os.path.join(OUT, f"libf2g_datapath_emul_{h.hexdigest()[:12]}.so")
+        so = os.path.join(OUT, f"libf2g_emul_{h.hexdigest()[:12]}{'_rev' if REVERSE else ''}.so")
         if not os.path.exists(so):
             subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2G_HOST_EMUL",
-                                   "-shared", "-fPIC", *cus, "-o", so])
+                                   *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", *cus, "-o", so])
         l = C.CDLL(so)
         vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
         l.f2g_pcm_decode.argtypes = [vp, i, i, ll, ll, vp, vp, vp]

@@ -2,6 +2,9 @@
 same source (tests/_emul.py) behind the product's autograd wrappers (flow2gan_b200/losses.py,
 gan.py), against torch autograd of the reference's expressions (flow2gan/models/gan.py:57-99)."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import pytest
 import torch
@@ -60,3 +63,16 @@ def test_no_cpu_fallback():
     from flow2gan_b200.losses import hinge_terms
     with pytest.raises((RuntimeError, AssertionError)):
         hinge_terms([torch.zeros(3)], [1.0])
+
+
+@pytest.mark.skipif(os.environ.get("F2G_EMUL_REVERSE") == "1", reason="already the reversed run")
+def test_emulated_kernels_do_not_depend_on_thread_order():
+    """The host emulation runs blocks and threads sequentially; a kernel that silently relied on that
+    order would still be wrong on the GPU.  Re-run both emulated suites with blocks / threads in
+    DESCENDING order (-DF2G_EMUL_REVERSE)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, F2G_EMUL_REVERSE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_datapath_cpu.py"), os.path.join(here, "test_losses_cpu.py")],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
