@@ -9,7 +9,7 @@
 //   2. scalars: one CTA -- grad-norm, clip factor, scale_grads / param_rms / size-step logic
 //   3. update : exp_avg_sq EMA, -lr*g/(sqrt(v)+eps) * rms, + p*scale_step, momentum, p += delta
 //               (HBM: read p, g, v, d; write p, v, d -> 28 B/param, pure streaming)
-#include "common.cuh"
+#include "simt.cuh"
 #include "../../include/flow2gan_b200.h"
 
 namespace f2g {
@@ -17,7 +17,7 @@ namespace f2g {
 constexpr int CHUNK = 4096;        // elements per CTA pass
 constexpr int OPT_THREADS = 256;
 
-__global__ void adam_reduce_kernel(const F2GAdamTensor* __restrict__ tab, const int2* __restrict__ chunks,
+F2G_KERNEL void adam_reduce_kernel(const F2GAdamTensor* __restrict__ tab, const int2* __restrict__ chunks,
                                    float* __restrict__ acc /* [n_tensors][3] */) {
   const int2 ck = chunks[blockIdx.x];
   const F2GAdamTensor t = tab[ck.x];
@@ -45,7 +45,7 @@ __global__ void adam_reduce_kernel(const F2GAdamTensor* __restrict__ tab, const 
 
 // state scalars per tensor: [0]=param_rms [1]=scale_exp_avg_sq [2..5]=scale_grads[0..3] [6]=scale_step
 // group scalars: [0]=tot_norm (out) [1]=clip (out) [2]=threshold (<0: unset)
-__global__ void adam_norm_kernel(const F2GAdamTensor* __restrict__ tab, int n, const float* __restrict__ acc,
+F2G_KERNEL void adam_norm_kernel(const F2GAdamTensor* __restrict__ tab, int n, const float* __restrict__ acc,
                                  float* __restrict__ ts, float* __restrict__ gs, int step,
                                  float scalar_lr_scale, float* __restrict__ model_norms, int period) {
   __shared__ float red[OPT_THREADS / 32];
@@ -75,7 +75,7 @@ __global__ void adam_norm_kernel(const F2GAdamTensor* __restrict__ tab, int n, c
   }
 }
 
-__global__ void adam_scalars_kernel(const F2GAdamTensor* __restrict__ tab, int n, const float* __restrict__ acc,
+F2G_KERNEL void adam_scalars_kernel(const F2GAdamTensor* __restrict__ tab, int n, const float* __restrict__ acc,
                                     float* __restrict__ ts, float* __restrict__ gs, int step,
                                     int use_clip, float lr, float scalar_lr_scale, float beta2,
                                     float eps, float min_rms, float max_rms, int size_period) {
@@ -114,7 +114,7 @@ __global__ void adam_scalars_kernel(const F2GAdamTensor* __restrict__ tab, int n
   }
 }
 
-__global__ void adam_update_kernel(const F2GAdamTensor* __restrict__ tab, const int2* __restrict__ chunks,
+F2G_KERNEL void adam_update_kernel(const F2GAdamTensor* __restrict__ tab, const int2* __restrict__ chunks,
                                    const float* __restrict__ ts, const float* __restrict__ gs, int step,
                                    float lr, float scalar_lr_scale, float beta1, float beta2, float eps,
                                    float min_rms, float scalar_max) {
@@ -162,19 +162,18 @@ extern "C" int f2g_scaled_adam_step(const F2GAdamTensor* tab_dev, int n_tensors,
   }
   const int2* chunks = reinterpret_cast<const int2*>(chunks_dev);
   if (phase == 0) {         // reductions + gradient norm (host may then refresh the threshold)
-    cudaMemsetAsync(acc_dev, 0, sizeof(float) * 3 * (size_t)n_tensors, stream);
-    adam_reduce_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(tab_dev, chunks, acc_dev);
-    adam_norm_kernel<<<1, OPT_THREADS, 0, stream>>>(tab_dev, n_tensors, acc_dev, tensor_state_dev,
-                                                    group_state_dev, step, h->scalar_lr_scale,
-                                                    model_norms_dev, h->clipping_update_period);
+    if (int rc = simt_memset_async(acc_dev, 0, sizeof(float) * 3 * (size_t)n_tensors, stream)) return rc;
+    F2G_LAUNCH_COOP(adam_reduce_kernel, n_chunks, OPT_THREADS, stream, tab_dev, chunks, acc_dev);
+    F2G_LAUNCH_COOP(adam_norm_kernel, 1, OPT_THREADS, stream, tab_dev, n_tensors, acc_dev, tensor_state_dev,
+                    group_state_dev, step, h->scalar_lr_scale, model_norms_dev, h->clipping_update_period);
     return check_launch("f2g_scaled_adam_step(reduce)");
   }
   const int sb = (n_tensors + OPT_THREADS - 1) / OPT_THREADS;
-  adam_scalars_kernel<<<sb, OPT_THREADS, 0, stream>>>(
-      tab_dev, n_tensors, acc_dev, tensor_state_dev, group_state_dev, step, h->use_clipping, h->lr,
-      h->scalar_lr_scale, h->beta2, h->eps, h->param_min_rms, h->param_max_rms, h->size_update_period);
-  adam_update_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(
-      tab_dev, chunks, tensor_state_dev, group_state_dev, step, h->lr, h->scalar_lr_scale, h->beta1,
-      h->beta2, h->eps, h->param_min_rms, h->scalar_max);
+  F2G_LAUNCH_COOP(adam_scalars_kernel, sb, OPT_THREADS, stream, tab_dev, n_tensors, acc_dev, tensor_state_dev,
+                  group_state_dev, step, h->use_clipping, h->lr, h->scalar_lr_scale, h->beta2, h->eps,
+                  h->param_min_rms, h->param_max_rms, h->size_update_period);
+  F2G_LAUNCH_COOP(adam_update_kernel, n_chunks, OPT_THREADS, stream, tab_dev, chunks, tensor_state_dev,
+                  group_state_dev, step, h->lr, h->scalar_lr_scale, h->beta1, h->beta2, h->eps, h->param_min_rms,
+                  h->scalar_max);
   return check_launch("f2g_scaled_adam_step(update)");
 }

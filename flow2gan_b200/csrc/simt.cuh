@@ -20,6 +20,7 @@
 #define F2G_SIMT_DEV __device__ __forceinline__
 #define F2G_GRID_CONSTANT __grid_constant__
 #define F2G_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 
 namespace f2g {
 // per-thread partials -> one atomic per warp (the kernels using these are HBM streams; a few
@@ -68,11 +69,22 @@ inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 #define F2G_EMUL_ORDER(i, n) (i)
 #endif
 
+#include <pthread.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
+
 typedef void* cudaStream_t;
 struct f2g_dim3 {
   unsigned x, y, z;
 };
-static f2g_dim3 threadIdx, blockIdx, blockDim, gridDim;
+struct int2 {
+  int x, y;
+};
+static thread_local f2g_dim3 threadIdx, blockIdx;
+static f2g_dim3 blockDim, gridDim;
+#define __shared__ static      /* blocks run one after the other: one copy per kernel is "per block" */
 
 #define F2G_LAUNCH(kernel, grid, block, stream, ...)                            \
   do {                                                                          \
@@ -87,6 +99,59 @@ static f2g_dim3 threadIdx, blockIdx, blockDim, gridDim;
       }                                                                         \
   } while (0)
 
+// Cooperative kernels (shared memory, __syncthreads, warp shuffles, atomics): one host thread per
+// CUDA thread of a block, blocks one after the other.  Used by tests for small problems only.
+namespace f2g {
+inline pthread_barrier_t g_block_bar;
+inline pthread_barrier_t g_warp_bar[32];
+inline float g_shfl[32][32];
+inline std::mutex g_atomic_mu;
+inline void emul_coop_begin(unsigned block) {
+  pthread_barrier_init(&g_block_bar, nullptr, block);
+  for (unsigned w = 0; w < (block + 31) / 32; ++w) {
+    const unsigned lanes = block - 32 * w < 32 ? block - 32 * w : 32;
+    pthread_barrier_init(&g_warp_bar[w], nullptr, lanes);
+  }
+}
+inline void emul_coop_end(unsigned block) {
+  pthread_barrier_destroy(&g_block_bar);
+  for (unsigned w = 0; w < (block + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_bar[w]);
+}
+}  // namespace f2g
+static inline void __syncthreads() { pthread_barrier_wait(&f2g::g_block_bar); }
+static inline float __shfl_xor_sync(unsigned, float v, int o) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  f2g::g_shfl[w][l] = v;
+  pthread_barrier_wait(&f2g::g_warp_bar[w]);
+  const float r = f2g::g_shfl[w][l ^ (unsigned)o];
+  pthread_barrier_wait(&f2g::g_warp_bar[w]);
+  return r;
+}
+static inline float atomicAdd(float* p, float v) {
+  std::lock_guard<std::mutex> lk(f2g::g_atomic_mu);
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
+#define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                  \
+  do {                                                                                     \
+    (void)(stream);                                                                        \
+    gridDim = {(unsigned)(grid), 1, 1};                                                    \
+    blockDim = {(unsigned)(block), 1, 1};                                                  \
+    f2g::emul_coop_begin(blockDim.x);                                                      \
+    for (unsigned b_ = 0; b_ < gridDim.x; ++b_) {                                          \
+      std::vector<std::thread> th_;                                                        \
+      for (unsigned t_ = 0; t_ < blockDim.x; ++t_)                                         \
+        th_.emplace_back([&, b_, t_]() {                                                   \
+          blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                                \
+          threadIdx = {t_, 0, 0};                                                          \
+          kernel(__VA_ARGS__);                                                             \
+        });                                                                                \
+      for (auto& x_ : th_) x_.join();                                                      \
+    }                                                                                      \
+    f2g::emul_coop_end(blockDim.x);                                                        \
+  } while (0)
+
 namespace f2g {
 enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
 inline char g_emul_err[512];       // one buffer for every translation unit of the emulated library
@@ -97,6 +162,10 @@ static inline void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static inline int check_launch(const char*) { return 0; }
+F2G_SIMT_DEV float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 // the compiler flags of the emulated build forbid contraction (-ffp-contract=off)
 F2G_SIMT_DEV void simt_block_sum(float v, float* dst) { *dst += v; }
 F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {

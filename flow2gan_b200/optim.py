@@ -137,9 +137,9 @@ class ScaledAdam(Optimizer):
         if self._gs[gi] is None:
             g = self.param_groups[gi]
             for p in g["params"]:
-                if not (p.is_cuda and p.dtype == torch.float32):
-                    raise RuntimeError("flow2gan_b200.ScaledAdam runs on CUDA fp32 parameters only "
-                                       "(fused sm_100a kernels, no CPU fallback)")
+                L.require_cuda(p, "ScaledAdam parameter (fused sm_100a kernels)")
+                if p.dtype != torch.float32:
+                    raise RuntimeError("flow2gan_b200.ScaledAdam runs on fp32 parameters only")
             self._gs[gi] = _Group(list(g["params"]), self.parameters_names[gi],
                                   g["size_update_period"], g["clipping_update_period"])
         return self._gs[gi]

@@ -1,6 +1,7 @@
-"""Host emulation of the thread-independent SIMT kernels (csrc/datapath.cu written against
-csrc/simt.cuh): the SAME source is compiled with g++ -DF2G_HOST_EMUL so its index arithmetic and
-rounding can be checked on a box without a GPU.  Test infrastructure only; the product library
+"""Host emulation of the SIMT kernels written against csrc/simt.cuh (datapath.cu, losses.cu: thread-
+independent, run as sequential loops; optim.cu: cooperative -- shared memory, __syncthreads, warp
+shuffles, atomics -- run with one host thread per CUDA thread of a block): the SAME source is compiled
+with g++ -DF2G_HOST_EMUL so its index arithmetic and rounding can be checked on a box without a GPU.  Test infrastructure only; the product library
 never contains this build and flow2gan_b200/_lib.py never loads it."""
 from __future__ import annotations
 
@@ -32,7 +33,7 @@ def available() -> bool:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu")]
+        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu")]
         srcs = cus + [os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
         h = hashlib.sha256()
         for s in srcs:
@@ -41,7 +42,8 @@ def lib() -> C.CDLL:
         so = os.path.join(OUT, f"libf2g_emul_{h.hexdigest()[:12]}{'_rev' if REVERSE else ''}.so")
         if not os.path.exists(so):
             subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2G_HOST_EMUL",
-                                   *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", *cus, "-o", so])
+                                   *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", "-pthread", *cus,
+                                   "-o", so])
         l = C.CDLL(so)
         vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
         l.f2g_pcm_decode.argtypes = [vp, i, i, ll, ll, vp, vp, vp]
@@ -49,6 +51,7 @@ def lib() -> C.CDLL:
         l.f2g_pcm16_encode.argtypes = [vp, ll, i, vp, vp]
         l.f2g_average_update.argtypes = [vp, vp, i, d, d, d, vp]
         l.f2g_loss_terms.argtypes = [vp, i, i, vp, vp, vp]
+        l.f2g_scaled_adam_step.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, i, vp, vp]
         _lib = l
     return _lib
 

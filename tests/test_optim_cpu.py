@@ -1,0 +1,110 @@
+"""ScaledAdam on the CPU: the kernels of csrc/optim.cu compiled for the host from the same source
+(cooperative emulation: one host thread per CUDA thread, tests/_emul.py) behind the product's
+optimizer class, against the reference's own 45-step optimizer run (tests/golden/ref_scaled_adam.pt)
+and the CPU oracle.  Same cases as tests/test_optim_gpu.py."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+import _emul
+from _cases import GOLDEN, rel_rms
+from oracle import flow2gan_oracle as O
+
+pytestmark = pytest.mark.skipif(not _emul.available(), reason="g++ not available")
+
+
+@pytest.fixture
+def emulated_adam(monkeypatch):
+    from flow2gan_b200 import _lib as L
+    e = _emul.lib()
+
+    def p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def step(tab, n_tensors, chunks, n_chunks, acc, tstate, gstate, norms, step_, phase, hyper):
+        rc = e.f2g_scaled_adam_step(p(tab), n_tensors, p(chunks), n_chunks, p(acc), p(tstate), p(gstate), p(norms),
+                                    step_, phase, C.cast(C.byref(hyper), C.c_void_p), None)
+        if rc != 0:
+            raise RuntimeError("flow2gan_b200 native call failed (rc=%d): %s" % (rc, _emul.last_error()))
+
+    monkeypatch.setattr(L, "require_cuda", lambda t, what: None)
+    monkeypatch.setattr(L, "scaled_adam_step", step)
+    return L
+
+
+def _run(g, upto=None, resume_at=None):
+    from flow2gan_b200.optim import Eden2, ScaledAdam
+    h = g["hyper"]
+    names = [n for n, _ in g["shapes"]]
+    params = [torch.nn.Parameter(p.clone()) for p in g["init"]]
+
+    def make(ps):
+        opt = ScaledAdam(list(zip(names, ps)), lr=h["lr"], clipping_scale=h["clipping_scale"])
+        return opt, Eden2(opt, lr_batches=h["lr_batches"], warmup_batches=h["warmup_batches"],
+                          warmup_start=h["warmup_start"])
+    opt, sched = make(params)
+    lrs = []
+    for step, gs in enumerate(g["grads"][:upto]):
+        if resume_at is not None and step == resume_at:
+            sd, ssd = opt.state_dict(), sched.state_dict()
+            params = [torch.nn.Parameter(p.detach().clone()) for p in params]
+            opt, sched = make(params)
+            opt.load_state_dict(sd)
+            sched.load_state_dict(ssd)
+            sched._set_lrs()
+        for p, gr in zip(params, gs):
+            p.grad = None if gr is None else gr.clone()
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sched.step_batch()
+    return params, lrs, opt
+
+
+def test_scaled_adam_matches_reference_run(emulated_adam):
+    g = torch.load(os.path.join(GOLDEN, "ref_scaled_adam.pt"), weights_only=False)
+    params, lrs, opt = _run(g)
+    assert max(abs(a - b) for a, b in zip(lrs, g["lrs"])) < 1e-12
+    for p, ref, (n, _) in zip(params, g["final"], g["shapes"]):
+        assert rel_rms(p.detach(), ref) < 2e-5, n
+    st = opt.state_dict()["state"]
+    assert any("model_norms" in v for v in st.values())
+    assert all(set(v) >= {"step", "exp_avg_sq", "delta"} for v in st.values())
+
+
+def test_scaled_adam_checkpoint_resume_is_transparent(emulated_adam):
+    g = torch.load(os.path.join(GOLDEN, "ref_scaled_adam.pt"), weights_only=False)
+    a, _, _ = _run(g, upto=30)
+    b, _, _ = _run(g, upto=30, resume_at=17)
+    for x, y in zip(a, b):
+        assert rel_rms(x.detach(), y.detach()) < 1e-6
+
+
+def test_scaled_adam_many_tensors_vs_oracle(emulated_adam):
+    from flow2gan_b200.optim import ScaledAdam
+    gen = torch.Generator().manual_seed(11)
+    shapes = [(64, 33, 3)] * 2 + [(257,)] * 4 + [()] * 5 + [(300, 1)] * 2 + [(5000, 3)]
+    names = [f"p{i}" for i in range(len(shapes))]
+    init = [torch.randn(s, generator=gen) * 0.2 for s in shapes]
+    cpu = [p.clone() for p in init]
+    mine = [torch.nn.Parameter(p.clone()) for p in init]
+    ora = O.ScaledAdamOracle(names, cpu, lr=0.01, clipping_scale=2.0)
+    opt = ScaledAdam(list(zip(names, mine)), lr=0.01, clipping_scale=2.0)
+    for step in range(14):
+        gs = [torch.randn(s, generator=gen) * (8.0 if step == 11 else 1.0) for s in shapes]
+        ora.step(cpu, gs)
+        for p, gr in zip(mine, gs):
+            p.grad = gr
+        opt.step()
+    for a, b, n in zip(mine, cpu, names):
+        assert rel_rms(a.detach(), b) < 2e-5, n
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less box")
+def test_no_cpu_fallback():
+    from flow2gan_b200.optim import ScaledAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA"):
+        ScaledAdam([("p", p)], lr=0.1).step()
