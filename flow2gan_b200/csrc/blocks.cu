@@ -2,7 +2,7 @@
 // small dense layers, sinusoidal time embedding, packing helpers.  All HBM/L2-bound.
 // Reference: flow2gan/models/modules.py:217-232 (SinusoidalPosEmb), :286-416 (BiasNorm),
 // :456-495 (ConvNeXtBlock.forward), :523-542 (CondEncoder), :595-627 (ConvNeXtDecoder).
-#include "common.cuh"
+#include "simt.cuh"
 #include "../../include/flow2gan_b200.h"
 
 #include <string.h>
@@ -337,8 +337,8 @@ extern "C" int f2g_biasnorm(const float* x, int rows, int C, int ld, const float
                             const float* log_scale, float* y, int ld_y, float* inv_out, void* stream) {
   if (int rc = check_channels("f2g_biasnorm", C, ld | ld_y)) return rc;
   const int wpb = 4;
-  biasnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, C, ld, bias, log_scale, y, ld_y, inv_out);
+  F2G_LAUNCH_COOP(biasnorm_kernel, (rows + wpb - 1) / wpb, wpb * 32, static_cast<cudaStream_t>(stream), x, rows, C,
+                  ld, bias, log_scale, y, ld_y, inv_out);
   return check_launch("f2g_biasnorm");
 }
 
@@ -425,7 +425,7 @@ extern "C" int f2g_linear_small(const F2GLinear* probs, int n, int B, int act, v
   }
   const int wpb = 4;
   dim3 grid((max_o + wpb - 1) / wpb, n);
-  linear_small_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  F2G_LAUNCH_COOP(linear_small_kernel, grid, wpb * 32, static_cast<cudaStream_t>(stream), a);
   return check_launch("f2g_linear_small");
 }
 
@@ -433,8 +433,8 @@ extern "C" int f2g_time_sinusoid(const float* t, int B, int dim, const float* fr
                                  float* out, void* stream) {
   const int half = dim / 2;
   const int total = B * half;
-  time_sinusoid_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, B, half, freqs, scale, out);
+  F2G_LAUNCH_COOP(time_sinusoid_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), t, B, half, freqs,
+                  scale, out);
   return check_launch("f2g_time_sinusoid");
 }
 
@@ -448,9 +448,8 @@ extern "C" int f2g_pack2d(const float* src, long long src_rs, long long src_cs, 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  pack2d_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_rs, src_cs, rows,
-                                                                      cols, dst, ld, ld_fill,
-                                                                      round_tf32);
+  F2G_LAUNCH_COOP(pack2d_kernel, blocks, 256, static_cast<cudaStream_t>(stream), src, src_rs, src_cs, rows, cols, dst,
+                  ld, ld_fill, round_tf32);
   return check_launch("f2g_pack2d");
 }
 
@@ -463,14 +462,14 @@ extern "C" int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, flo
   const long long total = (long long)B * T * ld;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_cf_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, B, C, T, ktaps, out,
-                                                                         ld, round_tf32);
+  F2G_LAUNCH_COOP(im2col_cf_kernel, blocks, 256, static_cast<cudaStream_t>(stream), x, B, C, T, ktaps, out, ld,
+                  round_tf32);
   return check_launch("f2g_im2col_cf");
 }
 
 extern "C" int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream) {
   const int total = B * frames;
-  frame_mask_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lens, B, frames, hop, out);
+  F2G_LAUNCH_COOP(frame_mask_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), lens, B, frames, hop,
+                  out);
   return check_launch("f2g_frame_mask");
 }

@@ -52,72 +52,113 @@ inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 #else
 // ------------------------------------------------------------------------------- host emulation
 #include <math.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #define F2G_KERNEL static
 #define F2G_SIMT_DEV static inline
+#define F2G_DEVINL static inline
 #define F2G_GRID_CONSTANT
 #define __restrict__ __restrict
+#define __global__ static
+#define __shared__ static      /* blocks run one after the other: one copy per kernel is "per block" */
+#define __launch_bounds__(...)
+#define __grid_constant__
 
-// -DF2G_EMUL_REVERSE runs blocks and threads in descending order: results must not depend on it
+// -DF2G_EMUL_REVERSE runs blocks (and, in the sequential mode, threads) in descending order: results
+// must not depend on it
 #ifdef F2G_EMUL_REVERSE
 #define F2G_EMUL_ORDER(i, n) ((n) - 1u - (i))
 #else
 #define F2G_EMUL_ORDER(i, n) (i)
 #endif
 
-#include <pthread.h>
-
-#include <mutex>
-#include <thread>
-#include <vector>
-
 typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+static inline const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
 struct f2g_dim3 {
   unsigned x, y, z;
+};
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct int2 {
   int x, y;
 };
-static thread_local f2g_dim3 threadIdx, blockIdx;
-static f2g_dim3 blockDim, gridDim;
-#define __shared__ static      /* blocks run one after the other: one copy per kernel is "per block" */
+struct alignas(8) uint2 {
+  unsigned x, y;
+};
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+struct __half {
+  unsigned short bits;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline thread_local f2g_dim3 threadIdx, blockIdx;
+inline f2g_dim3 blockDim, gridDim;
 
-#define F2G_LAUNCH(kernel, grid, block, stream, ...)                            \
-  do {                                                                          \
-    (void)(stream);                                                             \
-    gridDim = {(unsigned)(grid), 1, 1};                                         \
-    blockDim = {(unsigned)(block), 1, 1};                                       \
-    for (unsigned b_ = 0; b_ < gridDim.x; ++b_)                                 \
-      for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                            \
-        blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                       \
-        threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                     \
-        kernel(__VA_ARGS__);                                                    \
-      }                                                                         \
-  } while (0)
-
-// Cooperative kernels (shared memory, __syncthreads, warp shuffles, atomics): one host thread per
-// CUDA thread of a block, blocks one after the other.  Used by tests for small problems only.
+// Cooperative kernels (shared memory, __syncthreads, warp shuffles, atomics) run with one host
+// thread per CUDA thread of a block, blocks one after the other; thread-independent kernels run as
+// plain loops (F2G_LAUNCH).  Tests only, small problems.
 namespace f2g {
+enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
+inline char g_emul_err[512];       // one buffer for every translation unit of the emulated library
+static inline void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_emul_err, sizeof(g_emul_err), fmt, ap);
+  va_end(ap);
+}
+static inline int check_launch(const char*) { return 0; }
 inline pthread_barrier_t g_block_bar;
 inline pthread_barrier_t g_warp_bar[32];
 inline float g_shfl[32][32];
 inline std::mutex g_atomic_mu;
-inline void emul_coop_begin(unsigned block) {
-  pthread_barrier_init(&g_block_bar, nullptr, block);
-  for (unsigned w = 0; w < (block + 31) / 32; ++w) {
-    const unsigned lanes = block - 32 * w < 32 ? block - 32 * w : 32;
-    pthread_barrier_init(&g_warp_bar[w], nullptr, lanes);
-  }
-}
-inline void emul_coop_end(unsigned block) {
+
+template <typename F>
+inline void emul_run_grid(dim3 grid, dim3 block, F&& body) {
+  gridDim = {grid.x, grid.y, grid.z};
+  blockDim = {block.x, block.y, block.z};
+  const unsigned nthreads = block.x * block.y * block.z;
+  pthread_barrier_init(&g_block_bar, nullptr, nthreads);
+  for (unsigned w = 0; w < (nthreads + 31) / 32; ++w)
+    pthread_barrier_init(&g_warp_bar[w], nullptr, nthreads - 32 * w < 32 ? nthreads - 32 * w : 32);
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      std::vector<std::thread> th;
+      th.reserve(nthreads);
+      for (unsigned t = 0; t < nthreads; ++t)
+        th.emplace_back([&, bx, by, t]() {
+          blockIdx = {F2G_EMUL_ORDER(bx, grid.x), by, 0};
+          threadIdx = {t, 0, 0};
+          body();
+        });
+      for (auto& x : th) x.join();
+    }
   pthread_barrier_destroy(&g_block_bar);
-  for (unsigned w = 0; w < (block + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_bar[w]);
+  for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_bar[w]);
+}
+
+// same call shape as common.cuh's launch_pdl (programmatic dependent launch has no host meaning)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
+  emul_run_grid(grid, block, [&]() { kern(static_cast<KArgs>(args)...); });
+  return cudaSuccess;
 }
 }  // namespace f2g
+
 static inline void __syncthreads() { pthread_barrier_wait(&f2g::g_block_bar); }
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -133,39 +174,61 @@ static inline float atomicAdd(float* p, float v) {
   *p = old + v;
   return old;
 }
-#define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                  \
-  do {                                                                                     \
-    (void)(stream);                                                                        \
-    gridDim = {(unsigned)(grid), 1, 1};                                                    \
-    blockDim = {(unsigned)(block), 1, 1};                                                  \
-    f2g::emul_coop_begin(blockDim.x);                                                      \
-    for (unsigned b_ = 0; b_ < gridDim.x; ++b_) {                                          \
-      std::vector<std::thread> th_;                                                        \
-      for (unsigned t_ = 0; t_ < blockDim.x; ++t_)                                         \
-        th_.emplace_back([&, b_, t_]() {                                                   \
-          blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                                \
-          threadIdx = {t_, 0, 0};                                                          \
-          kernel(__VA_ARGS__);                                                             \
-        });                                                                                \
-      for (auto& x_ : th_) x_.join();                                                      \
-    }                                                                                      \
-    f2g::emul_coop_end(blockDim.x);                                                        \
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline int __float2int_rd(float v) { return (int)floorf(v); }
+static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+
+#define F2G_LAUNCH(kernel, grid, block, stream, ...)                            \
+  do {                                                                          \
+    (void)(stream);                                                             \
+    gridDim = {(unsigned)(grid), 1, 1};                                         \
+    blockDim = {(unsigned)(block), 1, 1};                                       \
+    for (unsigned b_ = 0; b_ < gridDim.x; ++b_)                                 \
+      for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                            \
+        blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                       \
+        threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                     \
+        kernel(__VA_ARGS__);                                                    \
+      }                                                                         \
+  } while (0)
+#define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                         \
+  do {                                                                                            \
+    (void)(stream);                                                                               \
+    f2g::emul_run_grid(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); });                  \
   } while (0)
 
 namespace f2g {
-enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
-inline char g_emul_err[512];       // one buffer for every translation unit of the emulated library
-static inline void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_emul_err, sizeof(g_emul_err), fmt, ap);
-  va_end(ap);
-}
-static inline int check_launch(const char*) { return 0; }
 F2G_SIMT_DEV float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+F2G_SIMT_DEV float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// cvt.rna.tf32.f32 for finite inputs: nearest, ties away from zero, 10 explicit significand bits
+F2G_SIMT_DEV float tf32_rna(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+// cvt.rn.satfinite.f16x2.f32: nearest-even, clamped to the finite fp16 range
+F2G_SIMT_DEV unsigned short half_bits_sat(float v) {
+  v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+  const _Float16 h = (_Float16)v;
+  unsigned short b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+F2G_SIMT_DEV uint2 pack_half4(float4 v) {
+  return make_uint2((unsigned)half_bits_sat(v.x) | ((unsigned)half_bits_sat(v.y) << 16),
+                    (unsigned)half_bits_sat(v.z) | ((unsigned)half_bits_sat(v.w) << 16));
+}
+F2G_SIMT_DEV void pdl_wait() {}
+F2G_SIMT_DEV void pdl_launch() {}
 // the compiler flags of the emulated build forbid contraction (-ffp-contract=off)
 F2G_SIMT_DEV void simt_block_sum(float v, float* dst) { *dst += v; }
 F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {
@@ -181,7 +244,6 @@ static inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t) {
   return 0;
 }
 }  // namespace f2g
-static inline long long min(long long a, long long b) { return a < b ? a : b; }
 extern "C" __attribute__((weak)) const char* f2g_emul_last_error(void) { return f2g::g_emul_err; }
 #endif
 

@@ -33,7 +33,7 @@ def available() -> bool:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu")]
+        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu", "blocks.cu")]
         srcs = cus + [os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
         h = hashlib.sha256()
         for s in srcs:
@@ -103,3 +103,23 @@ def average_update(pairs, w_avg: float, w_cur: float, scale: float, chunk: int =
             chunks += [i, ci]
     ch = np.asarray(chunks, dtype=np.int32)
     return lib().f2g_average_update(C.cast(tab, C.c_void_p), _p(ch), len(chunks) // 2, w_avg, w_cur, scale, None)
+
+
+def native_fixture(monkeypatch):
+    """Redirect flow2gan_b200._lib to the emulated library for every entry point it contains: the
+    product's own ctypes wrappers (shape bookkeeping, descriptor structs) then run unchanged on CPU
+    tensors.  Entry points that are not emulated (tcgen05 GEMMs, FFTs ...) raise AttributeError."""
+    from flow2gan_b200 import _lib as L
+    e = lib()
+    for name, (args, res) in L._SIGS.items():
+        if hasattr(e, name):
+            fn = getattr(e, name)
+            fn.argtypes, fn.restype = args, res
+    monkeypatch.setattr(L, "lib", lambda: e)
+    monkeypatch.setattr(L, "load", lambda: e)
+    monkeypatch.setattr(L, "ptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(L, "stream", lambda: None)
+    monkeypatch.setattr(L, "require_cuda", lambda t, what: None)
+    e.f2g_last_error = e.f2g_emul_last_error
+    e.f2g_last_error.restype = C.c_char_p
+    return L

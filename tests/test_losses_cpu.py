@@ -73,6 +73,7 @@ def test_emulated_kernels_do_not_depend_on_thread_order():
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, F2G_EMUL_REVERSE="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
-                        os.path.join(here, "test_datapath_cpu.py"), os.path.join(here, "test_losses_cpu.py")],
+                        os.path.join(here, "test_datapath_cpu.py"), os.path.join(here, "test_losses_cpu.py"),
+                        os.path.join(here, "test_blocks_cpu.py")],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
