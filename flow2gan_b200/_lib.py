@@ -501,7 +501,8 @@ def pcm16_encode(x, n, clamp, out_i16):
 
 def average_update(tab_u8, chunks_i32, n_chunks, w_avg, w_cur, scale):
     require_cuda(tab_u8, "tensor table")
-    assert chunks_i32.is_cuda and chunks_i32.dtype == torch.int32
+    require_cuda(chunks_i32, "chunk table")
+    assert chunks_i32.dtype == torch.int32
     _check(lib().f2g_average_update(tab_u8.data_ptr(), chunks_i32.data_ptr(), n_chunks, float(w_avg),
                                     float(w_cur), float(scale), stream()))
 

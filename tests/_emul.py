@@ -45,21 +45,18 @@ def lib() -> C.CDLL:
                                    *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", "-pthread", *cus,
                                    "-o", so])
         l = C.CDLL(so)
-        vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
-        l.f2g_pcm_decode.argtypes = [vp, i, i, ll, ll, vp, vp, vp]
-        l.f2g_gain_resample.argtypes = [vp, ll, vp, f, i, i, i, vp, vp, ll, vp]
-        l.f2g_pcm16_encode.argtypes = [vp, ll, i, vp, vp]
-        l.f2g_average_update.argtypes = [vp, vp, i, d, d, d, vp]
-        l.f2g_loss_terms.argtypes = [vp, i, i, vp, vp, vp]
-        l.f2g_scaled_adam_step.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, i, vp, vp]
+        from flow2gan_b200 import _lib as L          # the product's own signatures (include/flow2gan_b200.h)
+        for name, (args, res) in L._SIGS.items():
+            if hasattr(l, name):
+                fn = getattr(l, name)
+                fn.argtypes, fn.restype = args, res
+        l.f2g_emul_last_error.restype = C.c_char_p
         _lib = l
     return _lib
 
 
 def last_error() -> str:
-    fn = lib().f2g_emul_last_error
-    fn.restype = C.c_char_p
-    return fn().decode()
+    return lib().f2g_emul_last_error().decode()
 
 
 def _p(a):
@@ -111,15 +108,10 @@ def native_fixture(monkeypatch):
     tensors.  Entry points that are not emulated (tcgen05 GEMMs, FFTs ...) raise AttributeError."""
     from flow2gan_b200 import _lib as L
     e = lib()
-    for name, (args, res) in L._SIGS.items():
-        if hasattr(e, name):
-            fn = getattr(e, name)
-            fn.argtypes, fn.restype = args, res
     monkeypatch.setattr(L, "lib", lambda: e)
     monkeypatch.setattr(L, "load", lambda: e)
     monkeypatch.setattr(L, "ptr", lambda t: None if t is None else t.data_ptr())
     monkeypatch.setattr(L, "stream", lambda: None)
     monkeypatch.setattr(L, "require_cuda", lambda t, what: None)
     e.f2g_last_error = e.f2g_emul_last_error
-    e.f2g_last_error.restype = C.c_char_p
     return L

@@ -261,29 +261,10 @@ def test_emulated_average_update_ragged_chunks():
 # ------------------------------------------- host layer dry run: product Python + emulated kernels
 @pytest.fixture
 def emulated_lib(monkeypatch):
-    """Redirects the four data-path entry points of flow2gan_b200._lib to the host-emulated build of
-    the same kernels so that datapath.py / averaging.py run end to end on CPU tensors.  Nothing in
-    the product does this: without the patch the calls below raise (no CPU fallback)."""
-    import ctypes as C
-    from flow2gan_b200 import _lib as L
-    e = _emul.lib()
-
-    def chk(rc):
-        if rc != 0:
-            raise RuntimeError("flow2gan_b200 native call failed (rc=%d): %s" % (rc, _emul.last_error()))
-
-    def p(t):
-        return None if t is None else C.c_void_p(t.data_ptr())
-
-    monkeypatch.setattr(L, "require_cuda", lambda t, what: None)
-    monkeypatch.setattr(L, "pcm_decode", lambda pcm, fmt, ch, first, n, mono, stats:
-                        chk(e.f2g_pcm_decode(p(pcm), fmt, ch, first, n, p(mono), p(stats), None)))
-    monkeypatch.setattr(L, "gain_resample", lambda x, n_in, stats, db, o, n, w, taps, out, n_out:
-                        chk(e.f2g_gain_resample(p(x), n_in, p(stats), float(db), o, n, w, p(taps), p(out), n_out, None)))
-    monkeypatch.setattr(L, "pcm16_encode", lambda x, n, clamp, out:
-                        chk(e.f2g_pcm16_encode(p(x), n, int(clamp), p(out), None)))
-    monkeypatch.setattr(L, "average_update", lambda tab, chunks, n, w1, w2, sc:
-                        chk(e.f2g_average_update(p(tab), p(chunks), n, float(w1), float(w2), float(sc), None)))
+    """flow2gan_b200._lib redirected to the host-emulated build of the same kernels (tests/_emul.py), so
+    that datapath.py / averaging.py run end to end on CPU tensors through the product's own wrappers.
+    Nothing in the product does this: without the patch the calls below raise (no CPU fallback)."""
+    L = _emul.native_fixture(monkeypatch)
     import flow2gan_b200.datapath as D
     monkeypatch.setattr(D, "_TAPS", {})
     import flow2gan_b200.averaging as A

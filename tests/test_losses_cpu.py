@@ -1,7 +1,6 @@
 """CPU checks of the fused multi-tensor loss reductions: csrc/losses.cu compiled for the host from the
 same source (tests/_emul.py) behind the product's autograd wrappers (flow2gan_b200/losses.py,
 gan.py), against torch autograd of the reference's expressions (flow2gan/models/gan.py:57-99)."""
-import ctypes as C
 import os
 import subprocess
 import sys
@@ -17,20 +16,7 @@ pytestmark = pytest.mark.skipif(not _emul.available(), reason="g++ not available
 
 @pytest.fixture
 def emulated_losses(monkeypatch):
-    from flow2gan_b200 import _lib as L
-    e = _emul.lib()
-
-    def loss_terms(terms, backward, out, gout):
-        arr = (L.F2GLossTerm * len(terms))(*terms)
-        rc = e.f2g_loss_terms(C.cast(arr, C.c_void_p), len(terms), int(backward),
-                              None if out is None else C.c_void_p(out.data_ptr()),
-                              None if gout is None else C.c_void_p(gout.data_ptr()), None)
-        if rc != 0:
-            raise RuntimeError("flow2gan_b200 native call failed (rc=%d): %s" % (rc, _emul.last_error()))
-
-    monkeypatch.setattr(L, "ptr", lambda t: None if t is None else t.data_ptr())
-    monkeypatch.setattr(L, "loss_terms", loss_terms)
-    return L
+    return _emul.native_fixture(monkeypatch)
 
 
 def test_l1_terms(emulated_losses):

@@ -2,7 +2,6 @@
 (cooperative emulation: one host thread per CUDA thread, tests/_emul.py) behind the product's
 optimizer class, against the reference's own 45-step optimizer run (tests/golden/ref_scaled_adam.pt)
 and the CPU oracle.  Same cases as tests/test_optim_gpu.py."""
-import ctypes as C
 import os
 
 import pytest
@@ -17,21 +16,7 @@ pytestmark = pytest.mark.skipif(not _emul.available(), reason="g++ not available
 
 @pytest.fixture
 def emulated_adam(monkeypatch):
-    from flow2gan_b200 import _lib as L
-    e = _emul.lib()
-
-    def p(t):
-        return None if t is None else C.c_void_p(t.data_ptr())
-
-    def step(tab, n_tensors, chunks, n_chunks, acc, tstate, gstate, norms, step_, phase, hyper):
-        rc = e.f2g_scaled_adam_step(p(tab), n_tensors, p(chunks), n_chunks, p(acc), p(tstate), p(gstate), p(norms),
-                                    step_, phase, C.cast(C.byref(hyper), C.c_void_p), None)
-        if rc != 0:
-            raise RuntimeError("flow2gan_b200 native call failed (rc=%d): %s" % (rc, _emul.last_error()))
-
-    monkeypatch.setattr(L, "require_cuda", lambda t, what: None)
-    monkeypatch.setattr(L, "scaled_adam_step", step)
-    return L
+    return _emul.native_fixture(monkeypatch)
 
 
 def _run(g, upto=None, resume_at=None):
