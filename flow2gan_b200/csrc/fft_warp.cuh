@@ -13,7 +13,7 @@
 // per-frame twiddle generation (one 2048-entry root-of-unity table in global memory): the
 // shared-memory Stockham kernel this replaces was bound by its 10-stage __syncthreads chain.
 #pragma once
-#include "common.cuh"
+#include "simt.cuh"
 
 namespace f2g {
 

@@ -21,6 +21,10 @@
 #define F2G_GRID_CONSTANT __grid_constant__
 #define F2G_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define F2G_LAUNCH_COOP_SMEM(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// dynamic shared memory of the enclosing kernel, viewed as T[]
+#define F2G_DYN_SMEM(T, name) extern __shared__ T name[]
 
 namespace f2g {
 // per-thread partials -> one atomic per warp (the kernels using these are HBM streams; a few
@@ -72,6 +76,10 @@ inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 #define __shared__ static      /* blocks run one after the other: one copy per kernel is "per block" */
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __device__
+#define __host__
+#define __constant__
+#define __forceinline__ inline
 
 // -DF2G_EMUL_REVERSE runs blocks (and, in the sequential mode, threads) in descending order: results
 // must not depend on it
@@ -101,9 +109,13 @@ struct alignas(8) uint2 {
 struct alignas(16) float4 {
   float x, y, z, w;
 };
+struct alignas(8) float2 {
+  float x, y;
+};
 struct __half {
   unsigned short bits;
 };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline thread_local f2g_dim3 threadIdx, blockIdx;
@@ -122,6 +134,7 @@ static inline void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static inline int check_launch(const char*) { return 0; }
+alignas(128) inline unsigned char g_dyn_smem[228 * 1024];     // "dynamic shared memory" of the running block
 inline pthread_barrier_t g_block_bar;
 inline pthread_barrier_t g_warp_bar[32];
 inline float g_shfl[32][32];
@@ -159,7 +172,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 }  // namespace f2g
 
+#define F2G_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(f2g::g_dyn_smem)
 static inline void __syncthreads() { pthread_barrier_wait(&f2g::g_block_bar); }
+static inline void __syncwarp() { pthread_barrier_wait(&f2g::g_warp_bar[threadIdx.x >> 5]); }
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
   f2g::g_shfl[w][l] = v;
@@ -176,9 +191,27 @@ static inline float atomicAdd(float* p, float v) {
 }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
+static inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
 static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
+static inline void sincospif(float x, float* s, float* c) {
+  *s = (float)sin(3.14159265358979323846 * (double)x);
+  *c = (float)cos(3.14159265358979323846 * (double)x);
+}
+static inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
+template <typename T>
+static inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t n) {
+  memcpy(&symbol, src, n);
+  return cudaSuccess;
+}
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K>
+static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 
 #define F2G_LAUNCH(kernel, grid, block, stream, ...)                            \
   do {                                                                          \
@@ -195,6 +228,12 @@ static inline T __ldg(const T* p) { return *p; }
 #define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                         \
   do {                                                                                            \
     (void)(stream);                                                                               \
+    f2g::emul_run_grid(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); });                  \
+  } while (0)
+#define F2G_LAUNCH_COOP_SMEM(kernel, grid, block, smem, stream, ...)                              \
+  do {                                                                                            \
+    (void)(stream);                                                                               \
+    if ((size_t)(smem) > sizeof(f2g::g_dyn_smem)) abort();                                        \
     f2g::emul_run_grid(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); });                  \
   } while (0)
 

@@ -3,7 +3,7 @@
 // + envelope divide + branch fusion + Euler update.  All HBM-bound SIMT kernels.
 // Reference semantics: torch.stft / torch.istft (center=True, reflect pad, onesided) as called
 // from flow2gan/models/modules.py:68-84,105-116 and the torchaudio (Mel)Spectrogram wrappers.
-#include "common.cuh"
+#include "simt.cuh"
 #include "../../include/flow2gan_b200.h"
 #include "fft_warp.cuh"
 
@@ -63,7 +63,7 @@ F2G_DEVINL void stft_frame(const float* __restrict__ audio, int T, int ld_audio,
                            const float* __restrict__ fb, int n_filt, float log_clip,
                            float* __restrict__ out, int ld_out, int round_tf32, int center,
                            int adjoint_scale, const float* __restrict__ row_mask, int row) {
-  extern __shared__ float2 sm[];
+  F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
@@ -171,7 +171,7 @@ __global__ void stft_group_kernel(const __grid_constant__ SpecGroupArgs g) {
 
 F2G_DEVINL void irfft_frame(const float* __restrict__ packed, int ld, int n, int logn,
                             float* __restrict__ frames_out, int row) {
-  extern __shared__ float2 sm[];
+  F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
@@ -314,7 +314,7 @@ __global__ void ola_combine_kernel(OlaArgs a, const float* __restrict__ weight,
 // STFT adjoint, per frame: fr[i] = w[i] * Re( sum_{k<=n/2} (dRe_k + i dIm_k) e^{+2 pi i k i / n} )
 __global__ void stft_bwd_frames_kernel(const float* __restrict__ dpacked, int ld, int n, int logn,
                                        float* __restrict__ frames_out, int interleaved) {
-  extern __shared__ float2 sm[];
+  F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
@@ -340,7 +340,7 @@ __global__ void spec_loss_bwd_kernel(const float* __restrict__ audio, int T, int
                                      int hop, int frames, int mode, const float* __restrict__ fb,
                                      int n_filt, float log_clip, const float* __restrict__ dF, int ld_dF,
                                      float* __restrict__ frames_out) {
-  extern __shared__ float2 sm[];
+  F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
   float2* tw = sm + 2 * n;
@@ -462,9 +462,9 @@ static int stft_launch(const float* audio, int B, int T, int ld_audio, int n_fft
   const int frames = center ? 1 + T / hop : 1 + (T - n_fft) / hop;
   const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2) + (n_fft / 2 + 1) * sizeof(float);
-  stft_kernel<<<B * frames, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      audio, T, ld_audio, n_fft, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out,
-      round_tf32, center, adjoint_scale, row_mask);
+  F2G_LAUNCH_COOP_SMEM(stft_kernel, B * frames, threads, smem, static_cast<cudaStream_t>(stream), audio, T, ld_audio,
+                       n_fft, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out, round_tf32, center,
+                       adjoint_scale, row_mask);
   return check_launch("f2g_stft");
 }
 
@@ -597,8 +597,8 @@ extern "C" int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n
   }
   const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2);
-  stft_bwd_frames_kernel<<<rows, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dpacked, ld, n_fft, logn, frames_out, interleaved);
+  F2G_LAUNCH_COOP_SMEM(stft_bwd_frames_kernel, rows, threads, smem, static_cast<cudaStream_t>(stream), dpacked, ld,
+                       n_fft, logn, frames_out, interleaved);
   return check_launch("f2g_stft_bwd_frames");
 }
 
@@ -619,13 +619,13 @@ extern "C" int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio,
     cudaFuncSetAttribute(spec_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  spec_loss_bwd_kernel<<<B * frames, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      audio, T, ld_audio, n_fft, logn, hop, frames, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out);
+  F2G_LAUNCH_COOP_SMEM(spec_loss_bwd_kernel, B * frames, threads, smem, static_cast<cudaStream_t>(stream), audio, T,
+                       ld_audio, n_fft, logn, hop, frames, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out);
   return check_launch("f2g_spec_loss_bwd");
 }
 
 extern "C" int f2g_dc_peak(const float* audio, int B, int T, int ld_audio, float* pre, void* stream) {
-  dc_peak_kernel<<<B, 512, 0, static_cast<cudaStream_t>(stream)>>>(audio, T, ld_audio, pre);
+  F2G_LAUNCH_COOP(dc_peak_kernel, B, 512, static_cast<cudaStream_t>(stream), audio, T, ld_audio, pre);
   return check_launch("f2g_dc_peak");
 }
 
@@ -638,8 +638,8 @@ extern "C" int f2g_irfft_frames(const float* packed, int rows, int ld, int n_fft
   }
   const int threads = n_fft / 2 < 32 ? 32 : n_fft / 2;
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2);
-  irfft_frames_kernel<<<rows, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      packed, ld, n_fft, logn, frames_out);
+  F2G_LAUNCH_COOP_SMEM(irfft_frames_kernel, rows, threads, smem, static_cast<cudaStream_t>(stream), packed, ld, n_fft,
+                       logn, frames_out);
   return check_launch("f2g_irfft_frames");
 }
 
@@ -660,7 +660,7 @@ extern "C" int f2g_ola_combine(const float* const* frames, const int* n_ffts, co
     a.frames[j] = n_frames[j];
   }
   dim3 grid((T + 255) / 256, B);
-  ola_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, weight, x, out, T,
-                                                                          euler, t, dt, clamp);
+  F2G_LAUNCH_COOP(ola_combine_kernel, grid, 256, static_cast<cudaStream_t>(stream), a, weight, x, out, T, euler, t, dt,
+                  clamp);
   return check_launch("f2g_ola_combine");
 }

@@ -33,8 +33,9 @@ def available() -> bool:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu", "blocks.cu")]
-        srcs = cus + [os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
+        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu", "blocks.cu", "spectral.cu")]
+        srcs_extra = [os.path.join(CSRC, "fft_warp.cuh")]
+        srcs = cus + srcs_extra + [os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
         h = hashlib.sha256()
         for s in srcs:
             h.update(open(s, "rb").read())
