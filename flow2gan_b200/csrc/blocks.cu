@@ -433,7 +433,7 @@ extern "C" int f2g_time_sinusoid(const float* t, int B, int dim, const float* fr
                                  float* out, void* stream) {
   const int half = dim / 2;
   const int total = B * half;
-  F2G_LAUNCH_COOP(time_sinusoid_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), t, B, half, freqs,
+  F2G_LAUNCH(time_sinusoid_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), t, B, half, freqs,
                   scale, out);
   return check_launch("f2g_time_sinusoid");
 }
@@ -448,7 +448,7 @@ extern "C" int f2g_pack2d(const float* src, long long src_rs, long long src_cs, 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  F2G_LAUNCH_COOP(pack2d_kernel, blocks, 256, static_cast<cudaStream_t>(stream), src, src_rs, src_cs, rows, cols, dst,
+  F2G_LAUNCH(pack2d_kernel, blocks, 256, static_cast<cudaStream_t>(stream), src, src_rs, src_cs, rows, cols, dst,
                   ld, ld_fill, round_tf32);
   return check_launch("f2g_pack2d");
 }
@@ -462,14 +462,14 @@ extern "C" int f2g_im2col_cf(const float* x, int B, int C, int T, int ktaps, flo
   const long long total = (long long)B * T * ld;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  F2G_LAUNCH_COOP(im2col_cf_kernel, blocks, 256, static_cast<cudaStream_t>(stream), x, B, C, T, ktaps, out, ld,
+  F2G_LAUNCH(im2col_cf_kernel, blocks, 256, static_cast<cudaStream_t>(stream), x, B, C, T, ktaps, out, ld,
                   round_tf32);
   return check_launch("f2g_im2col_cf");
 }
 
 extern "C" int f2g_frame_mask(const int* lens, int B, int frames, int hop, float* out, void* stream) {
   const int total = B * frames;
-  F2G_LAUNCH_COOP(frame_mask_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), lens, B, frames, hop,
+  F2G_LAUNCH(frame_mask_kernel, (total + 255) / 256, 256, static_cast<cudaStream_t>(stream), lens, B, frames, hop,
                   out);
   return check_launch("f2g_frame_mask");
 }

@@ -148,18 +148,21 @@ inline void emul_run_grid(dim3 grid, dim3 block, F&& body) {
   pthread_barrier_init(&g_block_bar, nullptr, nthreads);
   for (unsigned w = 0; w < (nthreads + 31) / 32; ++w)
     pthread_barrier_init(&g_warp_bar[w], nullptr, nthreads - 32 * w < 32 ? nthreads - 32 * w : 32);
-  for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
-      std::vector<std::thread> th;
-      th.reserve(nthreads);
-      for (unsigned t = 0; t < nthreads; ++t)
-        th.emplace_back([&, bx, by, t]() {
-          blockIdx = {F2G_EMUL_ORDER(bx, grid.x), by, 0};
-          threadIdx = {t, 0, 0};
-          body();
-        });
-      for (auto& x : th) x.join();
-    }
+  // one host thread per CUDA thread for the whole launch; the threads walk the blocks together (a
+  // barrier after each block: the next one reuses the "shared memory" statics)
+  const unsigned nblocks = grid.x * grid.y;
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      threadIdx = {t, 0, 0};
+      for (unsigned b = 0; b < nblocks; ++b) {
+        blockIdx = {F2G_EMUL_ORDER(b % grid.x, grid.x), b / grid.x, 0};
+        body();
+        pthread_barrier_wait(&g_block_bar);
+      }
+    });
+  for (auto& x : th) x.join();
   pthread_barrier_destroy(&g_block_bar);
   for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_bar[w]);
 }
@@ -216,14 +219,16 @@ static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess
 #define F2G_LAUNCH(kernel, grid, block, stream, ...)                            \
   do {                                                                          \
     (void)(stream);                                                             \
-    gridDim = {(unsigned)(grid), 1, 1};                                         \
+    const dim3 g_ = dim3(grid);                                                 \
+    gridDim = {g_.x, g_.y, g_.z};                                               \
     blockDim = {(unsigned)(block), 1, 1};                                       \
-    for (unsigned b_ = 0; b_ < gridDim.x; ++b_)                                 \
-      for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                            \
-        blockIdx = {F2G_EMUL_ORDER(b_, gridDim.x), 0, 0};                       \
-        threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                     \
-        kernel(__VA_ARGS__);                                                    \
-      }                                                                         \
+    for (unsigned by_ = 0; by_ < g_.y; ++by_)                                   \
+      for (unsigned b_ = 0; b_ < g_.x; ++b_)                                    \
+        for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                          \
+          blockIdx = {F2G_EMUL_ORDER(b_, g_.x), by_, 0};                        \
+          threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                   \
+          kernel(__VA_ARGS__);                                                  \
+        }                                                                       \
   } while (0)
 #define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                         \
   do {                                                                                            \

@@ -660,7 +660,7 @@ extern "C" int f2g_ola_combine(const float* const* frames, const int* n_ffts, co
     a.frames[j] = n_frames[j];
   }
   dim3 grid((T + 255) / 256, B);
-  F2G_LAUNCH_COOP(ola_combine_kernel, grid, 256, static_cast<cudaStream_t>(stream), a, weight, x, out, T, euler, t, dt,
+  F2G_LAUNCH(ola_combine_kernel, grid, 256, static_cast<cudaStream_t>(stream), a, weight, x, out, T, euler, t, dt,
                   clamp);
   return check_launch("f2g_ola_combine");
 }
