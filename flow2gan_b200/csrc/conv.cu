@@ -5,7 +5,7 @@
 //   (Co_pad, (ih*kw + iw)*Ci + ci)
 // Reference: torch.nn.Conv2d call sites flow2gan/models/discriminators.py:65-76,95-104,171-184,
 // 203-217 ((5,1)/(3,1) strided convs of DiscriminatorP, (3,9)/(3,3) convs of DiscriminatorR).
-#include "common.cuh"
+#include "simt.cuh"
 #include "../../include/flow2gan_b200.h"
 
 namespace f2g {
@@ -226,8 +226,8 @@ extern "C" int f2g_im2col2d(const float* x, const F2GConv2d* p, float* col, int 
   const bool vec = (g.C % 4 == 0) && (g.pitch_h % 4 == 0) && (g.pitch_n % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
   const unsigned blocks = (unsigned)((M + 7) / 8);
-  if (vec) im2col2d_kernel<true><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
-  else im2col2d_kernel<false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, col, round_tf32);
+  if (vec) F2G_LAUNCH(im2col2d_kernel<true>, blocks, 256, static_cast<cudaStream_t>(stream), x, g, col, round_tf32);
+  else F2G_LAUNCH(im2col2d_kernel<false>, blocks, 256, static_cast<cudaStream_t>(stream), x, g, col, round_tf32);
   return check_launch("f2g_im2col2d");
 }
 
@@ -237,8 +237,8 @@ extern "C" int f2g_col2im2d(const float* dcol, const F2GConv2d* p, float* dx, in
   const bool vec = (g.C % 4 == 0) && (g.pitch_h % 4 == 0) && (g.pitch_n % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0);
   const long long total = (long long)g.Nb * g.H * g.W * (vec ? g.C / 4 : g.C);
-  if (vec) col2im2d_kernel<true><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
-  else col2im2d_kernel<false><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, g, dx, accumulate);
+  if (vec) F2G_LAUNCH(col2im2d_kernel<true>, grid_for(total), 256, static_cast<cudaStream_t>(stream), dcol, g, dx, accumulate);
+  else F2G_LAUNCH(col2im2d_kernel<false>, grid_for(total), 256, static_cast<cudaStream_t>(stream), dcol, g, dx, accumulate);
   return check_launch("f2g_col2im2d");
 }
 
@@ -254,8 +254,7 @@ extern "C" int f2g_pad2d(const float* x, int Nb, int H, int W, int C, long long 
   }
   const long long body4 = (long long)Nb * Hl * Wp * (C >> 2);
   const long long total4 = body4 + (slack >> 2);
-  pad2d_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, Nb, H, W, C >> 2, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, total4, body4, round_tf32, out);
+  F2G_LAUNCH(pad2d_kernel, grid_for(total4), 256, static_cast<cudaStream_t>(stream),  x, Nb, H, W, C >> 2, pitch_n, pitch_h, pitch_w, Hl, Wp, ph, pw, total4, body4, round_tf32, out);
   return check_launch("f2g_pad2d");
 }
 
@@ -266,8 +265,7 @@ extern "C" int f2g_conv_w_pack(const float* src, int Co, int Ci, int taps, int C
     return F2G_EINVAL;
   }
   const long long total = dir == 0 ? (long long)Co_pad * ld : (long long)Co * Ci * taps;
-  conv_w_pack_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, Co, Ci, taps,
-                                                                                    Co_pad, ld, dst, dir);
+  F2G_LAUNCH(conv_w_pack_kernel, grid_for(total), 256, static_cast<cudaStream_t>(stream), src, Co, Ci, taps, Co_pad, ld, dst, dir);
   return check_launch("f2g_conv_w_pack");
 }
 
@@ -278,7 +276,6 @@ extern "C" int f2g_conv_w_pack_dgrad(const float* w, int Co, int Ci, int kh, int
     return F2G_EINVAL;
   }
   const long long total = (long long)Ci * kh * kw * Cop;
-  conv_w_pack_dgrad_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, Co, Ci, kh, kw, sw,
-                                                                                          Cop, out);
+  F2G_LAUNCH(conv_w_pack_dgrad_kernel, grid_for(total), 256, static_cast<cudaStream_t>(stream), w, Co, Ci, kh, kw, sw, Cop, out);
   return check_launch("f2g_conv_w_pack_dgrad");
 }

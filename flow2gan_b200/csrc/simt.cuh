@@ -150,14 +150,14 @@ inline void emul_run_grid(dim3 grid, dim3 block, F&& body) {
     pthread_barrier_init(&g_warp_bar[w], nullptr, nthreads - 32 * w < 32 ? nthreads - 32 * w : 32);
   // one host thread per CUDA thread for the whole launch; the threads walk the blocks together (a
   // barrier after each block: the next one reuses the "shared memory" statics)
-  const unsigned nblocks = grid.x * grid.y;
+  const unsigned nblocks = grid.x * grid.y * grid.z;
   std::vector<std::thread> th;
   th.reserve(nthreads);
   for (unsigned t = 0; t < nthreads; ++t)
     th.emplace_back([&, t]() {
       threadIdx = {t, 0, 0};
       for (unsigned b = 0; b < nblocks; ++b) {
-        blockIdx = {F2G_EMUL_ORDER(b % grid.x, grid.x), b / grid.x, 0};
+        blockIdx = {F2G_EMUL_ORDER(b % grid.x, grid.x), (b / grid.x) % grid.y, b / (grid.x * grid.y)};
         body();
         pthread_barrier_wait(&g_block_bar);
       }
@@ -222,13 +222,14 @@ static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess
     const dim3 g_ = dim3(grid);                                                 \
     gridDim = {g_.x, g_.y, g_.z};                                               \
     blockDim = {(unsigned)(block), 1, 1};                                       \
-    for (unsigned by_ = 0; by_ < g_.y; ++by_)                                   \
-      for (unsigned b_ = 0; b_ < g_.x; ++b_)                                    \
-        for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                          \
-          blockIdx = {F2G_EMUL_ORDER(b_, g_.x), by_, 0};                        \
-          threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                   \
-          kernel(__VA_ARGS__);                                                  \
-        }                                                                       \
+    for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                   \
+      for (unsigned by_ = 0; by_ < g_.y; ++by_)                                 \
+        for (unsigned b_ = 0; b_ < g_.x; ++b_)                                  \
+          for (unsigned t_ = 0; t_ < blockDim.x; ++t_) {                        \
+            blockIdx = {F2G_EMUL_ORDER(b_, g_.x), by_, bz_};                    \
+            threadIdx = {F2G_EMUL_ORDER(t_, blockDim.x), 0, 0};                 \
+            kernel(__VA_ARGS__);                                                \
+          }                                                                     \
   } while (0)
 #define F2G_LAUNCH_COOP(kernel, grid, block, stream, ...)                                         \
   do {                                                                                            \

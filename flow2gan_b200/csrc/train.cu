@@ -4,7 +4,7 @@
 // run on the tcgen05 GEMM (gemm_tf32.cu) with MN-major operands.
 // Reference forward definitions: flow2gan/models/modules.py:286-339 (BiasNormFunction),
 // :456-495 (ConvNeXtBlock.forward), :668-680 (upsample_cond), :69-116 (STFT/ISTFT).
-#include "common.cuh"
+#include "simt.cuh"
 #include "../../include/flow2gan_b200.h"
 
 namespace f2g {
@@ -454,8 +454,7 @@ extern "C" int f2g_block_bwd_a(const float* da1, int ld_da, const float* y, cons
     return F2G_EINVAL;
   }
   const int rows = B * T;
-  block_bwd_a_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      da1, ld_da, y, inv, bn_bias, log_scale, tscale, ld_ts, B, T, C, dy, du, coef, gs);
+  F2G_LAUNCH_COOP(block_bwd_a_kernel, (rows + 3) / 4, 128, static_cast<cudaStream_t>(stream),  da1, ld_da, y, inv, bn_bias, log_scale, tscale, ld_ts, B, T, C, dy, du, coef, gs);
   return check_launch("f2g_block_bwd_a");
 }
 
@@ -475,7 +474,7 @@ extern "C" int f2g_block_bwd_c(const F2GBlockBwdC* p, void* stream) {
   a.rows_per_cta = (a.T + want - 1) / want;
   if (a.rows_per_cta < 8) a.rows_per_cta = 8;
   dim3 grid(cb, (a.T + a.rows_per_cta - 1) / a.rows_per_cta, a.B);
-  block_bwd_c_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  F2G_LAUNCH_COOP(block_bwd_c_kernel, grid, 128, static_cast<cudaStream_t>(stream), a);
   return check_launch("f2g_block_bwd_c");
 }
 
@@ -487,8 +486,7 @@ extern "C" int f2g_block_bwd_b(const float* dy, const float* dw_wT, const float*
     return F2G_EINVAL;
   }
   const int rows = B * T;
-  block_bwd_b_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, dw_wT, row_mask, dxo, ld_dxo, rs, B, T, C, dx, ld_dx);
+  F2G_LAUNCH_COOP(block_bwd_b_kernel, (rows + 3) / 4, 128, static_cast<cudaStream_t>(stream),  dy, dw_wT, row_mask, dxo, ld_dxo, rs, B, T, C, dx, ld_dx);
   return check_launch("f2g_block_bwd_b");
 }
 
@@ -508,21 +506,17 @@ extern "C" int f2g_act_bwd(const float* dh, int ld_dh, const float* z, int ld_z,
     rpc = ((rpc + 4 * rpp - 1) / (4 * rpp)) * (4 * rpp);
     dim3 grid(cb, (rows + rpc - 1) / rpc);
     if (tpr == 32)
-      act_bwd_vec_kernel<32><<<grid, 128, 0, st>>>(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz,
-                                                   ld_dz, g_bias, g_slope, round_tf32);
+      F2G_LAUNCH_COOP(act_bwd_vec_kernel<32>, grid, 128, st, dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
     else if (tpr == 16)
-      act_bwd_vec_kernel<16><<<grid, 128, 0, st>>>(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz,
-                                                   ld_dz, g_bias, g_slope, round_tf32);
+      F2G_LAUNCH_COOP(act_bwd_vec_kernel<16>, grid, 128, st, dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
     else
-      act_bwd_vec_kernel<8><<<grid, 128, 0, st>>>(dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz,
-                                                  ld_dz, g_bias, g_slope, round_tf32);
+      F2G_LAUNCH_COOP(act_bwd_vec_kernel<8>, grid, 128, st, dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
     return check_launch("f2g_act_bwd");
   }
   const int cb = (cols + 127) / 128;
   const int rpc = pick_rows_per_cta(rows, cb);
   dim3 grid(cb, (rows + rpc - 1) / rpc);
-  act_bwd_kernel<<<grid, 128, 0, st>>>(
-      dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
+  F2G_LAUNCH_COOP(act_bwd_kernel, grid, 128, st,  dh, ld_dh, z, ld_z, slope, leaky, act, rows, cols, rpc, dz, ld_dz, g_bias, g_slope, round_tf32);
   return check_launch("f2g_act_bwd");
 }
 
@@ -552,8 +546,9 @@ extern "C" int f2g_act_bwd_win(const float* dy, long long s_n, long long s_h, lo
   rpc = ((rpc + 4 * rpp - 1) / (4 * rpp)) * (4 * rpp);
   dim3 grid(cb, (rows + rpc - 1) / rpc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define F2G_ABW(T_) act_bwd_win_kernel<T_><<<grid, 128, 0, st>>>(dy, s_n, s_h, s_w, Hl, R, Ho, Wo, z, ld_z, leaky, act, \
-    rows, cols, cols_total, rpc, dz, ld_dz, guard_rows, g_bias, round_tf32)
+#define F2G_ABW(T_)                                                                                            \
+  F2G_LAUNCH_COOP(act_bwd_win_kernel<T_>, grid, 128, st, dy, s_n, s_h, s_w, Hl, R, Ho, Wo, z, ld_z, leaky, act, rows, \
+                  cols, cols_total, rpc, dz, ld_dz, guard_rows, g_bias, round_tf32)
   if (tpr == 32) F2G_ABW(32);
   else if (tpr == 16) F2G_ABW(16);
   else F2G_ABW(8);
@@ -564,9 +559,7 @@ extern "C" int f2g_act_bwd_win(const float* dy, long long s_n, long long s_h, lo
 extern "C" int f2g_cond_reduce(const float* du, int B, int T, int C, int cond_T, int factor, int zero_row,
                                float* out, int ld_out, void* stream) {
   dim3 grid((C + 127) / 128, B * cond_T + 1);
-  cond_reduce_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(du, B, T, C, cond_T,
-                                                                         factor < 1 ? 1 : factor,
-                                                                         zero_row, out, ld_out);
+  F2G_LAUNCH_COOP(cond_reduce_kernel, grid, 128, static_cast<cudaStream_t>(stream), du, B, T, C, cond_T, factor < 1 ? 1 : factor, zero_row, out, ld_out);
   return check_launch("f2g_cond_reduce");
 }
 
@@ -574,16 +567,14 @@ extern "C" int f2g_istft_bwd_prep(const float* g, int B, int T, int n_fft, int h
                                   float scale, float* gs, void* stream) {
   const int Lp = n_fft + hop * (frames - 1);
   dim3 grid((Lp + 255) / 256, B);
-  istft_bwd_prep_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, T, n_fft, hop, frames,
-                                                                             scale, gs, Lp);
+  F2G_LAUNCH(istft_bwd_prep_kernel, grid, 256, static_cast<cudaStream_t>(stream), g, T, n_fft, hop, frames, scale, gs, Lp);
   return check_launch("f2g_istft_bwd_prep");
 }
 
 extern "C" int f2g_stft_bwd_fold(const float* frames_grad, int B, int T, int n_fft, int hop, int frames,
                                  float* dx, int accumulate, void* stream) {
   dim3 grid((T + 255) / 256, B);
-  stft_bwd_fold_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames_grad, n_fft, hop,
-                                                                            frames, T, dx, accumulate);
+  F2G_LAUNCH(stft_bwd_fold_kernel, grid, 256, static_cast<cudaStream_t>(stream), frames_grad, n_fft, hop, frames, T, dx, accumulate);
   return check_launch("f2g_stft_bwd_fold");
 }
 
@@ -591,6 +582,6 @@ extern "C" int f2g_colsum(const float* x, int ld, int rows, int cols, float* out
   const int cb = (cols + 127) / 128;
   const int rpc = pick_rows_per_cta(rows, cb);
   dim3 grid(cb, (rows + rpc - 1) / rpc);
-  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, rpc, out);
+  F2G_LAUNCH_COOP(colsum_kernel, grid, 128, static_cast<cudaStream_t>(stream), x, ld, rows, cols, rpc, out);
   return check_launch("f2g_colsum");
 }

@@ -33,7 +33,8 @@ def available() -> bool:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu", "blocks.cu", "spectral.cu")]
+        cus = [os.path.join(CSRC, f) for f in ("datapath.cu", "losses.cu", "optim.cu", "blocks.cu", "spectral.cu", "train.cu",
+                                                   "conv.cu")]
         srcs_extra = [os.path.join(CSRC, "fft_warp.cuh")]
         gemm = os.path.join(ROOT, "tests", "emul_gemm.cpp")      # host restatement of the tensor-core contraction
         srcs = cus + srcs_extra + [gemm, os.path.join(CSRC, "simt.cuh"), os.path.join(ROOT, "include", "flow2gan_b200.h")]
@@ -44,9 +45,10 @@ def lib() -> C.CDLL:
         so = os.path.join(OUT, f"libf2g_emul_{h.hexdigest()[:12]}{'_rev' if REVERSE else ''}.so")
         if not os.path.exists(so):
             obj = so[:-3] + "_gemm.o"
-            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-c", gemm, "-o", obj])
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-c", gemm,
+                                   "-o", obj])
             subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-DF2G_HOST_EMUL",
-                                   *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", "-pthread", *cus,
+                                   *(["-DF2G_EMUL_REVERSE"] if REVERSE else []), "-shared", "-fPIC", "-pthread", "-fopenmp", *cus,
                                    "-x", "none", obj, "-o", so])
         l = C.CDLL(so)
         from flow2gan_b200 import _lib as L          # the product's own signatures (include/flow2gan_b200.h)

@@ -57,6 +57,7 @@ extern "C" int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void*) {
     std::vector<float> arow((size_t)d.K), bmat((size_t)d.N * d.K);
     for (int n = 0; n < d.N; ++n)
       for (int k = 0; k < d.K; ++k) bmat[(size_t)n * d.K + k] = b_elem(d, n, k);
+#pragma omp parallel for schedule(static) firstprivate(arow)
     for (int m = 0; m < d.M; ++m) {
       for (int k = 0; k < d.K; ++k) arow[k] = a_elem(d, m, k);
       for (int n = 0; n < d.N; ++n) {

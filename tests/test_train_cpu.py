@@ -1,0 +1,109 @@
+"""Dry run of the TRAINING path on a GPU-less box (same construction as tests/test_engine_cpu.py: the
+product's autograd functions / GAN wrapper / trainers on the host-emulated SIMT kernels of train.cu,
+conv.cu, blocks.cu, spectral.cu, losses.cu, optim.cu, datapath.cu plus the host restatement of the
+GEMM contract), against outputs of the reference itself:
+  * stage-1 flow-matching loss and parameter gradients (tests/golden/ref_fm_loss_24k.pt) -- default;
+  * both GAN phases, losses and gradients (tests/golden/ref_gan_24k.pt), with the fused multi-tensor
+    loss reductions on and off, and FMTrainer steps with the fp64 model average -- F2G_SLOW_TESTS=1
+    (several minutes of emulation: the discriminators are ~80 GFLOP of plain host GEMM)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import _emul
+from _cases import GOLDEN, rel_rms
+from _synth import synth_state_dict
+from oracle import datapath_oracle as DO
+from test_train_gpu import _assert_grads, _grad_errors
+
+pytestmark = pytest.mark.skipif(not _emul.available(), reason="g++ not available")
+slow = pytest.mark.skipif(os.environ.get("F2G_SLOW_TESTS") != "1", reason="set F2G_SLOW_TESTS=1 (minutes of emulation)")
+
+
+@pytest.fixture
+def L(monkeypatch):
+    lib = _emul.native_fixture(monkeypatch)
+    import flow2gan_b200.engine as E
+    from flow2gan_b200.generator import BaseAudioGenerator
+    monkeypatch.setattr(E, "FORK_COND", False)
+    monkeypatch.setattr(BaseAudioGenerator, "_require_cuda", lambda self: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)
+    return lib
+
+
+def _generator(g):
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    m = MelAudioGenerator(**get_generator_config(g["model_name"]))
+    m.load_state_dict(synth_state_dict(g["sd_spec"], g["sd_seed"]), strict=False)
+    return m
+
+
+def test_fm_loss_and_grads_match_reference(L):
+    g = torch.load(os.path.join(GOLDEN, "ref_fm_loss_24k.pt"), weights_only=False)
+    m = _generator(g).eval()          # the golden run used eval(): no branch dropout / limit_param_value draws
+    loss = m(cond=g["mel"], audio=g["audio"], audio_lens=g["lens"], noise=g["noise"], t=g["t"])
+    rel = abs(float(loss.detach()) - float(g["loss"])) / float(g["loss"])
+    print("fm loss", float(loss.detach()), "ref", float(g["loss"]), "rel", rel)
+    assert rel < 2e-3
+    loss.backward()
+    _assert_grads(_grad_errors(list(m.named_parameters()), g["grads"]))
+
+
+@slow
+@pytest.mark.parametrize("fused", [False, True])
+def test_gan_phases_match_reference(L, monkeypatch, fused):
+    import flow2gan_b200.gan as G
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from flow2gan_b200.modules import LogMelSpectrogram
+    monkeypatch.setattr(G, "FUSED_LOSSES", fused)
+    g = torch.load(os.path.join(GOLDEN, "ref_gan_24k.pt"), weights_only=False)
+    gen = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    gen.branch_dropout = 0.0
+    gan = G.GAN(gen, **get_gan_config("gan_multi_scale_mel_recon"))
+    gan.load_state_dict(synth_state_dict(g["sd_spec"], g["sd_seed"]), strict=False)
+    audio, lens, noise = g["audio"], g["lens"], g["noise"]
+    mel = LogMelSpectrogram(24000, 1024, 256, 100)(audio)
+    assert rel_rms(mel, g["mel"]) < 1e-5
+    rr = random.random
+    random.random = lambda: 0.99                     # limit_param_value hook off ("limit_off" golden)
+    try:
+        for train_disc, ph, wts in ((True, "d", (1.0, 0.1)), (False, "g", (1.0, 0.1, 1.0, 0.1, 45.0))):
+            gan.zero_grad()
+            losses = gan(cond=mel, audio=audio, audio_lens=lens, n_timesteps=1, train_disc=train_disc, noise=noise)
+            got = torch.stack([l.detach() for l in losses])
+            ref = g[f"{ph}_limit_off_losses"]
+            rel = ((got - ref).abs() / ref.abs()).max()
+            print(ph, "fused" if fused else "torch", "losses", got.tolist(), "max rel", float(rel))
+            assert float(rel) < 2e-3
+            sum(l * w for l, w in zip(losses, wts)).backward()
+            sub = gan.discriminator if train_disc else gan.generator
+            pre = "discriminator." if train_disc else "generator."
+            _assert_grads(_grad_errors([(pre + k, p) for k, p in sub.named_parameters()], g[f"{ph}_limit_off_grads"]))
+    finally:
+        random.random = rr
+
+
+@slow
+def test_pretrain_steps_and_model_average(L):
+    from flow2gan_b200.pretrainer import FMTrainer
+    g = torch.load(os.path.join(GOLDEN, "ref_fm_loss_24k.pt"), weights_only=False)
+    m = _generator(g)
+    m.estimators[1].lr_scale = 0.5
+    tr = FMTrainer(m, average_period=2, rank=0)
+    assert sorted(tr.scheduler.base_lrs) == [0.0175, 0.035]
+    torch.manual_seed(0)
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    avg0 = {k: v.detach().clone() for k, v in tr.model_avg.state_dict().items()}
+    losses = [float(tr.step(g["audio"], g["lens"])["loss"]) for _ in range(2)]
+    assert np.isfinite(losses).all(), losses
+    moved = [k for k, v in m.state_dict().items() if not torch.equal(v, before[k])]
+    assert len(moved) > 400, len(moved)
+    want = DO.average_state_dict(avg0, {k: v.detach() for k, v in m.state_dict().items()}, 1 - 2 / 2, 2 / 2)
+    for k, v in tr.model_avg.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    assert tr.batch_idx_train == 2 and tr.scheduler.batch == 2
