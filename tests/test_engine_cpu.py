@@ -112,3 +112,21 @@ def test_model_infer_dry_run_matches_reference_golden(L):
             errs["clamp"] = rel_rms(out, g["audio_n2_clamp"])
     print("dry-run rel-RMS vs reference:", errs)
     assert all(v < 1e-3 for v in errs.values()), errs
+
+
+def test_ragged_tiny_batch_vs_oracle(L):
+    """Edge shapes the golden files do not hold: 4 mel frames, ragged lengths that are no multiple of
+    the hop (1023 and 529 samples), 2 Euler steps -- against the CPU oracle."""
+    from _cases import mel_input, noise_input
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from oracle import flow2gan_oracle as O
+    m = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    sd = synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 7)
+    m.load_state_dict(sd, strict=False)
+    m.eval()
+    mel, noise, lens = mel_input(2, 100, 4, seed=4), noise_input(2, 1023, seed=5), torch.tensor([1023, 529])
+    with torch.no_grad():
+        out = m.infer(mel, audio_lens=lens, n_timesteps=2, noise=noise)
+        ref = O.generator_infer(sd, O.generator_config("mel_24k_base"), mel, noise, lens, 2, False)
+    assert out.shape == (2, 1023) and rel_rms(out, ref) < 1e-3
