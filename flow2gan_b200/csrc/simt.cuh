@@ -63,8 +63,12 @@ inline int simt_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 #include <stdlib.h>
 #include <string.h>
 
+#include <ucontext.h>
+
+#include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #define F2G_KERNEL static
@@ -121,9 +125,9 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline thread_local f2g_dim3 threadIdx, blockIdx;
 inline f2g_dim3 blockDim, gridDim;
 
-// Cooperative kernels (shared memory, __syncthreads, warp shuffles, atomics) run with one host
-// thread per CUDA thread of a block, blocks one after the other; thread-independent kernels run as
-// plain loops (F2G_LAUNCH).  Tests only, small problems.
+// Cooperative kernels (shared memory, __syncthreads, warp shuffles, atomics) run block after block
+// with one host thread per warp (see below); thread-independent kernels run as plain loops
+// (F2G_LAUNCH).  Tests only, small problems.
 namespace f2g {
 enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
 inline char g_emul_err[512];       // one buffer for every translation unit of the emulated library
@@ -135,36 +139,140 @@ static inline void set_error(const char* fmt, ...) {
 }
 static inline int check_launch(const char*) { return 0; }
 alignas(128) inline unsigned char g_dyn_smem[228 * 1024];     // "dynamic shared memory" of the running block
-inline pthread_barrier_t g_block_bar;
-inline pthread_barrier_t g_warp_bar[32];
-inline float g_shfl[32][32];
 inline std::mutex g_atomic_mu;
+
+// Cooperative execution model: one host thread per WARP, its 32 lanes are user-level contexts
+// (ucontext) that the warp thread runs round-robin and that yield at every warp- or block-level
+// synchronisation point (shuffles, __syncwarp, __syncthreads).  A warp-level point completes when
+// every live lane of the warp has reached it; a block-level point additionally waits for the other
+// warp threads.  Exited lanes / warps count as arrived, like on the GPU.
+enum { LANE_READY = 0, LANE_WAIT_WARP = 1, LANE_WAIT_BLOCK = 2, LANE_DONE = 3 };
+constexpr size_t EMUL_STACK = 96 * 1024;
+struct EmulLane {
+  ucontext_t ctx;
+  int state;
+};
+struct EmulWarp {
+  ucontext_t sched;
+  EmulLane lane[32];
+  unsigned nlanes, base_tid, cur, phase;
+  float shfl[2][32];
+  void (*trampoline)(void*);
+  void* body;
+};
+inline thread_local EmulWarp* g_warp = nullptr;
+
+struct EmulBlockBarrier {       // barrier over the warps that have not finished the current block
+  std::mutex m;
+  std::condition_variable cv;
+  unsigned expected = 0, arrived = 0, gen = 0;
+  void reset(unsigned n) { expected = n; arrived = 0; }
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++arrived == expected) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+  }
+  void drop() {
+    std::unique_lock<std::mutex> lk(m);
+    --expected;
+    if (expected > 0 && arrived == expected) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    }
+  }
+};
+inline EmulBlockBarrier g_block_sync;
+inline pthread_barrier_t g_block_end;
+
+inline void emul_yield(int state) {
+  EmulWarp* w = g_warp;
+  w->lane[w->cur].state = state;
+  swapcontext(&w->lane[w->cur].ctx, &w->sched);
+}
+inline void emul_lane_main() {
+  EmulWarp* w = g_warp;
+  w->trampoline(w->body);
+  w->lane[w->cur].state = LANE_DONE;       // uc_link returns to the warp scheduler
+}
+
+// runs one block's worth of this warp's lanes to completion
+inline void emul_run_warp_block(EmulWarp* w, char* stacks) {
+  for (unsigned l = 0; l < w->nlanes; ++l) {
+    getcontext(&w->lane[l].ctx);
+    w->lane[l].ctx.uc_stack.ss_sp = stacks + (size_t)l * EMUL_STACK;
+    w->lane[l].ctx.uc_stack.ss_size = EMUL_STACK;
+    w->lane[l].ctx.uc_link = &w->sched;
+    makecontext(&w->lane[l].ctx, emul_lane_main, 0);
+    w->lane[l].state = LANE_READY;
+  }
+  w->phase = 0;
+  for (;;) {
+    for (unsigned l = 0; l < w->nlanes; ++l) {
+      if (w->lane[l].state != LANE_READY) continue;
+      w->cur = l;
+      threadIdx = {w->base_tid + l, 0, 0};
+      swapcontext(&w->sched, &w->lane[l].ctx);
+    }
+    unsigned n_warp = 0, n_block = 0, n_done = 0;
+    for (unsigned l = 0; l < w->nlanes; ++l) {
+      n_warp += w->lane[l].state == LANE_WAIT_WARP;
+      n_block += w->lane[l].state == LANE_WAIT_BLOCK;
+      n_done += w->lane[l].state == LANE_DONE;
+    }
+    if (n_done == w->nlanes) return;
+    if (n_warp && n_block) {
+      fprintf(stderr, "f2g emulation: lanes of one warp wait at different synchronisation points\n");
+      abort();
+    }
+    if (n_block) g_block_sync.arrive_and_wait();
+    else ++w->phase;
+    for (unsigned l = 0; l < w->nlanes; ++l)
+      if (w->lane[l].state != LANE_DONE) w->lane[l].state = LANE_READY;
+  }
+}
 
 template <typename F>
 inline void emul_run_grid(dim3 grid, dim3 block, F&& body) {
   gridDim = {grid.x, grid.y, grid.z};
   blockDim = {block.x, block.y, block.z};
   const unsigned nthreads = block.x * block.y * block.z;
-  pthread_barrier_init(&g_block_bar, nullptr, nthreads);
-  for (unsigned w = 0; w < (nthreads + 31) / 32; ++w)
-    pthread_barrier_init(&g_warp_bar[w], nullptr, nthreads - 32 * w < 32 ? nthreads - 32 * w : 32);
-  // one host thread per CUDA thread for the whole launch; the threads walk the blocks together (a
-  // barrier after each block: the next one reuses the "shared memory" statics)
+  const unsigned nwarps = (nthreads + 31) / 32;
   const unsigned nblocks = grid.x * grid.y * grid.z;
+  pthread_barrier_init(&g_block_end, nullptr, nwarps);
+  g_block_sync.reset(nwarps);
+  using Body = typename std::remove_reference<F>::type;
   std::vector<std::thread> th;
-  th.reserve(nthreads);
-  for (unsigned t = 0; t < nthreads; ++t)
-    th.emplace_back([&, t]() {
-      threadIdx = {t, 0, 0};
+  th.reserve(nwarps);
+  for (unsigned wi = 0; wi < nwarps; ++wi)
+    th.emplace_back([&, wi]() {
+      EmulWarp* w = new EmulWarp();
+      char* stacks = static_cast<char*>(malloc(32 * EMUL_STACK));
+      w->nlanes = nthreads - 32 * wi < 32 ? nthreads - 32 * wi : 32;
+      w->base_tid = 32 * wi;
+      w->trampoline = [](void* b) { (*static_cast<Body*>(b))(); };
+      w->body = const_cast<void*>(static_cast<const void*>(&body));
+      g_warp = w;
       for (unsigned b = 0; b < nblocks; ++b) {
         blockIdx = {F2G_EMUL_ORDER(b % grid.x, grid.x), (b / grid.x) % grid.y, b / (grid.x * grid.y)};
-        body();
-        pthread_barrier_wait(&g_block_bar);
+        emul_run_warp_block(w, stacks);
+        g_block_sync.drop();                                   // this warp is out of the block's barriers
+        // the block is over for every warp before its successor reuses the "shared memory" statics
+        if (pthread_barrier_wait(&g_block_end) == PTHREAD_BARRIER_SERIAL_THREAD) g_block_sync.reset(nwarps);
+        pthread_barrier_wait(&g_block_end);
       }
+      g_warp = nullptr;
+      free(stacks);
+      delete w;
     });
   for (auto& x : th) x.join();
-  pthread_barrier_destroy(&g_block_bar);
-  for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_bar[w]);
+  pthread_barrier_destroy(&g_block_end);
 }
 
 // same call shape as common.cuh's launch_pdl (programmatic dependent launch has no host meaning)
@@ -176,15 +284,14 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }  // namespace f2g
 
 #define F2G_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(f2g::g_dyn_smem)
-static inline void __syncthreads() { pthread_barrier_wait(&f2g::g_block_bar); }
-static inline void __syncwarp() { pthread_barrier_wait(&f2g::g_warp_bar[threadIdx.x >> 5]); }
+static inline void __syncthreads() { f2g::emul_yield(f2g::LANE_WAIT_BLOCK); }
+static inline void __syncwarp() { f2g::emul_yield(f2g::LANE_WAIT_WARP); }
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
-  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  f2g::g_shfl[w][l] = v;
-  pthread_barrier_wait(&f2g::g_warp_bar[w]);
-  const float r = f2g::g_shfl[w][l ^ (unsigned)o];
-  pthread_barrier_wait(&f2g::g_warp_bar[w]);
-  return r;
+  f2g::EmulWarp* w = f2g::g_warp;
+  const unsigned l = w->cur, p = w->phase & 1u;      // double-buffered: nobody is more than one phase ahead
+  w->shfl[p][l] = v;
+  f2g::emul_yield(f2g::LANE_WAIT_WARP);
+  return w->shfl[p][l ^ (unsigned)o];
 }
 static inline float atomicAdd(float* p, float v) {
   std::lock_guard<std::mutex> lk(f2g::g_atomic_mu);
