@@ -1,13 +1,16 @@
-// Portable subset for the thread-independent SIMT kernels of the data path (datapath.cu).
+// Portable layer for the SIMT kernels of this library (everything but the tcgen05 / TMA GEMMs).
 //
-// Under nvcc this is ordinary CUDA.  Under a host compiler with -DF2G_HOST_EMUL the same kernel
-// bodies run as sequential loops over (block, thread): tests/ builds that variant with g++ so the
-// index arithmetic and rounding of these kernels are checked on a machine without a GPU
-// (tests/test_datapath_cpu.py).  The emulated build is test infrastructure only -- the product
-// library never contains it and `_lib.py` never loads it.
+// Under nvcc this is ordinary CUDA (it includes common.cuh and the launch macros expand to <<<>>>).
+// Under a host compiler with -DF2G_HOST_EMUL the same kernel bodies run on the host --
+// thread-independent kernels (F2G_LAUNCH) as sequential loops over (block, thread), cooperative ones
+// (F2G_LAUNCH_COOP / launch_pdl: shared memory, barriers, shuffles, atomics) with one host thread per
+// warp whose lanes are user-level contexts -- so that tests/ can check index arithmetic, rounding and
+// the Python host layer on a machine without a GPU (tests/_emul.py, tests/test_*_cpu.py).  The
+// emulated build is test infrastructure only: the product library never contains it and `_lib.py`
+// never loads it.
 //
-// Rules for kernels written against this header: no __syncthreads, no shared memory, no warp
-// intrinsics outside f2g::simt_block_{sum,max}; every thread's work may run in any order.
+// F2G_LAUNCH kernels must not use __syncthreads, shared memory or warp intrinsics other than
+// f2g::simt_block_{sum,max}: their threads may run in any order.
 #pragma once
 
 #ifndef F2G_HOST_EMUL

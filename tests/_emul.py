@@ -1,6 +1,6 @@
 """Host emulation of the SIMT kernels written against csrc/simt.cuh (datapath.cu, losses.cu: thread-
 independent, run as sequential loops; optim.cu: cooperative -- shared memory, __syncthreads, warp
-shuffles, atomics -- run with one host thread per CUDA thread of a block): the SAME source is compiled
+shuffles, atomics -- run with one host thread per warp whose 32 lanes are ucontext fibers): the SAME source is compiled
 with g++ -DF2G_HOST_EMUL so its index arithmetic and rounding can be checked on a box without a GPU.  Test infrastructure only; the product library
 never contains this build and flow2gan_b200/_lib.py never loads it."""
 from __future__ import annotations
