@@ -130,3 +130,35 @@ def test_ragged_tiny_batch_vs_oracle(L):
         out = m.infer(mel, audio_lens=lens, n_timesteps=2, noise=noise)
         ref = O.generator_infer(sd, O.generator_config("mel_24k_base"), mel, noise, lens, 2, False)
     assert out.shape == (2, 1023) and rel_rms(out, ref) < 1e-3
+
+
+@pytest.mark.skipif(os.environ.get("F2G_SLOW_TESTS") != "1", reason="set F2G_SLOW_TESTS=1 (minutes of emulation)")
+def test_streaming_dry_run_matches_oracle_chunk_by_chunk(L):
+    """flow2gan_b200.streaming (bin/infer_dir.py:126-168) on the emulated kernels: chunked synthesis with
+    24 frames of context equals the oracle chunk by chunk; stacking the interior chunks along the batch
+    axis gives the same numbers."""
+    from _cases import mel_input, noise_input
+    from flow2gan_b200 import AttributeDict, get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from flow2gan_b200.streaming import chunk_plan, streaming_infer_audio
+    from oracle import flow2gan_oracle as O
+    m = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    sd = synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 99)
+    m.load_state_dict(sd, strict=False)
+    m.eval()
+    B, frames, chunk, hop = 1, 70, 16, 256
+    mel = mel_input(B, 100, frames, seed=5)
+    params = AttributeDict(n_timesteps=1, chunk_size=chunk)
+    plan = chunk_plan(frames, chunk, hop)
+    noises = [noise_input(B, (f1 - f0) * hop, seed=40 + i) for i, (f0, f1, _, _) in enumerate(plan)]
+    got = streaming_infer_audio(params, m, None, cond=mel, noise_fn=lambda i, shape: noises[i])
+    assert got.shape == (B, frames * hop)
+    cfg = O.generator_config("mel_24k_base")
+    ref = []
+    with torch.no_grad():
+        for (f0, f1, lp, rp), nz in zip(plan, noises):
+            a = O.generator_infer(sd, cfg, mel[:, :, f0:f1], nz, None, 1, True)
+            ref.append(a[:, lp: a.size(1) - rp])
+    assert rel_rms(got, torch.cat(ref, -1)) < 1e-3
+    got_b = streaming_infer_audio(params, m, None, cond=mel, batch_chunks=True, noise_fn=lambda i, shape: noises[i])
+    assert rel_rms(got_b, got) < 1e-5

@@ -107,3 +107,33 @@ def test_pretrain_steps_and_model_average(L):
     for k, v in tr.model_avg.state_dict().items():
         assert torch.equal(v, want[k]), k
     assert tr.batch_idx_train == 2 and tr.scheduler.batch == 2
+
+
+@slow
+def test_gan_trainer_alternates_phases_and_updates_the_stepped_half(L):
+    """GANTrainer (finetune.py:590-626) eager on the emulated kernels: D-iteration then G-iteration, only
+    the stepped half moves, schedulers advance, the loss dictionaries carry the recipe's entries."""
+    import flow2gan_b200.gan as G
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from flow2gan_b200.trainer import GANTrainer
+    g = torch.load(os.path.join(GOLDEN, "ref_gan_24k.pt"), weights_only=False)
+    gen = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    gen.branch_dropout = 0.0
+    gan = G.GAN(gen, **get_gan_config("gan_multi_scale_mel_recon"))
+    gan.load_state_dict(synth_state_dict(g["sd_spec"], g["sd_seed"]), strict=False)
+    tr = GANTrainer(gan, use_graph=False)
+    torch.manual_seed(0)
+    random.seed(0)
+    snap = lambda mod: {k: v.detach().clone() for k, v in mod.state_dict().items()}       # noqa: E731
+    g0, d0 = snap(gan.generator), snap(gan.discriminator)
+    info = tr.step(g["audio"], g["lens"])
+    assert set(info) == {"disc_loss", "disc_loss_mp", "disc_loss_mr"} and np.isfinite(float(info["disc_loss"]))
+    assert all(torch.equal(v, g0[k]) for k, v in gan.generator.state_dict().items())
+    assert sum(not torch.equal(v, d0[k]) for k, v in gan.discriminator.state_dict().items()) > 200
+    d1 = snap(gan.discriminator)
+    info = tr.step(g["audio"], g["lens"])
+    assert set(info) == {"gen_loss", "mel_recon_loss"} and np.isfinite(float(info["gen_loss"]))
+    assert all(torch.equal(v, d1[k]) for k, v in gan.discriminator.state_dict().items())
+    assert sum(not torch.equal(v, g0[k]) for k, v in gan.generator.state_dict().items()) > 400
+    assert tr.sched_d.batch == 1 and tr.sched_g.batch == 1 and tr.train_disc
