@@ -131,3 +131,17 @@ def test_logmel_44k_and_dc_peak(L):
     mean = a.mean(-1)
     sc = 0.8 / ((a - mean[:, None]).abs().max(-1)[0] + 1e-9)
     assert rel_rms(pre, torch.stack([mean, sc], 1)) < 1e-5
+
+
+def test_too_short_signals_are_refused_like_torch_stft(L):
+    """torch.stft(center=True, pad_mode="reflect") raises when n_fft // 2 >= T; the kernels would
+    otherwise reflect out of bounds."""
+    x = torch.zeros(1, 256)
+    with pytest.raises(RuntimeError, match="signal too short"):
+        L.stft(x, 1, 256, 256, 512, 128, L.SPEC_PACKED, torch.empty(3, 520), 520)
+    with pytest.raises(RuntimeError, match="signal too short"):
+        L.stft_group([(x, torch.empty(5, 516), 512, 256, 2, 2, 256, 516)], 1, 256, round_tf32=0)
+    with pytest.raises(RuntimeError, match="power of two"):
+        L.stft(torch.zeros(1, 4000), 1, 4000, 4000, 384, 96, L.SPEC_PACKED, torch.empty(42, 392), 392)
+    with pytest.raises(RuntimeError):
+        torch.stft(x, 512, 128, window=torch.hann_window(512), center=True, pad_mode="reflect", return_complex=True)
