@@ -137,3 +137,27 @@ def test_gan_trainer_alternates_phases_and_updates_the_stepped_half(L):
     assert all(torch.equal(v, d1[k]) for k, v in gan.discriminator.state_dict().items())
     assert sum(not torch.equal(v, g0[k]) for k, v in gan.generator.state_dict().items()) > 400
     assert tr.sched_d.batch == 1 and tr.sched_g.batch == 1 and tr.train_disc
+
+
+def test_fm_loss_ragged_batch_gradients_vs_oracle_autograd(L):
+    """Edge shape for the backward kernels: T = 1100 (no hop multiple), lengths (1100, 700), per-sample
+    t -- loss and the whole parameter-gradient vector against autograd of the CPU oracle."""
+    from _cases import audio_input, noise_input
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from oracle import flow2gan_oracle as O
+    m = MelAudioGenerator(**get_generator_config("mel_24k_base")).eval()
+    sd = synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 21)
+    m.load_state_dict(sd, strict=False)
+    audio, lens = audio_input(2, 1100, seed=3), torch.tensor([1100, 700])
+    audio[1, 700:] = 0
+    mel, noise, t = O.log_mel(audio), noise_input(2, 1100, seed=4), torch.tensor([[0.3], [0.8]])
+    loss = m(cond=mel, audio=audio, audio_lens=lens, noise=noise, t=t)
+    loss.backward()
+    leaves = {k: v.clone().requires_grad_(not (k.endswith("window") or k.endswith(".fb"))) for k, v in sd.items()}
+    ref = O.fm_loss(leaves, O.generator_config("mel_24k_base"), mel, audio, lens, noise, t)
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 2e-3 * float(ref.detach())
+    num = sum(float((p.grad.double() - leaves[k].grad.double()).pow(2).sum()) for k, p in m.named_parameters())
+    den = sum(float(leaves[k].grad.double().pow(2).sum()) for k, _ in m.named_parameters())
+    assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
