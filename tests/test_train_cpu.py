@@ -161,3 +161,40 @@ def test_fm_loss_ragged_batch_gradients_vs_oracle_autograd(L):
     num = sum(float((p.grad.double() - leaves[k].grad.double()).pow(2).sum()) for k, p in m.named_parameters())
     den = sum(float(leaves[k].grad.double().pow(2).sum()) for k, _ in m.named_parameters())
     assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
+
+
+def test_gan_phases_odd_length_ragged_vs_oracle_autograd(L, monkeypatch):
+    """Edge shape for the discriminators: T = 2500 (reflect padding for periods 3 / 7 / 11, five frames
+    for the 2048-point MRD), lengths (2500, 1800).  Losses to 2e-3; the whole gradient vector of the
+    stepped half to 8e-2 -- at this size a handful of LeakyReLU branch flips under TF32 operand rounding
+    already cost 4e-2 (the golden-size case above is gated at 3e-2)."""
+    import flow2gan_b200.gan as G
+    from _cases import audio_input, noise_input
+    from flow2gan_b200 import get_gan_config, get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from oracle import flow2gan_oracle as O
+    monkeypatch.setattr(G, "FUSED_LOSSES", False)
+    gen = MelAudioGenerator(**get_generator_config("mel_24k_base"))
+    gen.branch_dropout = 0.0
+    gan = G.GAN(gen, **get_gan_config("gan_multi_scale_mel_recon"))
+    sd = synth_state_dict([(k, tuple(v.shape)) for k, v in gan.state_dict().items()], 77)
+    gan.load_state_dict(sd, strict=False)
+    cfg = O.generator_config("mel_24k_base")
+    audio, lens = audio_input(2, 2500, seed=8), torch.tensor([2500, 1800])
+    audio[1, 1800:] = 0
+    mel, noise = O.log_mel(audio), noise_input(2, 2500, seed=9)
+    monkeypatch.setattr(random, "random", lambda: 0.99)          # limit_param_value hook off on both sides
+    for disc, w in ((True, (1.0, 0.1)), (False, (1.0, 0.1, 1.0, 0.1, 45.0))):
+        gan.zero_grad()
+        losses = gan(cond=mel, audio=audio, audio_lens=lens, n_timesteps=1, train_disc=disc, noise=noise)
+        sum(l * wi for l, wi in zip(losses, w)).backward()
+        pre = "discriminator." if disc else "generator."
+        leaves = {k: v.clone().requires_grad_(k.startswith(pre)) for k, v in sd.items()}
+        ref = O.gan_forward(leaves, cfg, mel, audio, noise, lens, 1, disc, limit=False)
+        sum(l * wi for l, wi in zip(ref, w)).backward()
+        got, rf = torch.stack([l.detach() for l in losses]), torch.stack([l.detach() for l in ref])
+        assert float(((got - rf).abs() / rf.abs()).max()) < 2e-3, (disc, got, rf)
+        sub = gan.discriminator if disc else gan.generator
+        num = sum(float((p.grad.double() - leaves[pre + k].grad.double()).pow(2).sum()) for k, p in sub.named_parameters())
+        den = sum(float(leaves[pre + k].grad.double().pow(2).sum()) for k, _ in sub.named_parameters())
+        assert (num / den) ** 0.5 < 8e-2, (disc, (num / den) ** 0.5)
