@@ -41,6 +41,11 @@ F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v));
 }
+F2G_SIMT_DEV float4 unpack_half4(uint2 u) {
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 F2G_SIMT_DEV float simt_fmul(float a, float b) { return __fmul_rn(a, b); }
 F2G_SIMT_DEV float simt_fadd(float a, float b) { return __fadd_rn(a, b); }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -381,6 +386,15 @@ F2G_SIMT_DEV unsigned short half_bits_sat(float v) {
 F2G_SIMT_DEV uint2 pack_half4(float4 v) {
   return make_uint2((unsigned)half_bits_sat(v.x) | ((unsigned)half_bits_sat(v.y) << 16),
                     (unsigned)half_bits_sat(v.z) | ((unsigned)half_bits_sat(v.w) << 16));
+}
+F2G_SIMT_DEV float half_bits_to_float(unsigned short b) {
+  _Float16 h;
+  memcpy(&h, &b, 2);
+  return (float)h;
+}
+F2G_SIMT_DEV float4 unpack_half4(uint2 u) {
+  return make_float4(half_bits_to_float((unsigned short)(u.x & 0xffffu)), half_bits_to_float((unsigned short)(u.x >> 16)),
+                     half_bits_to_float((unsigned short)(u.y & 0xffffu)), half_bits_to_float((unsigned short)(u.y >> 16)));
 }
 F2G_SIMT_DEV void pdl_wait() {}
 F2G_SIMT_DEV void pdl_launch() {}

@@ -40,6 +40,10 @@ assert BLOCK_OPERANDS in ("f16", "tf32"), BLOCK_OPERANDS
 # boundary; fp16 operands only)
 CHAIN_MLP = os.environ.get("F2G_CHAIN_MLP", "1") == "1"
 FORK_COND = os.environ.get("F2G_FORK_COND", "1") == "1"    # conditioning path on a second stream
+# F2G_F16_COND=1 (experiment, fp16 block operands only): the cond_proj GEMM stores its (Rc, 8C) output as
+# fp16 and the block prologue reads it as such -- halves the bytes of the launch that closes the
+# conditioning path (it is on the critical path of 1-step inference)
+F16_COND = os.environ.get("F2G_F16_COND", "0") == "1"
 
 
 def _ceil(a: int, b: int) -> int:
@@ -230,7 +234,7 @@ class InferencePlan:
             w.ts = z(1, bw.nl * bw.C)
             w.cm_h = zo(self.Rc, bw.ch)       # cond_mlp hidden / output: GEMM operands only
             w.c1 = zo(self.Rc, bw.cc)
-            w.cp = z(self.Rc, bw.nl * bw.C)
+            w.cp = (zo if F16_COND and BLOCK_OPERANDS == "f16" else z)(self.Rc, bw.nl * bw.C)
             w.mask = z(w.R) if masked else None
             self.br.append(w)
         # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
@@ -300,8 +304,9 @@ class InferencePlan:
                                       bw.ch, bw.ch, bw.cc, bias=cm[2].bias.data_ptr(), act=L.ACT_LEAKY,
                                       leaky=1.0, ab_f16=1, c_f16=1, wait_counter=cnt))
                 N = bw.nl * bw.C
+                kw3 = dict(act=L.ACT_LEAKY, leaky=1.0, c_f16=1) if w.cp.dtype == torch.float16 else {}
                 g3.append(L.gemm_desc(w.c1.data_ptr(), Wc.data_ptr(), w.cp.data_ptr(), Rc, N, bw.cc,
-                                      bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1))
+                                      bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1, **kw3))
             if self.chained:
                 L.gemm_group(g0 + g2)
             else:

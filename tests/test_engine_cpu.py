@@ -162,3 +162,19 @@ def test_streaming_dry_run_matches_oracle_chunk_by_chunk(L):
     assert rel_rms(got, torch.cat(ref, -1)) < 1e-3
     got_b = streaming_infer_audio(params, m, None, cond=mel, batch_chunks=True, noise_fn=lambda i, shape: noises[i])
     assert rel_rms(got_b, got) < 1e-5
+
+
+def test_fp16_conditioning_rows_keep_parity(L, monkeypatch):
+    """F2G_F16_COND (opt-in): cond_proj output stored as fp16, read by the fp16-cond instantiation of the
+    block prologue.  Same golden case as above; the parity number must stay at the fp16-operand level."""
+    import flow2gan_b200.engine as E
+    monkeypatch.setattr(E, "F16_COND", True)
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    m = _model(g)
+    with torch.no_grad():
+        out = m.infer(g["mel"], n_timesteps=1, noise=g["noise"])
+        plan = next(iter(m._plans.values()))
+        assert all(w.cp.dtype == torch.float16 for w in plan.br)
+    err = rel_rms(out, g["audio_n1"])
+    print("fp16 conditioning rows: rel-RMS vs reference", err)
+    assert err < 1e-3

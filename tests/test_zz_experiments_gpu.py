@@ -47,3 +47,12 @@ def test_pair_bn_hint_keeps_inference_output(tmp_path):
     assert torch.isfinite(base).all() and base.shape == (16, 24064)
     rel = float((base - hint).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
     assert rel < 1e-6, rel
+
+
+def test_fp16_conditioning_rows_keep_inference_output(tmp_path):
+    """F2G_F16_COND=1 rounds the cond_proj output to fp16 (11 significant bits) before the block prologue
+    adds it: the output moves by far less than the 1e-3 parity budget."""
+    base = _run_arm(tmp_path, "base2", {"F2G_F16_COND": "0"})
+    f16 = _run_arm(tmp_path, "f16cond", {"F2G_F16_COND": "1"})
+    rel = float((base - f16).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
+    assert 0.0 < rel < 3e-4, rel

@@ -29,6 +29,13 @@ for l in open('gpurun_out/bench_bn_hint.json'):
     if l.startswith('{'):
         d = json.loads(l); print('bn hint: ms/step %.3f gemm frac %.3f' % (d['ms_per_step'], d['roofline']['frac']))
 P
+F2G_F16_COND=1 timeout 900 python bench.py --no-train > gpurun_out/bench_f16_cond.json 2> gpurun_out/bench_f16_cond.err
+python - <<'P'
+import json
+for l in open('gpurun_out/bench_f16_cond.json'):
+    if l.startswith('{'):
+        d = json.loads(l); print('fp16 cond rows: ms/step %.3f e2e %.1fM' % (d['ms_per_step'], d['e2e']['value'] / 1e6))
+P
 bash tools/gpu_run_fabric.sh
 timeout 900 python tools/train_glue_census.py 30 > gpurun_out/train_glue_census.log 2>&1; head -20 gpurun_out/train_glue_census.log
 [ "$1" = "noprof" ] && exit 0
