@@ -44,6 +44,10 @@ FORK_COND = os.environ.get("F2G_FORK_COND", "1") == "1"    # conditioning path o
 # fp16 and the block prologue reads it as such -- halves the bytes of the launch that closes the
 # conditioning path (it is on the critical path of 1-step inference)
 F16_COND = os.environ.get("F2G_F16_COND", "0") == "1"
+# F2G_CACHE_TIME=1 (experiment): the sampler evaluates every batch element at the same t_k = k / N, so the
+# per-layer time-scale vectors of step k depend on the weights only: compute them once per (plan, N)
+# instead of in every model evaluation (4 small launches per ODE step leave the launch graph)
+CACHE_TIME = os.environ.get("F2G_CACHE_TIME", "0") == "1"
 
 
 def _ceil(a: int, b: int) -> int:
@@ -250,6 +254,7 @@ class InferencePlan:
         self.chain = torch.zeros(tot, device=dev, dtype=torch.int32)
         self.chain_off = offs
         self.t_all: Optional[Tensor] = None
+        self._ts_cache: Dict[int, list] = {}        # F2G_CACHE_TIME: n -> per step -> per branch (1, nl*C)
         self._side: Optional[torch.cuda.Stream] = None
         self.graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
         self._seen: Dict[Tuple[int, bool], bool] = {}
@@ -340,9 +345,9 @@ class InferencePlan:
         self.process_front(t_dev)
         self.process_blocks()
 
-    def process_front(self, t_dev: Tensor) -> None:
+    def process_front(self, t_dev: Tensor, with_time: bool = True) -> None:
         """The part of one model evaluation that does not read the conditioning: STFT, in_proj,
-        in_norm and the time-embedding path."""
+        in_norm and (unless the step's vectors are cached) the time-embedding path."""
         pk, B, T, Fm = self.pk, self.B, self.T, self.Fm
         L.stft_group([(self.x_audio, w.pin, bw.n_fft, bw.hop, w.F, w.R, T, bw.ldp)
                       for bw, w in zip(pk.branches, self.br)], B, T, round_tf32=1)
@@ -351,6 +356,13 @@ class InferencePlan:
                       for bw, w in zip(pk.branches, self.br)])
         for bw, w in zip(pk.branches, self.br):
             L.biasnorm(w.x, w.R, bw.C, bw.C, bw.dec.in_norm.bias, bw.dec.in_norm.log_scale, w.x, bw.C)
+        if with_time:
+            self.time_path(t_dev)
+
+    def time_path(self, t_dev: Tensor) -> None:
+        """SinusoidalPosEmb -> time_mlp -> the 8 time_embed_proj of every branch, for ONE row (all batch
+        elements share t at inference); writes w.ts."""
+        pk = self.pk
         L.time_sinusoid(t_dev, 1, self.te_dim, self.freqs, 1000.0, self.emb)
         prob1, prob2, prob3 = [], [], []
         for bw, w in zip(pk.branches, self.br):
@@ -410,6 +422,14 @@ class InferencePlan:
         # built on the device (no host->device copy: this also runs under stream capture)
         self.t_all = torch.linspace(0, 1, n + 1, device=self.x_audio.device)[:n].unsqueeze(1) \
             .expand(n, self.B).contiguous()
+        if CACHE_TIME and n not in self._ts_cache:
+            per_step = []
+            for k in range(n):
+                for w in self.br:
+                    w.ts = torch.zeros_like(w.ts)
+                self.time_path(self.t_all[k])
+                per_step.append([w.ts for w in self.br])
+            self._ts_cache[n] = per_step
         return ts, dt
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
@@ -436,13 +456,17 @@ class InferencePlan:
             with torch.cuda.stream(self._side):
                 self.encode_cond()
                 join.record(self._side)
-            self.process_front(self.t_all[0])
+            self.process_front(self.t_all[0], with_time=not (CACHE_TIME and n in self._ts_cache))
             main.wait_event(join)
         elif with_cond:
             self.encode_cond()
+        cached = self._ts_cache.get(n) if CACHE_TIME else None
         for k in range(n):
             if not (forked and k == 0):
-                self.process_front(self.t_all[k])
+                self.process_front(self.t_all[k], with_time=cached is None)
+            if cached is not None:
+                for w, ts_k in zip(self.br, cached[k]):
+                    w.ts = ts_k
             self.process_blocks()
             self.combine(self.x_audio, True, ts[k], dt, clamp and k == n - 1)
 

@@ -178,3 +178,22 @@ def test_fp16_conditioning_rows_keep_parity(L, monkeypatch):
     err = rel_rms(out, g["audio_n1"])
     print("fp16 conditioning rows: rel-RMS vs reference", err)
     assert err < 1e-3
+
+
+def test_cached_time_path_is_bit_identical(L, monkeypatch):
+    """F2G_CACHE_TIME (opt-in): per-step time-scale vectors computed once per (plan, N) -- the 2-step
+    output must equal the uncached run bit for bit (same kernels, same inputs, fewer launches)."""
+    import flow2gan_b200.engine as E
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    outs, counts = [], []
+    for flag in (False, True):
+        monkeypatch.setattr(E, "CACHE_TIME", flag)
+        m = _model(g)
+        with torch.no_grad():
+            m.infer(g["mel"], n_timesteps=2, noise=g["noise"])          # first call builds plan (+ cache)
+            L.COUNT = 0
+            outs.append(m.infer(g["mel"], n_timesteps=2, noise=g["noise"]).clone())
+            counts.append(L.COUNT)
+    assert torch.equal(outs[0], outs[1])
+    assert counts[1] == counts[0] - 2 * 4, counts                     # 4 launches per ODE step left the sequence
+    assert rel_rms(outs[1], g["audio_n2"]) < 1e-3

@@ -56,3 +56,10 @@ def test_fp16_conditioning_rows_keep_inference_output(tmp_path):
     f16 = _run_arm(tmp_path, "f16cond", {"F2G_F16_COND": "1"})
     rel = float((base - f16).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
     assert 0.0 < rel < 3e-4, rel
+
+
+def test_cached_time_path_keeps_inference_output_bit_identical(tmp_path):
+    """F2G_CACHE_TIME=1 only moves the time-embedding launches out of the per-step sequence."""
+    base = _run_arm(tmp_path, "base3", {"F2G_CACHE_TIME": "0"})
+    cached = _run_arm(tmp_path, "cached", {"F2G_CACHE_TIME": "1"})
+    assert torch.equal(base, cached)

@@ -36,6 +36,17 @@ for l in open('gpurun_out/bench_f16_cond.json'):
     if l.startswith('{'):
         d = json.loads(l); print('fp16 cond rows: ms/step %.3f e2e %.1fM' % (d['ms_per_step'], d['e2e']['value'] / 1e6))
 P
+for n in 2 4; do
+  for c in 0 1; do
+    F2G_CACHE_TIME=$c timeout 900 python bench.py --no-train --n-timesteps $n --steps 30 > gpurun_out/bench_n${n}_cache$c.json 2> gpurun_out/bench_n${n}_cache$c.err
+    python - gpurun_out/bench_n${n}_cache$c.json <<'P'
+import json, sys
+for l in open(sys.argv[1]):
+    if l.startswith('{'):
+        d = json.loads(l); print(sys.argv[1], 'ms/step %.3f' % d['ms_per_step'])
+P
+  done
+done
 bash tools/gpu_run_fabric.sh
 timeout 900 python tools/train_glue_census.py 30 > gpurun_out/train_glue_census.log 2>&1; head -20 gpurun_out/train_glue_census.log
 [ "$1" = "noprof" ] && exit 0
