@@ -29,7 +29,19 @@ torch.save(out.cpu(), {out!r})
 '''
 
 
+_ARMS = {}
+
+
 def _run_arm(tmp_path, name, env):
+    """One interpreter per distinct switch setting (cached across the tests of this module: all
+    switches default to off, so the three "base" arms are the same run)."""
+    key = tuple(sorted((k, v) for k, v in env.items() if v != "0"))
+    if key not in _ARMS:
+        _ARMS[key] = _spawn_arm(tmp_path, name, env)
+    return _ARMS[key]
+
+
+def _spawn_arm(tmp_path, name, env):
     out = str(tmp_path / f"{name}.pt")
     e = dict(os.environ)
     e.update(env)
