@@ -45,6 +45,11 @@ METRIC = "audio samples/sec (bs=16, 1s, 24 kHz) 1-step infer + GAN train step @1
 REF_FLOPS = {1: 347.6e9, 2: 675.8e9, 4: 1332.2e9}   # SURVEY.md section 8(d), conv/matmul FLOPs
 
 
+def workload_name(n_timesteps: int) -> str:
+    """`config.workload` of both arms (BASELINE.json configs[1])."""
+    return f"{MODEL} {n_timesteps}-step inference, synthetic mel (16,100,94) -> (16,24064) per GPU"
+
+
 def synth_inputs():
     from _cases import mel_input, noise_input
     return mel_input(B, N_MELS, FRAMES, seed=0), noise_input(B, T, seed=1)
@@ -218,7 +223,7 @@ def run_reference(args):
         "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL} {args.n_timesteps}-step inference, synthetic mel (16,100,94) -> (16,24064)",
+        "config": {"workload": workload_name(args.n_timesteps),
                    "global_batch": B, "note": "CPU oracle port of the reference PyTorch path (reference is "
                    "Python and cannot travel to the GPU box); bounded sample of %d steps" % steps},
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -415,7 +420,7 @@ def run_ours(args):
         "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16/tf32 operands -> f32 accumulate", "data": "synthetic",
-        "config": {"workload": f"{MODEL} {n}-step inference, synthetic mel (16,100,94) -> (16,24064) per GPU",
+        "config": {"workload": workload_name(n),
                    "global_batch": B * world, "parallelism": f"replicas x{world} (no data-path collective)",
                    "weights": "synthetic (seeded), reference state_dict layout",
                    "l2": "no explicit flush: every step streams its packed weights (~185 MB: fp16 block / conditioning "
