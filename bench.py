@@ -17,9 +17,10 @@ configuration).  Prints ONE JSON line (rank 0).
                bf16/fp16 tensor peak; `roofline_other` = the remaining TF32 GEMM launches;
                `roofline_hbm` = the block-prologue launches (dominant HBM-bound kernel) the same way;
                `traffic` = dram bytes per launch from the committed ncu capture (profiles/).
-  cpu_baseline / --impl reference : the oracle port (oracle/flow2gan_oracle.py, a functional
-               restatement of the reference's PyTorch path; the reference itself is Python and
-               cannot travel to the GPU box) on the host cores, bounded sample.
+  cpu_baseline / --impl reference : the UNMODIFIED reference (staged by tools/stage_reference.sh under
+               the git-ignored baseline/_ref/, which ships to the GPU box) through its own public API
+               get_model(checkpoint=...) -> model.infer on the host cores, bounded sample; falls back to
+               the oracle port (kind "port") only when baseline/_ref is absent.
 """
 from __future__ import annotations
 
@@ -126,41 +127,91 @@ def build_model(device):
     return m.to(device).eval()
 
 
-def cpu_oracle_rate(n_timesteps: int, iters: int, warmup: int = 1):
-    from oracle import flow2gan_oracle as O
-    from _synth import synth_state_dict
-    from flow2gan_b200 import get_generator_config
-    from flow2gan_b200.generator import MelAudioGenerator
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")       # tools/stage_reference.sh (git-ignored, ships with gpurun)
+
+
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (lhotse stubbed as in SURVEY.md App. B:
+    it is imported for type names / seed helpers only).  Returns the `flow2gan` module or None."""
+    if not os.path.isdir(os.path.join(REF_DIR, "flow2gan")):
+        return None
+    import types
+    l = types.ModuleType("lhotse")
+    l.__version__, l.__file__, l.RecordingSet = "stub", "/dev/null", object
+    for nm in ("lhotse.dataset", "lhotse.dataset.sampling", "lhotse.dataset.sampling.base", "lhotse.utils"):
+        sys.modules.setdefault(nm, types.ModuleType(nm))
+    sys.modules.setdefault("lhotse", l)
+    sys.modules["lhotse.dataset.sampling.base"].CutSampler = object
+    sys.modules["lhotse.utils"].fix_random_seed = lambda s: None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import flow2gan
+    return flow2gan
+
+
+def _best_threads(call, candidates=(8, 16, 32)):
+    """The reference's CPU path (mkldnn convs on short sequences) stops scaling well before a big
+    host's core count (measured on the 128-core B200 host: 16 threads 0.40 s/call, 64 threads
+    0.88 s, 128 threads > 20 s) -- give the baseline its best thread count."""
     ncpu = os.cpu_count() or 1
-    m = MelAudioGenerator(**get_generator_config(MODEL))
-    spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
-    sd = synth_state_dict(spec, 99)
-    cfg = O.generator_config(MODEL)
-    mel, noise = synth_inputs()
-    # The reference's CPU path (mkldnn convs on small sequences) stops scaling well before a
-    # big host's core count (measured on the 128-core B200 host: 16 threads 0.40 s/call, 64
-    # threads 0.88 s, 128 threads > 20 s) -- give the baseline its best thread count.
     best, cores = None, 1
-    with torch.inference_mode():
-        for th in sorted({min(ncpu, c) for c in (8, 16, 32)}):
-            torch.set_num_threads(th)
-            O.generator_infer(sd, cfg, mel[:4], noise[:4], None, 1, False)
-            t0 = time.perf_counter()
-            O.generator_infer(sd, cfg, mel[:4], noise[:4], None, 1, False)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, cores = dt, th
+    for th in sorted({min(ncpu, c) for c in candidates}):
+        torch.set_num_threads(th)
+        call()
+        t0 = time.perf_counter()
+        call()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, th
     torch.set_num_threads(cores)
+    return cores
+
+
+def cpu_reference_rate(n_timesteps: int, iters: int, warmup: int = 1):
+    """CPU arm.  kind == "reference": the reference's own code through its own public API --
+    flow2gan.get_model(checkpoint=...) -> model.infer(cond, n_timesteps) (flow2gan/__init__.py:29-47,
+    models/generator.py:327-366), same synthetic weights (saved as a {"model": state_dict} checkpoint,
+    the released-checkpoint format) and the same mel batch as the GPU arm.  kind == "port": the
+    oracle restatement, only when baseline/_ref is absent."""
+    from _synth import synth_state_dict
+    mel, noise = synth_inputs()
+    ref = import_reference()
+    if ref is not None:
+        import tempfile
+        from flow2gan.models.config import get_generator_config as ref_cfg
+        from flow2gan.models.generator import MelAudioGenerator as RefGen
+        import contextlib, io
+        m0 = RefGen(**ref_cfg(MODEL))
+        like = m0.state_dict()
+        sd = synth_state_dict([(k, tuple(v.shape)) for k, v in like.items()], 99, like=like)
+        with tempfile.TemporaryDirectory() as td:
+            ck = os.path.join(td, "synthetic.pt")
+            torch.save({"model": sd}, ck)
+            with contextlib.redirect_stdout(io.StringIO()):          # get_model prints the checkpoint path
+                model, _ = ref.get_model(model_name=MODEL, hf_model_name=None, checkpoint=ck)
+        model.eval()
+        call = lambda b=B: model.infer(cond=mel[:b], n_timesteps=n_timesteps)
+        kind = "reference"
+    else:
+        from oracle import flow2gan_oracle as O
+        from flow2gan_b200 import get_generator_config
+        from flow2gan_b200.generator import MelAudioGenerator
+        m = MelAudioGenerator(**get_generator_config(MODEL))
+        sd = synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 99)
+        cfg = O.generator_config(MODEL)
+        call = lambda b=B: O.generator_infer(sd, cfg, mel[:b], noise[:b], None, n_timesteps, False)
+        kind = "port"
     times = []
     with torch.inference_mode():
+        cores = _best_threads(lambda: call(4))
         for i in range(warmup + iters):
             t0 = time.perf_counter()
-            O.generator_infer(sd, cfg, mel, noise, None, n_timesteps, False)
+            call()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     tot = sum(times)
-    return SAMPLES_PER_STEP * len(times) / tot, tot / len(times) * 1e3, cores
+    return SAMPLES_PER_STEP * len(times) / tot, tot / len(times) * 1e3, cores, kind
 
 
 def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
@@ -210,24 +261,37 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
                         "(world>1), ScaledAdam.step, Eden2"}
 
 
+def config_for(n_timesteps: int, world: int) -> dict:
+    """`config` of BOTH arms (identical keys and values: the workload, nothing arm specific)."""
+    return {"workload": workload_name(n_timesteps), "model": MODEL, "n_timesteps": n_timesteps,
+            "batch_per_gpu": B, "global_batch": B * world, "mel_shape": [B, N_MELS, FRAMES],
+            "samples_per_step_per_gpu": SAMPLES_PER_STEP,
+            "parallelism": f"replicas x{world} (no data-path collective)",
+            "weights": "synthetic (seeded, tests/_synth.py seed 99), reference state_dict layout",
+            "l2": "no explicit flush: every step streams > 126 MB (packed weights ~185 MB + ~90 MB of activations)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # every requested step is timed (one step = one bs-16 x 1 s call, 0.3-0.9 s on the host cores);
     # the cap only guards against a K that would run for many minutes
-    steps = max(1, min(args.steps, 100))
-    rate, ms, cores = cpu_oracle_rate(args.n_timesteps, steps, warmup=min(args.warmup, 1))
+    steps = max(1, min(args.steps, 200))
+    W = max(3, args.warmup)
+    rate, ms, cores, kind = cpu_reference_rate(args.n_timesteps, steps, warmup=W)
+    what = ("the UNMODIFIED reference (baseline/_ref/flow2gan): get_model(checkpoint=synthetic) -> model.infer"
+            if kind == "reference" else
+            "oracle/flow2gan_oracle.py (baseline/_ref absent: run tools/stage_reference.sh where /root/reference is mounted)")
     line = {
         "impl": "reference", "metric": METRIC, "metric_part": "%d-step infer" % args.n_timesteps,
-        "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": W,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.n_timesteps),
-                   "global_batch": B, "note": "CPU oracle port of the reference PyTorch path (reference is "
-                   "Python and cannot travel to the GPU box); bounded sample of %d steps" % steps},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} x (bs=16, 1 s) {args.n_timesteps}-step calls"},
+        "config": config_for(args.n_timesteps, args.gpus),
+        "notes": {"arm": what, "torch_threads": cores},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} x (bs=16, 1 s) {args.n_timesteps}-step calls after {W} warm-up calls"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -414,18 +478,15 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-    cpu_rate, cpu_ms, cores = cpu_oracle_rate(n, iters=3 if n == 1 else 1) if world == 1 else (None, None, None)
+    cpu_rate, cpu_ms, cores, cpu_kind = (cpu_reference_rate(n, iters=8 if n == 1 else 3) if world == 1
+                                         else (None, None, None, None))
     line = {
         "metric": METRIC, "metric_part": "%d-step infer (`value`, `e2e`); GAN train step pair under `gan_train`" % n,
         "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16/tf32 operands -> f32 accumulate", "data": "synthetic",
-        "config": {"workload": workload_name(n),
-                   "global_batch": B * world, "parallelism": f"replicas x{world} (no data-path collective)",
-                   "weights": "synthetic (seeded), reference state_dict layout",
-                   "l2": "no explicit flush: every step streams its packed weights (~185 MB: fp16 block / conditioning "
-                         "matrices + TF32 projections) plus ~90 MB of activations, more than the 126 MB L2",
-                   "timed": "K CUDA-graph replays between two CUDA events"},
+        "config": config_for(n, world),
+        "notes": {"timed": "K CUDA-graph replays between two CUDA events"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * N_MELS * FRAMES * 4,
                 "d2h_bytes_per_step": B * T * 4},
         "gpu_launches": launches_per_step * K,
@@ -439,8 +500,8 @@ def run_ours(args):
     if train is not None:
         line["gan_train"] = train
     if cpu_rate is not None:
-        line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": f"{3 if n == 1 else 1} x (bs=16, 1 s) {n}-step calls, {cpu_ms:.0f} ms each"}
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": cpu_kind,
+                                "sample": f"{8 if n == 1 else 3} x (bs=16, 1 s) {n}-step calls, {cpu_ms:.0f} ms each"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

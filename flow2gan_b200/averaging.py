@@ -124,7 +124,10 @@ def average_checkpoints(filenames, device: torch.device = torch.device("cuda")) 
     """Plain mean of the `model` entries of several checkpoints (checkpoint.py:171-212, used by
     bin/save_averaged_model.py:148-157).  The running sums are one `f2g_average_update` launch per
     checkpoint (v * 1 + cur * 1 is the reference's fp32 `avg[k] += state_dict[k]` bit for bit); the
-    final division keeps torch's true-division rounding (one multi-tensor op)."""
+    final division is the reference's own op on the same device, `avg[k] /= n` per tensor
+    (checkpoint.py:207-210) -- on CUDA torch evaluates a tensor / python-scalar division as a
+    multiplication by the fp32 reciprocal, which differs from true division by up to 1 ulp, so the
+    result is whatever the reference produces on that device, bit for bit."""
     n = len(filenames)
     avg = torch.load(filenames[0], map_location=device, weights_only=False)["model"]
     keys = unique_float_keys(avg)
@@ -139,9 +142,8 @@ def average_checkpoints(filenames, device: torch.device = torch.device("cuda")) 
         average_state_dict(avg, sd, 1.0, 1.0)
         for k in int_keys:
             avg[k] += sd[k]
-    floats = [avg[k] for k in keys if avg[k].numel() > 0]
-    if floats:
-        torch._foreach_div_(floats, n)
+    for k in keys:
+        avg[k] /= n
     for k in int_keys:
         avg[k] //= n
     return avg
