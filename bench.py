@@ -68,7 +68,7 @@ class ClockSampler:
     """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks line')."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index: int):
         self.index = index
@@ -98,7 +98,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, sm_load, mx, reasons, pw = [], [], [], set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -107,13 +107,20 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+                if len(f) > 9 and float(f[9]) >= 50.0:
+                    sm_load.append(float(f[1]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
                                f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        use = sorted(sm_load if sm_load else sm)         # median over the samples taken under load
+        return {"sm_mhz": use[len(use) // 2] if use else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(sm_load), "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons)}
 
 
 def build_model(device):
@@ -214,6 +221,118 @@ def cpu_reference_rate(n_timesteps: int, iters: int, warmup: int = 1):
     return SAMPLES_PER_STEP * len(times) / tot, tot / len(times) * 1e3, cores, kind
 
 
+def build_model_named(device, model_name: str, seed: int = 99):
+    from flow2gan_b200 import get_generator_config
+    from flow2gan_b200.generator import MelAudioGenerator
+    from _synth import synth_state_dict
+    torch.manual_seed(0)
+    m = MelAudioGenerator(**get_generator_config(model_name))
+    spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    m.load_state_dict(synth_state_dict(spec, seed), strict=False)
+    return m.to(device).eval()
+
+
+# reference-equivalent conv/matmul FLOPs of one bs-16 call
+LEGS = {  # key: (model, n_mels, frames, hop, n_timesteps, mel scale, mel shift, reference-equivalent FLOPs)
+    "infer_n2": ("mel_24k_base", 100, 94, 256, 2, 1.7, -1.6, 675.8e9),
+    "infer_n4": ("mel_24k_base", 100, 94, 256, 4, 1.7, -1.6, 1332.2e9),
+    "infer_44k_n4": ("mel_44k_128band_512x_base", 128, 87, 512, 4, 1.4, 0.2, 1252.9e9),
+}
+
+
+def extra_infer_leg(dev, key: str, steps: int, warmup: int, model=None):
+    """BASELINE.json configs[1] (2 / 4 ODE steps) and configs[3] (44.1 kHz family, 4 steps): K graph
+    replays between two CUDA events, inputs resident in HBM, plus the same call end to end through
+    model.infer with pinned host buffers."""
+    name, n_mels, frames, hop, n, sc, sh, flops = LEGS[key]
+    m = model if model is not None else build_model_named(dev, name)
+    T_ = frames * hop
+    g = torch.Generator().manual_seed(0)
+    mel_h = torch.randn(B, n_mels, frames, generator=g) * sc + sh          # SURVEY 8(d) input statistics
+    noise = (torch.randn(B, T_, generator=torch.Generator().manual_seed(1)) * 0.1).to(dev)
+    mel = mel_h.to(dev)
+    with torch.no_grad():
+        plan = m.plan(B, frames, T_, False)
+        plan.infer(mel, noise, None, n, False)
+        plan.infer(mel, noise, None, n, False)
+        graph = plan.graphs[(n, False)][0]
+        for _ in range(warmup):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        mel_pin, out_pin = mel_h.pin_memory(), torch.empty(B, T_).pin_memory()
+        for _ in range(warmup):
+            m.infer(mel_pin, n_timesteps=n, out=out_pin)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.infer(mel_pin, n_timesteps=n, out=out_pin)
+            torch.cuda.current_stream().synchronize()
+        wall = (time.perf_counter() - t0) / steps
+    return {"workload": f"{name} {n}-step inference, synthetic mel ({B},{n_mels},{frames}) -> ({B},{T_})",
+            "ms_per_step": ms, "value": B * T_ / (ms * 1e-3), "unit": "samples/s",
+            "e2e_value": B * T_ / wall, "steps": steps,
+            "ref_equiv_gflop": flops / 1e9, "ref_equiv_tflops": flops / (ms * 1e-3) / 1e12}
+
+
+def tf32_operand_leg(steps: int, warmup: int):
+    """The same bench shape with fp32-container TF32 operands in the ConvNeXt-block GEMMs
+    (F2G_BLOCK_OPERANDS=tf32 is read at import, hence a child interpreter): the line that sits beside
+    the fp16-operand headline (SURVEY.md section 8(d) names TF32 as the precision contract)."""
+    env = dict(os.environ, F2G_BLOCK_OPERANDS="tf32")
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--no-train", "--no-legs", "--no-cpu",
+                            "--steps", str(steps), "--warmup", str(warmup)], env=env, capture_output=True,
+                           text=True, timeout=600)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                return {"dtype": "tf32 operands -> f32 accumulate", "ms_per_step": d["ms_per_step"],
+                        "value": d["value"], "unit": "samples/s", "e2e_value": d["e2e"]["value"],
+                        "roofline_frac_of_tf32_peak": d["roofline"]["frac"],
+                        "roofline_achieved_tflops": d["roofline"]["achieved"]}
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def kernel_census(run_once, match=("gemm_pair_kernel", "gemm_tf32_kernel")):
+    """GPU time of one call of `run_once` by kernel family, from CUPTI activity records
+    (torch.profiler; the records are timestamps taken by the device, not a replay profiler)."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run_once()
+        torch.cuda.synchronize()
+    tot = gemm = glue = 0.0
+    n_all = n_gemm = n_glue = 0
+    for ev in prof.events():
+        if ev.device_type.name != "CUDA" or "memcpy" in ev.name.lower() or "memset" in ev.name.lower():
+            if ev.device_type.name == "CUDA":                       # memcpy / memset nodes: glue
+                glue += ev.device_time
+                n_glue += 1
+                tot += ev.device_time
+                n_all += 1
+            continue
+        dt = ev.device_time
+        tot += dt
+        n_all += 1
+        if any(k in ev.name for k in match):
+            gemm += dt
+            n_gemm += 1
+        elif "f2g::" not in ev.name:
+            glue += dt
+            n_glue += 1
+    return {"gpu_busy_us": tot, "gemm_us": gemm, "torch_glue_us": glue, "launches": n_all,
+            "gemm_launches": n_gemm, "torch_glue_launches": n_glue}
+
+
 def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
     """GAN fine-tune step pair (D-iteration + G-iteration on bs=16 x 24000 samples per GPU, incl.
     ScaledAdam updates and, for world > 1, the NCCL gradient all-reduce of the stepped half) --
@@ -252,7 +371,41 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    roof = None
+    if int(os.environ.get("RANK", "0")) == 0:
+        try:
+            from flow2gan_b200 import _lib as L
+            # (a) FLOPs as executed: the pair's GEMM descriptors, recorded on one eager D + G iteration
+            was = tr.use_graph
+            tr.use_graph = False
+            L.PROFILE = []
+            tr.step(audio, lens)
+            tr.step(audio, lens)
+            torch.cuda.synchronize()
+            rec, L.PROFILE = L.PROFILE, None
+            tr.use_graph = was
+            flops = sum(r[2] for r in rec)
+            # (b) GPU time by kernel family of one replayed pair (CUPTI activity records)
+            cen = kernel_census(lambda: (tr.step(audio, lens), tr.step(audio, lens)))
+            pk, how = peaks()
+            peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
+            ach = flops / (cen["gemm_us"] * 1e-6) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel / gemm_tf32_kernel (kind::tf32), all launches of one D+G pair",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "gemm_gflop_as_executed": flops / 1e9, "gemm_launches": cen["gemm_launches"],
+                    "gemm_ms": cen["gemm_us"] / 1e3, "gpu_busy_ms": cen["gpu_busy_us"] / 1e3,
+                    "gemm_share": cen["gemm_us"] / cen["gpu_busy_us"],
+                    "torch_glue_share": cen["torch_glue_us"] / cen["gpu_busy_us"],
+                    "torch_glue_launches": cen["torch_glue_launches"], "launches_per_pair": cen["launches"],
+                    "pair_ref_equiv_tflops": 7261e9 / (ms / pairs * 1e-3) / 1e12,
+                    "how": "FLOPs = sum(2MNK) of the pair's GEMM descriptors (one eager pair); times = CUPTI kernel "
+                           "records of one graph-replayed pair (torch.profiler)",
+                    "peak_source": f"{how}: bf16_tflops_sustained / 2 (TF32 issues at half the bf16 rate; kernels timed "
+                                   "inside a long step)"}
+        except Exception as e:
+            roof = {"error": repr(e)[:300]}
     return {"value": world * 2 * B * Tt * pairs / (ms * 1e-3), "unit": "samples/s", "ms_per_pair": ms / pairs,
+            "roofline": roof,
             "pairs": pairs, "n_timesteps": n_timesteps, "global_batch": B * world,
             "allreduce_bytes_per_pair": 0 if world == 1 else (78949542 + 42503752) * 4,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
@@ -375,7 +528,6 @@ def run_ours(args):
         e3.record()
         barrier()
         wall = time.perf_counter() - t0
-        clocks = sampler.stop()
         ms_e2e = max(e2.elapsed_time(e3), wall * 1e3)
         t_dev = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
         if dist is not None:
@@ -468,18 +620,30 @@ def run_ours(args):
                 roof["traffic"] = tj.get("dram_bytes_per_launch_avg")
                 roof["traffic_source"] = tj.get("source")
 
+    # the other configurations of BASELINE.json (rank 0, N=1 only: they are per-GPU numbers)
+    legs = {}
+    if rank == 0 and world == 1 and not args.no_legs:
+        for key in LEGS:
+            try:
+                legs[key] = extra_infer_leg(dev, key, steps=max(10, K // 2), warmup=W,
+                                            model=model if LEGS[key][0] == MODEL else None)
+            except Exception as e:
+                legs[key] = {"error": repr(e)[:300]}
     train = None
     if not args.no_train:
         try:
             train = gan_train_bench(dev, dist, world, pairs=args.train_pairs, n_timesteps=n)
         except Exception as e:                       # keep the headline line alive
             train = {"error": repr(e)[:300]}
+    clocks = sampler.stop()      # sampled from the warm-up of the headline leg through the train pairs
+    if rank == 0 and world == 1 and not args.no_legs:
+        legs["tf32_operands"] = tf32_operand_leg(K, W)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    cpu_rate, cpu_ms, cores, cpu_kind = (cpu_reference_rate(n, iters=8 if n == 1 else 3) if world == 1
-                                         else (None, None, None, None))
+    cpu_rate, cpu_ms, cores, cpu_kind = (cpu_reference_rate(n, iters=8 if n == 1 else 3)
+                                         if world == 1 and not args.no_cpu else (None, None, None, None))
     line = {
         "metric": METRIC, "metric_part": "%d-step infer (`value`, `e2e`); GAN train step pair under `gan_train`" % n,
         "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -497,6 +661,8 @@ def run_ours(args):
         line["roofline_other"] = roof_other
     if roof_hbm is not None:
         line["roofline_hbm"] = roof_hbm
+    for k_, v_ in legs.items():
+        line[k_] = v_
     if train is not None:
         line["gan_train"] = train
     if cpu_rate is not None:
@@ -516,6 +682,8 @@ def main():
     ap.add_argument("--n-timesteps", type=int, default=1, choices=[1, 2, 4])
     ap.add_argument("--no-train", action="store_true", help="skip the GAN train-step measurement")
     ap.add_argument("--train-pairs", type=int, default=3)
+    ap.add_argument("--no-legs", action="store_true", help="skip the 2/4-step, 44.1 kHz and TF32-operand legs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -325,7 +325,7 @@ def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_ma
     d.B, d.T, d.C, d.ld_x, d.ld_cond, d.cond_T = B, T, Cc, ld_x, ld_cond, cond_T
     d.factor, d.zero_row, d.ld_ts, d.ld_out = factor, zero_row, ld_ts, ld_out
     # bit flags (include/flow2gan_b200.h): 1 = fp16 output rows, 2 = fp16 conditioning rows
-    d.out_f16 = int(out.dtype == torch.float16) | (2 if cond is not None and cond.dtype == torch.float16 else 0)
+    d.out_f16 = int(out.dtype == torch.float16)
     return d
 
 

@@ -70,7 +70,7 @@ struct BlockPreArgs {
   int n;
 };
 
-template <int PRE_S, int MINB, bool COND_F16 = false>
+template <int PRE_S, int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __grid_constant__ BlockPreArgs a) {
   __shared__ float red[PRE_MAX_TL * PRE_S][8];
   int pi = 0;
@@ -158,11 +158,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
         if (t < T) {
           const int fr = fsh >= 0 ? (t >> fsh) : t / P.factor;
           const int crow = t < t_cond ? bi * P.cond_T + fr : P.zero_row;
-          if (COND_F16)   // conditioning rows stored as fp16 (F2G_PRE_COND_F16): 8 B per channel quad
-            cv[s] = unpack_half4(*reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(P.cond) + c +
-                                                                  (size_t)crow * P.ld_cond));
-          else
-            cv[s] = ld4(cbase + (size_t)crow * P.ld_cond);
+          cv[s] = ld4(cbase + (size_t)crow * P.ld_cond);
         }
       }
     }
@@ -214,7 +210,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     float4 z = make_float4(acc[s].x * inv, acc[s].y * inv, acc[s].z * inv, acc[s].w * inv);
     z.x += cv[s].x; z.y += cv[s].y; z.z += cv[s].z; z.w += cv[s].w;
     z.x *= 1.f + sc.x; z.y *= 1.f + sc.y; z.z *= 1.f + sc.z; z.w *= 1.f + sc.w;
-    if (COND_F16 ? (P.out_f16 & F2G_PRE_OUT_F16) : P.out_f16) {   // operand of a kind::f16 GEMM: same 11-bit significand as the TF32 rounding
+    if (P.out_f16) {   // operand of a kind::f16 GEMM: same 11-bit significand as the TF32 rounding
       __half* o = reinterpret_cast<__half*>(P.out) + (rb + t) * (size_t)P.ld_out + c;
       *reinterpret_cast<uint2*>(o) = pack_half4(z);
     } else {
@@ -381,15 +377,8 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
     ctas += a.ctas_t[i] * p.B;
   }
   for (int i = n; i <= 4; ++i) a.cta_begin[i] = ctas;
-  int n_cf16 = 0;
-  for (int i = 0; i < n; ++i) n_cf16 += (probs[i].out_f16 & F2G_PRE_COND_F16) && probs[i].cond;
-  if (n_cf16 && n_cf16 != n) {
-    set_error("f2g_block_pre_group: fp16 conditioning rows must be used by all problems of a launch or none");
-    return F2G_EINVAL;
-  }
   void (*kern)(BlockPreArgs) = block_pre_kernel<4, 2>;
-  if (n_cf16) kern = block_pre_kernel<4, 2, true>;
-  else if (variant == 1) kern = block_pre_kernel<2, 3>;
+  if (variant == 1) kern = block_pre_kernel<2, 3>;
   if (variant == 2) kern = block_pre_kernel<2, 2>;
   if (variant == 3) kern = block_pre_kernel<8, 1>;
   cudaError_t le = launch_pdl(kern, dim3(ctas), dim3(PRE_THREADS), 0, static_cast<cudaStream_t>(stream), a);

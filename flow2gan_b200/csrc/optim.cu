@@ -44,7 +44,8 @@ F2G_KERNEL void adam_reduce_kernel(const F2GAdamTensor* __restrict__ tab, const 
 }
 
 // state scalars per tensor: [0]=param_rms [1]=scale_exp_avg_sq [2..5]=scale_grads[0..3] [6]=scale_step
-// group scalars: [0]=tot_norm (out) [1]=clip (out) [2]=threshold (<0: unset)
+// group scalars: [0]=tot_norm (out) [1]=clip (out) [2]=threshold (<0: unset) [3]=num_clipped (counter,
+// optim.py:607-608; the host reads and clears it when it refreshes the threshold)
 F2G_KERNEL void adam_norm_kernel(const F2GAdamTensor* __restrict__ tab, int n, const float* __restrict__ acc,
                                  float* __restrict__ ts, float* __restrict__ gs, int step,
                                  float scalar_lr_scale, float* __restrict__ model_norms, int period) {
@@ -85,7 +86,10 @@ F2G_KERNEL void adam_scalars_kernel(const F2GAdamTensor* __restrict__ tab, int n
     clip = fminf(1.f, gs[2] / (gs[0] + 1.0e-20f));
     if (clip != clip) clip = 0.f;
   }
-  if (threadIdx.x == 0 && blockIdx.x == 0) gs[1] = clip;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    gs[1] = clip;
+    if (clip < 1.f) gs[3] += 1.f;
+  }
   const int slot = step % size_period;
   const bool refresh = slot == size_period - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -158,6 +162,10 @@ extern "C" int f2g_scaled_adam_step(const F2GAdamTensor* tab_dev, int n_tensors,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_tensors <= 0 || n_chunks <= 0) {
     set_error("f2g_scaled_adam_step: empty parameter table");
+    return F2G_EINVAL;
+  }
+  if (h->size_update_period < 1 || h->size_update_period > 4) {   // scale_grads is a fixed 4-slot row
+    set_error("f2g_scaled_adam_step: size_update_period %d outside 1..4", h->size_update_period);
     return F2G_EINVAL;
   }
   const int2* chunks = reinterpret_cast<const int2*>(chunks_dev);

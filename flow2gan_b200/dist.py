@@ -44,7 +44,22 @@ def get_rank() -> int:
 
 
 def get_local_rank() -> int:
-    return int(os.environ.get("LOCAL_RANK", get_rank()))
+    return int(os.environ.get("LOCAL_RANK", 0))          # dist.py:63-69: defaults to 0
+
+
+def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None) -> int:
+    """What the reference's DDP wrapper does at construction (bin/finetune.py:913-915): every rank
+    starts from rank `src`'s parameters AND buffers.  Without it, replicas that were not seeded
+    identically (the freshly initialised discriminators) would train apart under averaged
+    gradients without any error.  Returns the number of tensors broadcast (0 = single process)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    n = 0
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+            n += 1
+    return n
 
 
 class GradBuckets:

@@ -40,14 +40,11 @@ assert BLOCK_OPERANDS in ("f16", "tf32"), BLOCK_OPERANDS
 # boundary; fp16 operands only)
 CHAIN_MLP = os.environ.get("F2G_CHAIN_MLP", "1") == "1"
 FORK_COND = os.environ.get("F2G_FORK_COND", "1") == "1"    # conditioning path on a second stream
-# F2G_F16_COND=1 (experiment, fp16 block operands only): the cond_proj GEMM stores its (Rc, 8C) output as
-# fp16 and the block prologue reads it as such -- halves the bytes of the launch that closes the
-# conditioning path (it is on the critical path of 1-step inference)
-F16_COND = os.environ.get("F2G_F16_COND", "0") == "1"
-# F2G_CACHE_TIME=1 (experiment): the sampler evaluates every batch element at the same t_k = k / N, so the
-# per-layer time-scale vectors of step k depend on the weights only: compute them once per (plan, N)
-# instead of in every model evaluation (4 small launches per ODE step leave the launch graph)
-CACHE_TIME = os.environ.get("F2G_CACHE_TIME", "0") == "1"
+# The sampler evaluates every batch element at the same t_k = k / N, so the per-layer time-scale
+# vectors of step k depend on the weights only: they are computed once per (plan, N, weight version)
+# instead of in every model evaluation (4 small launches per ODE step leave the launch graph; output
+# bit-identical, profiles/r02_switches.md).  F2G_CACHE_TIME=0 restores the per-step launches (A/B).
+CACHE_TIME = os.environ.get("F2G_CACHE_TIME", "1") == "1"
 
 
 def _ceil(a: int, b: int) -> int:
@@ -82,28 +79,49 @@ class _BlockW:
         C, H = blk.channels, blk.hidden_channels
         self.C, self.H = C, H
         self.blk = blk
-        self.dwT = _pack(blk.dwconv.weight.detach(), 7, C, 1, 7, C, rnd=0)          # (7, C)
-        self.W1 = _pack(blk.pwconv1.weight.detach(), H, C, C, 1, C)                  # (H, C)
-        self.W2 = _pack(blk.pwconv2.weight.detach(), C, H, H, 1, H)                  # (C, H)
+        self.dwT = self.W1 = self.W2 = None
         self._half = None
+        self._half_fresh = False
+        self.refresh()
+
+    def refresh(self) -> None:
+        """(Re)packs IN PLACE: the buffers are allocated once, so every captured CUDA graph that
+        holds their addresses (inference plans, the trainer's phase graphs) stays valid."""
+        blk, C, H = self.blk, self.C, self.H
+        self.dwT = _pack(blk.dwconv.weight.detach(), 7, C, 1, 7, C, rnd=0, dst=self.dwT)     # (7, C)
+        self.W1 = _pack(blk.pwconv1.weight.detach(), H, C, C, 1, C, dst=self.W1)             # (H, C)
+        self.W2 = _pack(blk.pwconv2.weight.detach(), C, H, H, 1, H, dst=self.W2)             # (C, H)
+        self._half_fresh = False
+        if self._half is not None:          # already handed out (and maybe baked into a graph): keep current
+            self.half()
 
     def half(self) -> Tuple[Tensor, Tensor]:
-        """fp16 copies (RN) of the two matrices for the kind::f16 inference GEMMs; built on first
-        use after every refresh (the training path never asks for them)."""
+        """fp16 copies (RN) of the two matrices for the kind::f16 inference GEMMs: allocated on first
+        use (the training path never asks for them), rewritten in place after every refresh."""
+        b = self.blk
         if self._half is None:
-            b = self.blk
-            self._half = (b.pwconv1.weight.detach().reshape(self.H, self.C).to(torch.float16),
-                          b.pwconv2.weight.detach().reshape(self.C, self.H).to(torch.float16))
+            dev = b.pwconv1.weight.device
+            self._half = (torch.empty(self.H, self.C, device=dev, dtype=torch.float16),
+                          torch.empty(self.C, self.H, device=dev, dtype=torch.float16))
+            self._half_fresh = False
+        if not self._half_fresh:
+            self._half[0].copy_(b.pwconv1.weight.detach().reshape(self.H, self.C))
+            self._half[1].copy_(b.pwconv2.weight.detach().reshape(self.C, self.H))
+            self._half_fresh = True
         return self._half
 
 
 class PackedGenerator:
     """GEMM-ready (TF32-rounded, 16B-aligned, concatenated) copies of the generator matrices.
-    Rebuilt automatically when the parameters change (signature over tensor versions)."""
+    Allocated once; `refresh()` rewrites them IN PLACE when the parameters change (signature over
+    tensor versions), so buffer addresses baked into captured CUDA graphs never go stale.
+    `version` counts refreshes (plans key their own derived caches on it)."""
 
     def __init__(self, model):
         self.model = model
         self.signature = None
+        self.version = 0
+        self._built = False
         self.refresh()
 
     def stale(self) -> bool:
@@ -111,50 +129,67 @@ class PackedGenerator:
 
     def refresh(self) -> None:
         m = self.model
+        first = not self._built
         self._plist = list(m.parameters())
         with torch.no_grad():
             ce = m.cond_encoder
             nm = ce.cond_dim
-            self.ld_mel = _ceil(3 * nm, 4)
-            self.ce_Win = torch.zeros(ce.channels, self.ld_mel, device=ce.in_proj.weight.device)
+            if first:
+                self.ld_mel = _ceil(3 * nm, 4)
+                self.ce_Win = torch.zeros(ce.channels, self.ld_mel, device=ce.in_proj.weight.device)
             for k in range(3):   # (Co, Ci, 3) -> column k*Ci + ci
                 w = ce.in_proj.weight.detach()
                 L.pack2d(w.data_ptr() + 4 * k, 3 * nm, 3, ce.channels, nm,
                          self.ce_Win.data_ptr() + 4 * k * nm, self.ld_mel, nm, 1)
-            self.ce_blocks = [_BlockW(b) for b in ce.blocks]
-            self.branches = []
-            for est in m.estimators:
+            if first:
+                self.ce_blocks = [_BlockW(b) for b in ce.blocks]
+                self.branches = []
+            else:
+                for bw in self.ce_blocks:
+                    bw.refresh()
+            for bi, est in enumerate(m.estimators):
                 d = est.decoder
                 C, nin = d.channels, d.in_channels
                 ldp = _ceil(nin, 4)
-                br = type("BranchW", (), {})()
-                br.C, br.nin, br.ldp = C, nin, ldp
-                br.n_fft, br.hop = est.fft.n_fft, est.fft.hop_length
-                br.factor = est.cond_upsample_factor
-                br.dec = d
-                br.Win = _pack(d.in_proj.weight.detach(), C, nin, nin, 1, ldp)
-                br.Wout = _pack(d.out_proj.weight.detach(), nin, C, C, 1, C)
                 cc = d.cond_mlp[0].weight.shape[1]
                 ch = d.cond_mlp[0].weight.shape[0]
-                br.cc, br.ch = cc, ch
-                br.cmW0 = _pack(d.cond_mlp[0].weight.detach(), ch, cc, cc, 1, cc)
-                br.cmW2 = _pack(d.cond_mlp[2].weight.detach(), cc, ch, ch, 1, ch)
                 nl = len(d.blocks)
-                br.nl = nl
                 te = d.time_mlp[0].weight.shape[1]
-                br.te = te
-                br.Wcp = torch.zeros(nl * C, cc, device=br.Win.device)
-                br.bcp = torch.zeros(nl * C, device=br.Win.device)
-                br.Wte = torch.zeros(nl * C, te, device=br.Win.device)
-                br.bte = torch.zeros(nl * C, device=br.Win.device)
+                if first:
+                    br = type("BranchW", (), {})()
+                    br.C, br.nin, br.ldp = C, nin, ldp
+                    br.n_fft, br.hop = est.fft.n_fft, est.fft.hop_length
+                    br.factor = est.cond_upsample_factor
+                    br.dec = d
+                    br.cc, br.ch, br.nl, br.te = cc, ch, nl, te
+                    br.Win = br.Wout = br.cmW0 = br.cmW2 = None
+                    dev = d.in_proj.weight.device
+                    br.Wcp = torch.zeros(nl * C, cc, device=dev)
+                    br.bcp = torch.zeros(nl * C, device=dev)
+                    br.Wte = torch.zeros(nl * C, te, device=dev)
+                    br.bte = torch.zeros(nl * C, device=dev)
+                    br._halves = {}
+                    self.branches.append(br)
+                br = self.branches[bi]
+                br.Win = _pack(d.in_proj.weight.detach(), C, nin, nin, 1, ldp, dst=br.Win)
+                br.Wout = _pack(d.out_proj.weight.detach(), nin, C, C, 1, C, dst=br.Wout)
+                br.cmW0 = _pack(d.cond_mlp[0].weight.detach(), ch, cc, cc, 1, cc, dst=br.cmW0)
+                br.cmW2 = _pack(d.cond_mlp[2].weight.detach(), cc, ch, ch, 1, ch, dst=br.cmW2)
                 for i, blk in enumerate(d.blocks):
                     _pack(blk.cond_proj.weight.detach(), C, cc, cc, 1, cc, dst=br.Wcp, dst_row=i * C)
                     _pack(blk.time_embed_proj.weight.detach(), C, te, te, 1, te, rnd=0, dst=br.Wte,
                           dst_row=i * C)
                     br.bcp[i * C:(i + 1) * C].copy_(blk.cond_proj.bias.detach())
                     br.bte[i * C:(i + 1) * C].copy_(blk.time_embed_proj.bias.detach())
-                br.blocks = [_BlockW(b) for b in d.blocks]
-                self.branches.append(br)
+                if first:
+                    br.blocks = [_BlockW(b) for b in d.blocks]
+                else:
+                    for bw in br.blocks:
+                        bw.refresh()
+                for nm_, t in br._halves.items():       # fp16 copies already handed out: rewrite in place
+                    t.copy_(getattr(br, nm_))
+        self._built = True
+        self.version += 1
         self.signature = _params_signature(self._plist)
 
 
@@ -170,8 +205,10 @@ def _g1(bw: _BlockW, a, h, M, bn=None, done=None):
                        act=L.ACT_PRELU, round_tf32=1)
 
 
-# F2G_PAIR_BN_HINT=1 (experiment): N tile of the chained pwconv2 problems by output width
-_TAIL_BN = {768: 256, 512: 192, 384: 128} if os.environ.get("F2G_PAIR_BN_HINT", "0") == "1" else {}
+# N tile of the chained pwconv2 problems by output width: the LPT tile schedule places these problems
+# last, narrower tiles shorten the tail of the launch (measured: step 0.696 -> 0.672 ms, output equal to
+# 1e-6, profiles/r02_switches.md)
+_TAIL_BN = {768: 256, 512: 192, 384: 128}
 
 
 def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0, wait=None):
@@ -186,13 +223,12 @@ def _g2(bw: _BlockW, h, x, M, bn=None, round_out=0, wait=None):
 
 
 def _half(holder, name: str) -> Tensor:
-    """fp16 copy of a packed (TF32-rounded, hence exactly representable) fp32 matrix, cached on
-    its holder until the next PackedGenerator.refresh()."""
-    key = "_h_" + name
-    t = holder.__dict__.get(key)
+    """fp16 copy of a packed (TF32-rounded, hence exactly representable) fp32 matrix of a branch;
+    allocated once, kept current by PackedGenerator.refresh() (in place)."""
+    t = holder._halves.get(name)
     if t is None:
         t = getattr(holder, name).to(torch.float16)
-        holder.__dict__[key] = t
+        holder._halves[name] = t
     return t
 
 
@@ -238,7 +274,7 @@ class InferencePlan:
             w.ts = z(1, bw.nl * bw.C)
             w.cm_h = zo(self.Rc, bw.ch)       # cond_mlp hidden / output: GEMM operands only
             w.c1 = zo(self.Rc, bw.cc)
-            w.cp = (zo if F16_COND and BLOCK_OPERANDS == "f16" else z)(self.Rc, bw.nl * bw.C)
+            w.cp = z(self.Rc, bw.nl * bw.C)
             w.mask = z(w.R) if masked else None
             self.br.append(w)
         # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
@@ -309,9 +345,8 @@ class InferencePlan:
                                       bw.ch, bw.ch, bw.cc, bias=cm[2].bias.data_ptr(), act=L.ACT_LEAKY,
                                       leaky=1.0, ab_f16=1, c_f16=1, wait_counter=cnt))
                 N = bw.nl * bw.C
-                kw3 = dict(act=L.ACT_LEAKY, leaky=1.0, c_f16=1) if w.cp.dtype == torch.float16 else {}
                 g3.append(L.gemm_desc(w.c1.data_ptr(), Wc.data_ptr(), w.cp.data_ptr(), Rc, N, bw.cc,
-                                      bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1, **kw3))
+                                      bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1))
             if self.chained:
                 L.gemm_group(g0 + g2)
             else:
@@ -422,15 +457,29 @@ class InferencePlan:
         # built on the device (no host->device copy: this also runs under stream capture)
         self.t_all = torch.linspace(0, 1, n + 1, device=self.x_audio.device)[:n].unsqueeze(1) \
             .expand(n, self.B).contiguous()
-        if CACHE_TIME and n not in self._ts_cache:
-            per_step = []
-            for k in range(n):
-                for w in self.br:
-                    w.ts = torch.zeros_like(w.ts)
-                self.time_path(self.t_all[k])
-                per_step.append([w.ts for w in self.br])
-            self._ts_cache[n] = per_step
+        self._refresh_time_cache(n)
         return ts, dt
+
+    def _refresh_time_cache(self, n: int) -> None:
+        """Per-step time-scale vectors of an n-step sampler, recomputed IN PLACE whenever the packed
+        weights changed (PackedGenerator.version) -- captured graphs keep pointing at the same
+        tensors.  Under an outer stream capture (the trainer's phase graphs) they are always
+        recomputed, so that the outer graph carries its own time path."""
+        if not CACHE_TIME:
+            return
+        ent = self._ts_cache.get(n)
+        if ent is not None and ent[0] == self.pk.version and not torch.cuda.is_current_stream_capturing():
+            return
+        per_step = ent[1] if ent is not None else [[torch.zeros_like(w.ts) for w in self.br] for _ in range(n)]
+        t_rows = torch.linspace(0, 1, n + 1, device=self.x_audio.device)[:n].contiguous()
+        keep = [w.ts for w in self.br]
+        for k in range(n):
+            for w, t in zip(self.br, per_step[k]):
+                w.ts = t
+            self.time_path(t_rows[k:k + 1])
+        for w, t in zip(self.br, keep):
+            w.ts = t
+        self._ts_cache[n] = (self.pk.version, per_step)
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
         ts, dt = self._steps
@@ -456,11 +505,11 @@ class InferencePlan:
             with torch.cuda.stream(self._side):
                 self.encode_cond()
                 join.record(self._side)
-            self.process_front(self.t_all[0], with_time=not (CACHE_TIME and n in self._ts_cache))
+            self.process_front(self.t_all[0], with_time=not CACHE_TIME)
             main.wait_event(join)
         elif with_cond:
             self.encode_cond()
-        cached = self._ts_cache.get(n) if CACHE_TIME else None
+        cached = self._ts_cache[n][1] if CACHE_TIME else None
         for k in range(n):
             if not (forked and k == 0):
                 self.process_front(self.t_all[k], with_time=cached is None)
@@ -523,6 +572,7 @@ class InferencePlan:
             self.graphs[key] = (g, self._steps, self.t_all)
         else:
             g, self._steps, self.t_all = g
+            self._refresh_time_cache(n)             # weights repacked in place since the capture?
         g.replay()
         return result()
 

@@ -12,10 +12,11 @@ from .discriminators import MultiPeriodDiscriminator, MultiResolutionDiscriminat
 from .losses import hinge_terms, l1_terms, mel_recon_loss
 from .modules import MelSpectrogram
 
-# F2G_FUSED_LOSSES=1: hinge / feature-matching / mel L1 reductions through the multi-tensor kernels of
-# csrc/losses.cu (one launch per <= 24 terms each way) instead of element-wise torch ops per term.
-# Off by default until the round-2 GPU parity run has covered it (tests/test_zz_losses_gpu.py).
-FUSED_LOSSES = os.environ.get("F2G_FUSED_LOSSES", "0") == "1"
+# Hinge / feature-matching / mel L1 reductions go through the multi-tensor kernels of csrc/losses.cu
+# (one launch per <= 24 terms each way) instead of ~850 element-wise torch launches per D+G pair
+# (GPU parity: tests/test_zz_losses_gpu.py; A/B 66.8 -> 65.2 ms per pair, profiles/r02_switches.md).
+# F2G_FUSED_LOSSES=0 keeps the per-term torch reductions for A/B runs.
+FUSED_LOSSES = os.environ.get("F2G_FUSED_LOSSES", "1") == "1"
 
 
 class GAN(nn.Module):

@@ -115,8 +115,9 @@ class BaseAudioGenerator(nn.Module):
         if self._packed is None:
             self._packed = PackedGenerator(self)
         elif self._packed.stale():
+            # in place: plans and captured graphs keep pointing at the same buffers; plans notice
+            # the new `version` and recompute their derived caches (time-scale vectors)
             self._packed.refresh()
-            self._plans = {}                 # captured graphs point at the old packed buffers
         return self._packed
 
     def plan(self, B: int, Fm: int, T: int, masked: bool) -> InferencePlan:

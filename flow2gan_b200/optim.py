@@ -24,11 +24,14 @@ class _Group:
     def __init__(self, params: List[Tensor], names: List[str], period: int, clip_period: int):
         dev = params[0].device
         # same batching rule as BatchedOptimizer.batched_params (optim.py:77-98): group by
-        # (dtype, shape); order batches by their name lists
+        # (str(dtype), *shape); batches ordered by THAT key (optim.py:90-95 sorts
+        # `batches_names_keys[i]`, the key tuples) -- the first batch's first parameter holds
+        # model_norms / model_norm_threshold / num_clipped in the state_dict, so the order is part
+        # of the checkpoint layout
         by_key: Dict[tuple, List[int]] = defaultdict(list)
         for i, p in enumerate(params):
             by_key[(str(p.dtype), *p.shape)].append(i)
-        keys = sorted(by_key.keys(), key=lambda k: [names[i] for i in by_key[k]])
+        keys = sorted(by_key.keys())
         self.batches = [by_key[k] for k in keys]
         self.params = params
         self.names = names
@@ -38,7 +41,7 @@ class _Group:
         self.exp_avg_sq = [torch.zeros(len(b), *params[b[0]].shape, device=dev) for b in self.batches]
         self.delta = [torch.zeros(len(b), *params[b[0]].shape, device=dev) for b in self.batches]
         self.tstate = torch.zeros(n, 8, device=dev)
-        self.gstate = torch.tensor([0.0, 1.0, -1.0], device=dev)
+        self.gstate = torch.tensor([0.0, 1.0, -1.0, 0.0], device=dev)    # tot_norm, clip, threshold, num_clipped
         self.norms = torch.zeros(clip_period, device=dev)
         self.acc = torch.zeros(n, 3, device=dev)
         chunks = []
@@ -60,7 +63,6 @@ class _Group:
         self.tab_dev = torch.zeros(C.sizeof(L.F2GAdamTensor) * n, dtype=torch.uint8, device=dev)
         self.step = 0
         self.threshold: Optional[float] = None
-        self.num_clipped = 0
         self._keep = []
 
     def upload_table(self):
@@ -95,6 +97,10 @@ class ScaledAdam(Optimizer):
                         size_update_period=size_update_period,
                         clipping_update_period=clipping_update_period)
         self.show_dominant_parameters = True
+        if not 1 <= int(size_update_period) <= 4:
+            # the fused kernels keep scale_grads in a fixed 4-slot row of the per-tensor state
+            # (csrc/optim.cu); the reference's recipes all use 4
+            raise ValueError(f"flow2gan_b200.ScaledAdam: size_update_period must be in 1..4, got {size_update_period}")
         groups, names = self._split_names(params)
         super().__init__(groups, defaults)
         assert len(self.param_groups) == len(names)
@@ -163,9 +169,11 @@ class ScaledAdam(Optimizer):
         if step in irregular:
             thr *= 2.0
         st.threshold = thr
+        percent_clipped = float(st.gstate[3]) * 100.0 / n       # same read point as the norm ring
         st.gstate[2] = thr
-        logging.warning("Clipping_scale=%s, grad-norm quartiles %s, threshold=%.3e", group["clipping_scale"],
-                        " ".join("%.3e" % q for q in quartiles), thr)
+        st.gstate[3] = 0.0                                       # optim.py:585 num_clipped = 0
+        logging.warning("Clipping_scale=%s, grad-norm quartiles %s, threshold=%.3e, percent-clipped=%.1f",
+                        group["clipping_scale"], " ".join("%.3e" % q for q in quartiles), thr, percent_clipped)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -223,7 +231,7 @@ class ScaledAdam(Optimizer):
                     d["model_norms"] = st.norms.clone()
                     if st.threshold is not None:
                         d["model_norm_threshold"] = st.threshold
-                    d["num_clipped"] = st.num_clipped
+                    d["num_clipped"] = int(st.gstate[3])
                 self.state[p0] = d
                 slot += nb
 
@@ -250,6 +258,8 @@ class ScaledAdam(Optimizer):
                     if "model_norm_threshold" in d:
                         st.threshold = float(d["model_norm_threshold"])
                         st.gstate[2] = st.threshold
+                    if "num_clipped" in d:
+                        st.gstate[3] = float(d["num_clipped"])
                 slot += nb
 
 

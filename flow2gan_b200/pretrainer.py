@@ -14,7 +14,7 @@ import torch
 from torch import Tensor, nn
 
 from .averaging import update_averaged_model
-from .dist import GradBuckets, get_rank
+from .dist import GradBuckets, broadcast_module_state, get_rank
 from .modules import LogMelSpectrogram
 from .optim import Eden2, ScaledAdam
 from .utils import get_parameter_groups_with_lrs
@@ -25,6 +25,7 @@ class FMTrainer:
                  warmup_start: float = 0.1, average_period: int = 200, keep_average: bool = True,
                  rank: Optional[int] = None):
         self.model = model
+        broadcast_module_state(model)            # DDP's construction-time sync (pretrain.py:800-802)
         dev = next(model.parameters()).device
         self.cond_module = LogMelSpectrogram(model.sampling_rate, model.mel_n_fft, model.mel_hop_length,
                                              model.n_mels).to(dev)

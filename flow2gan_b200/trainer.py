@@ -8,7 +8,7 @@ from typing import Dict, Optional
 import torch
 from torch import Tensor
 
-from .dist import GradBuckets
+from .dist import GradBuckets, broadcast_module_state
 from .gan import GAN
 from .modules import LogMelSpectrogram
 from .optim import Eden2, ScaledAdam
@@ -22,6 +22,7 @@ class GANTrainer:
                  weights: Optional[Dict[str, float]] = None, use_graph: bool = True,
                  graph_warmup: int = 1):
         self.gan = gan
+        broadcast_module_state(gan)              # DDP's construction-time sync of parameters + buffers
         g = gan.generator
         self.cond_module = LogMelSpectrogram(g.sampling_rate, g.mel_n_fft, g.mel_hop_length, g.n_mels) \
             .to(next(gan.parameters()).device)
@@ -78,6 +79,7 @@ class GANTrainer:
         if int(audio_lens.max()) != length:          # finetune batches are padded to their longest item
             return None
         ent = {"audio": audio.clone(), "lens": audio_lens.clone(), "draws": T.DrawBuffer(audio.device)}
+        half = self.gan.discriminator if disc else self.gan.generator
         (self.opt_d if disc else self.opt_g).zero_grad(set_to_none=True)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -95,6 +97,11 @@ class GANTrainer:
             T._draws, gen._static_length = None, None
         ent["draws"].count = ent["draws"].i
         ent["graph"] = graph
+        # The graph writes this phase's gradients into the tensors that became `.grad` during the
+        # capture (private-pool memory, kept alive here).  Any later zero_grad(set_to_none=True) --
+        # the eager path, or the capture of another batch shape -- rebinds `.grad` elsewhere, so
+        # every replay re-attaches exactly these tensors before the all-reduce / optimizer read them.
+        ent["grads"] = [(p, p.grad) for p in half.parameters()]
         return ent
 
     def step(self, audio: Tensor, audio_lens: Tensor) -> Dict[str, Tensor]:
@@ -103,6 +110,10 @@ class GANTrainer:
         phase's forward+backward (~2.6 k launches) into a CUDA graph; later calls replay it."""
         disc = self.train_disc
         ent = None
+        # The generator's packed (TF32 / fp16) weight copies are refreshed HERE, eagerly and in place
+        # (engine.PackedGenerator), never inside a phase graph: every graph of every batch shape
+        # reads the same persistent buffers, whichever phase / path ran before it.
+        self.gan.generator.packed()
         if self.use_graph:
             key = (disc, tuple(audio.shape))
             ent = self._graphs.get(key)
@@ -121,6 +132,8 @@ class GANTrainer:
             ent["lens"].copy_(audio_lens)
             ent["draws"].refill()
             ent["graph"].replay()
+            for p, g in ent["grads"]:
+                p.grad = g
             info = ent["info"]
         else:
             (self.opt_d if disc else self.opt_g).zero_grad()

@@ -188,12 +188,11 @@ typedef struct F2GBlockPre {
   int B, T, C, ld_x, ld_cond, cond_T, factor, zero_row, ld_ts, ld_out;
   int* zero_ptr; /* problem 0 only: zero_n ints are cleared by this launch (the chaining counters of */
   int zero_n;    /* the GEMM group that follows in the stream), or NULL */
-  int out_f16; /* bit flags.  F2G_PRE_OUT_F16 (1): `out` points to fp16 rows (ld_out in elements, multiple
-                  of 4), RN-rounded and clamped to +-65504 instead of TF32-rounded fp32 -- operand of an
-                  ab_f16 GEMM.  F2G_PRE_COND_F16 (2): `cond` points to fp16 rows (ld_cond in elements,
-                  multiple of 4) -- the c_f16 output of the cond_proj GEMM; all problems of a launch or none */
+  int out_f16; /* F2G_PRE_OUT_F16 (1): `out` points to fp16 rows (ld_out in elements, multiple of 4),
+                  RN-rounded and clamped to +-65504 instead of TF32-rounded fp32 -- operand of an
+                  ab_f16 GEMM */
 } F2GBlockPre;
-enum { F2G_PRE_OUT_F16 = 1, F2G_PRE_COND_F16 = 2 };
+enum { F2G_PRE_OUT_F16 = 1 };
 int f2g_block_pre_group(const F2GBlockPre* problems, int n_problems, void* stream);
 
 /* Small dense layers for few-row inputs, fp32 SIMT, up to 4 independent problems per launch:

@@ -17,8 +17,15 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    from flow2gan_b200.dist import GradBuckets, cleanup_dist, setup_dist
+    from flow2gan_b200.dist import GradBuckets, broadcast_module_state, cleanup_dist, setup_dist
     setup_dist(rank, world, backend="gloo")
+    # construction-time sync (what the reference's DDP wrapper does): differently seeded replicas end
+    # up with rank 0's parameters and buffers
+    torch.manual_seed(100 + rank)
+    mod = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.BatchNorm1d(3))
+    mod[1].running_mean.fill_(float(rank + 1))
+    nb = broadcast_module_state(mod)
+    q.put(("sync", rank, nb, [t.detach().clone() for t in list(mod.parameters()) + list(mod.buffers())]))
     torch.manual_seed(0)
     params = [torch.nn.Parameter(torch.zeros(s)) for s in ((7, 5), (3,), (), (1000,), (64, 9, 3))]
     for i, p in enumerate(params):
@@ -38,7 +45,13 @@ def _run_once(world):
     for p in procs:
         p.start()
     try:
-        res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+        got = [q.get(timeout=180) for _ in range(2 * world)]
+        sync = sorted([g for g in got if g[0] == "sync"], key=lambda t: t[1])
+        assert sync[0][2] == sync[1][2] == len(sync[0][3]) > 0
+        for a, b in zip(sync[0][3], sync[1][3]):
+            assert torch.equal(a, b)
+        assert float(sync[1][3][-2].mean()) == 1.0 or any(float(t.float().mean()) == 1.0 for t in sync[1][3])
+        res = sorted([g for g in got if g[0] != "sync"], key=lambda t: t[0])
     finally:
         for p in procs:
             p.join(timeout=60)

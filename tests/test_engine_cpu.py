@@ -164,36 +164,39 @@ def test_streaming_dry_run_matches_oracle_chunk_by_chunk(L):
     assert rel_rms(got_b, got) < 1e-5
 
 
-def test_fp16_conditioning_rows_keep_parity(L, monkeypatch):
-    """F2G_F16_COND (opt-in): cond_proj output stored as fp16, read by the fp16-cond instantiation of the
-    block prologue.  Same golden case as above; the parity number must stay at the fp16-operand level."""
-    import flow2gan_b200.engine as E
-    monkeypatch.setattr(E, "F16_COND", True)
-    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
-    m = _model(g)
-    with torch.no_grad():
-        out = m.infer(g["mel"], n_timesteps=1, noise=g["noise"])
-        plan = next(iter(m._plans.values()))
-        assert all(w.cp.dtype == torch.float16 for w in plan.br)
-    err = rel_rms(out, g["audio_n1"])
-    print("fp16 conditioning rows: rel-RMS vs reference", err)
-    assert err < 1e-3
-
-
 def test_cached_time_path_is_bit_identical(L, monkeypatch):
-    """F2G_CACHE_TIME (opt-in): per-step time-scale vectors computed once per (plan, N) -- the 2-step
-    output must equal the uncached run bit for bit (same kernels, same inputs, fewer launches)."""
+    """F2G_CACHE_TIME (default on): per-step time-scale vectors computed once per (plan, N, weight
+    version) -- the 2-step output must equal the uncached run bit for bit (same kernels, same inputs,
+    fewer launches); after an in-place weight refresh the cache is recomputed; under an outer stream
+    capture (the trainer's phase graphs) it is recomputed on every call."""
     import flow2gan_b200.engine as E
     g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
     outs, counts = [], []
     for flag in (False, True):
         monkeypatch.setattr(E, "CACHE_TIME", flag)
+        monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
         m = _model(g)
+        B, _, Fm = g["mel"].shape
         with torch.no_grad():
-            m.infer(g["mel"], n_timesteps=2, noise=g["noise"])          # first call builds plan (+ cache)
+            plan = m.plan(B, Fm, g["noise"].shape[-1], False)
+            plan.infer(g["mel"], g["noise"], None, 2, False, use_graph=False)      # builds the cache
             L.COUNT = 0
-            outs.append(m.infer(g["mel"], n_timesteps=2, noise=g["noise"]).clone())
+            outs.append(plan.infer(g["mel"], g["noise"], None, 2, False, use_graph=False).clone())
             counts.append(L.COUNT)
+            if flag:
+                ver = m._packed.version
+                m.estimators[0].decoder.time_mlp[0].bias.data.add_(0.25)           # weights move ...
+                torch.autograd.graph.increment_version(list(m.parameters()))
+                assert m.plan(B, Fm, g["noise"].shape[-1], False) is plan           # ... the plan survives
+                assert m._packed.version == ver + 1
+                L.COUNT = 0
+                moved = plan.infer(g["mel"], g["noise"], None, 2, False, use_graph=False)
+                assert L.COUNT == counts[1] + 2 * 4                                 # cache rebuilt once
+                assert not torch.equal(moved, outs[1])
+                monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)
+                L.COUNT = 0
+                again = plan.infer(g["mel"], g["noise"], None, 2, False, use_graph=False)
+                assert L.COUNT == counts[1] + 2 * 4 and torch.equal(again, moved)   # outer capture: always
     assert torch.equal(outs[0], outs[1])
     assert counts[1] == counts[0] - 2 * 4, counts                     # 4 launches per ODE step left the sequence
     assert rel_rms(outs[1], g["audio_n2"]) < 1e-3

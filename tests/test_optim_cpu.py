@@ -86,6 +86,57 @@ def test_scaled_adam_many_tensors_vs_oracle(emulated_adam):
         assert rel_rms(a.detach(), b) < 2e-5, n
 
 
+def test_state_dict_loads_into_reference_scaled_adam(emulated_adam):
+    """Checkpoint interop (optim.py:84-101,304-339): a state_dict written here must put the clipping
+    history where the REFERENCE reads it -- `tuples[0]`, the first batch in (str(dtype), *shape) key
+    order -- and the reference optimizer must continue from it exactly like this one does."""
+    ref_root = "/root/reference"
+    if not os.path.isdir(os.path.join(ref_root, "flow2gan")):
+        pytest.skip("reference not mounted")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import import_reference
+    import_reference()
+    from flow2gan.optim import ScaledAdam as RefAdam
+    from flow2gan_b200.optim import ScaledAdam
+    gen = torch.Generator().manual_seed(3)
+    # names chosen so that NAME order and KEY order of the batches differ: 'a...' has the largest shape key
+    shapes = {"a_big": (40, 9), "b_vec": (12,), "c_scalar": (), "d_vec": (12,), "e_small": (3, 5)}
+    init = {k: torch.randn(s, generator=gen) * 0.3 for k, s in shapes.items()}
+    mine = {k: torch.nn.Parameter(v.clone()) for k, v in init.items()}
+    opt = ScaledAdam(list(mine.items()), lr=0.02, clipping_scale=2.0, clipping_update_period=10)
+    grads = [{k: torch.randn(s, generator=gen) for k, s in shapes.items()} for _ in range(16)]
+    for gs in grads[:12]:
+        for k, p in mine.items():
+            p.grad = gs[k].clone()
+        opt.step()
+    import copy
+    sd = copy.deepcopy(opt.state_dict())     # what torch.save / torch.load does (state_dict() itself returns live tensors)
+    theirs = {k: torch.nn.Parameter(v.detach().clone()) for k, v in mine.items()}
+    ref = RefAdam(list(theirs.items()), lr=0.02, clipping_scale=2.0, clipping_update_period=10)
+    ref.load_state_dict(sd)
+    # the reference's "first" batch: smallest (str(dtype), *shape) key
+    keys = sorted({(str(p.dtype), *p.shape) for p in theirs.values()})
+    first = next(p for p in theirs.values() if (str(p.dtype), *p.shape) == keys[0])
+    st = ref.state[first]
+    assert "model_norms" in st and "model_norm_threshold" in st and "num_clipped" in st
+    assert float(st["model_norms"].abs().sum()) > 0
+    for gs in grads[12:]:
+        for k in shapes:
+            mine[k].grad = gs[k].clone()
+            theirs[k].grad = gs[k].clone()
+        opt.step()
+        ref.step()
+    for k in shapes:
+        assert rel_rms(mine[k].detach(), theirs[k].detach()) < 2e-5, k
+
+
+def test_size_update_period_is_bounded():
+    from flow2gan_b200.optim import ScaledAdam
+    with pytest.raises(ValueError, match="size_update_period"):
+        ScaledAdam([("p", torch.nn.Parameter(torch.zeros(4)))], lr=0.1, size_update_period=5)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less box")
 def test_no_cpu_fallback():
     from flow2gan_b200.optim import ScaledAdam

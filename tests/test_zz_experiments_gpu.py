@@ -33,9 +33,8 @@ _ARMS = {}
 
 
 def _run_arm(tmp_path, name, env):
-    """One interpreter per distinct switch setting (cached across the tests of this module: all
-    switches default to off, so the three "base" arms are the same run)."""
-    key = tuple(sorted((k, v) for k, v in env.items() if v != "0"))
+    """One interpreter per distinct switch setting (cached across the tests of this module)."""
+    key = tuple(sorted(env.items()))
     if key not in _ARMS:
         _ARMS[key] = _spawn_arm(tmp_path, name, env)
     return _ARMS[key]
@@ -51,27 +50,19 @@ def _spawn_arm(tmp_path, name, env):
     return torch.load(out)
 
 
-def test_pair_bn_hint_keeps_inference_output(tmp_path):
-    """F2G_PAIR_BN_HINT=1 only changes the N-tile width of the chained pwconv2 problems: every output
-    element still accumulates its K products in the same order."""
-    base = _run_arm(tmp_path, "base", {"F2G_PAIR_BN_HINT": "0"})
-    hint = _run_arm(tmp_path, "hint", {"F2G_PAIR_BN_HINT": "1"})
-    assert torch.isfinite(base).all() and base.shape == (16, 24064)
-    rel = float((base - hint).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
-    assert rel < 1e-6, rel
-
-
-def test_fp16_conditioning_rows_keep_inference_output(tmp_path):
-    """F2G_F16_COND=1 rounds the cond_proj output to fp16 (11 significant bits) before the block prologue
-    adds it: the output moves by far less than the 1e-3 parity budget."""
-    base = _run_arm(tmp_path, "base2", {"F2G_F16_COND": "0"})
-    f16 = _run_arm(tmp_path, "f16cond", {"F2G_F16_COND": "1"})
-    rel = float((base - f16).double().pow(2).mean().sqrt() / base.double().pow(2).mean().sqrt())
-    assert 0.0 < rel < 3e-4, rel
-
-
 def test_cached_time_path_keeps_inference_output_bit_identical(tmp_path):
-    """F2G_CACHE_TIME=1 only moves the time-embedding launches out of the per-step sequence."""
+    """F2G_CACHE_TIME (default on) only moves the time-embedding launches out of the per-step sequence."""
     base = _run_arm(tmp_path, "base3", {"F2G_CACHE_TIME": "0"})
     cached = _run_arm(tmp_path, "cached", {"F2G_CACHE_TIME": "1"})
+    assert torch.isfinite(base).all() and base.shape == (16, 24064)
     assert torch.equal(base, cached)
+
+
+def test_tf32_block_operands_match_fp16_block_operands(tmp_path):
+    """F2G_BLOCK_OPERANDS=tf32 (fp32-container operands, 8-bit exponent) against the default fp16 operands
+    (same 11-bit significand): inside the fp16 range the two builds differ only by accumulation order."""
+    f16 = _run_arm(tmp_path, "f16", {"F2G_BLOCK_OPERANDS": "f16"})
+    tf32 = _run_arm(tmp_path, "tf32", {"F2G_BLOCK_OPERANDS": "tf32"})
+    rel = float((f16 - tf32).double().pow(2).mean().sqrt() / tf32.double().pow(2).mean().sqrt())
+    print("fp16 vs tf32 block operands, 2-step bench shape: rel-RMS", rel)
+    assert rel < 5e-4, rel
