@@ -40,7 +40,7 @@ class F2GGemm(C.Structure):
         ("round_tf32", _i), ("accumulate", _i), ("c_pre", _fp), ("ld_pre", _i), ("split_k", _i),
         ("a_seg_len", _i), ("a_seg_shift", _i), ("a_rows", _i),
         ("ab_f16", _i), ("c_f16", _i),
-        ("done_counter", _fp), ("wait_counter", _fp),
+        ("done_counter", _fp), ("wait_counter", _fp), ("sat_flag", _fp),
     ]
 
 
@@ -55,7 +55,7 @@ class F2GBlockPre(C.Structure):
                 ("inv_rms_out", _fp),
                 ("B", _i), ("T", _i), ("C", _i), ("ld_x", _i), ("ld_cond", _i), ("cond_T", _i),
                 ("factor", _i), ("zero_row", _i), ("ld_ts", _i), ("ld_out", _i),
-                ("zero_ptr", _fp), ("zero_n", _i), ("out_f16", _i)]
+                ("zero_ptr", _fp), ("zero_n", _i), ("out_f16", _i), ("sat_flag", _fp)]
 
 
 class F2GSpecProblem(C.Structure):
@@ -102,6 +102,7 @@ _SIGS = {
     "f2g_abi_version": ([], _i),
     "f2g_last_error": ([], C.c_char_p),
     "f2g_check_device": ([], _i),
+    "f2g_chain_watchdog": ([C.POINTER(_i)], _i),
     "f2g_gemm_tf32": ([C.POINTER(F2GGemm), _i, _fp], _i),
     "f2g_stft": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _i, _f, _fp, _i, _i, _fp], _i),
     "f2g_dc_peak": ([_fp, _i, _i, _i, _fp, _fp], _i),
@@ -168,7 +169,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 6:
+        if lib.f2g_abi_version() != 7:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -212,7 +213,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
               res=None, ld_res=0, res_scale=None, row_scale=None, gate=None, ld_gate=0,
               act=ACT_NONE, leaky=0.0, alpha=1.0, round_tf32=0, accumulate=0, c_pre=None,
               ld_pre=0, split_k=1, a_seg_len=0, a_seg_shift=0, a_rows=0, ab_f16=0, c_f16=0,
-              done_counter=None, wait_counter=None) -> F2GGemm:
+              done_counter=None, wait_counter=None, sat_flag=None) -> F2GGemm:
     d = F2GGemm()
     d.a, d.b, d.c = a, b, c
     d.M, d.N, d.K = M, N, K
@@ -228,6 +229,7 @@ def gemm_desc(a, b, c, M, N, K, lda, ldb, ldc, *, bn=128, a_mn=0, b_mn=0, bias=N
     d.a_seg_len, d.a_seg_shift, d.a_rows = a_seg_len, a_seg_shift, a_rows
     d.ab_f16, d.c_f16 = ab_f16, c_f16
     d.done_counter, d.wait_counter = done_counter, wait_counter
+    d.sat_flag = sat_flag
     return d
 
 
@@ -317,7 +319,8 @@ def block_pre(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, c
 
 
 def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_mask, cond, ld_cond, cond_T,
-                   factor, zero_row, tscale, ld_ts, out, ld_out, conv_out=None, inv_out=None) -> F2GBlockPre:
+                   factor, zero_row, tscale, ld_ts, out, ld_out, conv_out=None, inv_out=None,
+                   sat_flag=None) -> F2GBlockPre:
     d = F2GBlockPre()
     d.x, d.dw_wT, d.dw_b, d.bn_bias, d.bn_log_scale = ptr(x), ptr(dw_wT), ptr(dw_b), ptr(bn_bias), ptr(bn_log_scale)
     d.row_mask, d.cond, d.tscale, d.out = ptr(row_mask), ptr(cond), ptr(tscale), ptr(out)
@@ -326,6 +329,7 @@ def block_pre_desc(x, B, T, Cc, ld_x, dw_wT, dw_b, bn_bias, bn_log_scale, row_ma
     d.factor, d.zero_row, d.ld_ts, d.ld_out = factor, zero_row, ld_ts, ld_out
     # bit flags (include/flow2gan_b200.h): 1 = fp16 output rows, 2 = fp16 conditioning rows
     d.out_f16 = int(out.dtype == torch.float16)
+    d.sat_flag = ptr(sat_flag) if d.out_f16 else None
     return d
 
 

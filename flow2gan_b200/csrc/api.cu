@@ -1,5 +1,6 @@
 // C-ABI glue: error plumbing + device check.  Kernel entry points live next to their kernels.
 #include "common.cuh"
+#include <string.h>
 #include "gemm_tf32.h"
 
 #include <stdarg.h>
@@ -8,13 +9,47 @@
 
 namespace f2g {
 
-static thread_local char g_err[512] = "";
+static thread_local char g_err[1024] = "";
+
+// Watchdog report of the chained GEMM launches (gemm_pair.cu): four ints in mapped pinned host memory
+// {flag, problem, row tile, counter value seen}.  A consumer tile whose producer counter does not
+// arrive within the spin bound writes its coordinates here and traps; host memory stays readable
+// after the context has been poisoned by the trap, so the next failing call can say what happened.
+static int* g_watch_host = nullptr;
+static int* g_watch_dev = nullptr;
+
+int* chain_watchdog_dev() {
+  if (!g_watch_dev) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    memset(h, 0, 4 * sizeof(int));
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFreeHost(h);
+      return nullptr;
+    }
+    g_watch_host = static_cast<int*>(h);
+    g_watch_dev = static_cast<int*>(d);
+  }
+  return g_watch_dev;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+  if (g_watch_host && ((volatile int*)g_watch_host)[0]) {     // every later error is a consequence of the trap
+    const size_t n = strlen(g_err);
+    snprintf(g_err + n, sizeof(g_err) - n,
+             " -- a chained GEMM launch timed out waiting for its producer tiles (problem %d, row tile %d, counter %d) "
+             "and trapped: chained launches of one device must not run concurrently (include/flow2gan_b200.h)",
+             g_watch_host[1], g_watch_host[2], g_watch_host[3]);
+  }
 }
 
 bool pdl_enabled() {
@@ -58,6 +93,11 @@ int f2g_check_device(void) {
     return f2g::F2G_EARCH;
   }
   return 0;
+}
+
+int f2g_chain_watchdog(int out[4]) {
+  for (int i = 0; i < 4; ++i) out[i] = f2g::g_watch_host ? ((volatile int*)f2g::g_watch_host)[i] : 0;
+  return out[0];
 }
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream) {

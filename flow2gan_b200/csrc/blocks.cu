@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   if (!live) return;
   const float gain = expf(*P.bn_log_scale);
   const float inv_c = 1.0f / (float)C;
+  float amax = 0.f;      // fp16 range guard: largest |value| handed to the saturating conversion
 #pragma unroll
   for (int s = 0; s < PRE_S; ++s) {
     const int t = t0 + s;
@@ -213,10 +214,13 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     if (P.out_f16) {   // operand of a kind::f16 GEMM: same 11-bit significand as the TF32 rounding
       __half* o = reinterpret_cast<__half*>(P.out) + (rb + t) * (size_t)P.ld_out + c;
       *reinterpret_cast<uint2*>(o) = pack_half4(z);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(z.x), fabsf(z.y)), fmaxf(fabsf(z.z), fabsf(z.w))));
+      amax = (z.x - z.x + z.y - z.y + z.z - z.z + z.w - z.w) == 0.f ? amax : 3.0e38f;     // inf / NaN
     } else {
       st4(P.out + (rb + t) * P.ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
     }
   }
+  if (P.sat_flag && !(amax <= 65504.f)) atomicOr(P.sat_flag, 2);
 }
 
 // Batched small dense layers (up to 4 independent problems per launch, blockIdx.y = problem):
@@ -400,7 +404,7 @@ extern "C" int f2g_block_pre(const float* x, int B, int T, int C, int ld_x, cons
   p.ld_cond = ld_cond; p.cond_T = cond_T; p.factor = factor; p.zero_row = zero_row;
   p.tscale = tscale; p.ld_ts = ld_ts; p.out = out; p.ld_out = ld_out; p.conv_out = conv_out;
   p.inv_rms_out = inv_rms_out;
-  p.out_f16 = 0; p.zero_ptr = nullptr; p.zero_n = 0;
+  p.out_f16 = 0; p.zero_ptr = nullptr; p.zero_n = 0; p.sat_flag = nullptr;
   return f2g_block_pre_group(&p, 1, stream);
 }
 

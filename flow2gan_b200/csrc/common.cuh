@@ -20,6 +20,7 @@ namespace f2g {
 enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+int* chain_watchdog_dev();   // mapped pinned {flag, problem, row tile, counter} (api.cu), nullptr if unavailable
 
 // ---------------------------------------------------------------------------------------
 // numerics

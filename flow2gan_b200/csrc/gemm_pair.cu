@@ -29,7 +29,15 @@ constexpr int P_A_BYTES = PBM * PBK * 4;       // 16 KB
 constexpr int P_STAGE_BYTES = 2 * P_A_BYTES;   // A + up to 128 B-tile rows
 constexpr int P_STAGES = 5;
 constexpr int P_EPI_WARPS = 8;
-constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+// TMA producer warps: warp 0 plus P_PROD_WARPS - 1 warps behind the epilogue warps.  One elected thread
+// needs ~270 cycles per (wait, expect_tx, cp.async.bulk) round (tools/tma_rate_probe.cu: 0.137 us per
+// copy per issuing warp, independent of the copy size up to 16 KB, scaling linearly with the number of
+// issuing warps) -- with a single producer the 2 (K-major) to 8 (MN-major: 32-row boxes) copies of a
+// pipeline stage took as long as or longer than the stage's 512 tensor cycles.  The copies of a stage
+// are dealt round-robin to the producer warps.
+constexpr int P_PROD_WARPS = 3;       // 12 warps per CTA: register allocation is per 4 warps (13 warps cost the budget of 16)
+constexpr int P_FIRST_EXTRA_PROD = 2 + P_EPI_WARPS;            // warp index of producer 1
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS + 32 * (P_PROD_WARPS - 1);
 constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 36 * 4;
 constexpr int P_PARAM_BYTES = 3 * 256 * 4;
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + P_PARAM_BYTES;
@@ -59,6 +67,7 @@ struct alignas(64) PProblem {
   int* done;                // chaining (F2GGemm::done_counter / wait_counter)
   const int* wait;
   int wait_count;
+  int* sat_flag;            // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag)
 };
 
 struct alignas(64) PGroup {
@@ -74,7 +83,13 @@ struct alignas(64) PGroup {
   uint16_t sched[P_MAX_SCHED];
   int dbg;   // bring-up (F2G_PAIR_DBG): bit0 = epilogue drains TMEM but stores nothing,
              // bit1 = epilogue skips TMEM loads too
+  int* watchdog;   // mapped pinned host ints {flag, problem, row tile, counter seen} or nullptr
 };
+
+// Spin bound of a chained consumer tile: 2^22 polls x (>= 64 ns sleep + one L2 round trip) is seconds, five
+// orders of magnitude beyond any launch of this library.  Reaching it means the producer CTAs are not
+// running (two chained launches sharing the device, see the header): report and trap instead of hanging.
+constexpr uint32_t P_CHAIN_SPIN_LIMIT = 1u << 22;
 
 struct PTile {
   int prob, m0, n0, kb0, kb1;
@@ -246,8 +261,9 @@ F2G_DEVINL void epi_fast_chunk(const float* __restrict__ sl, float* __restrict__
 // BIAS_ACT chunk with an fp16 destination (the hidden activation of a ConvNeXt block, which only
 // the next GEMM reads): x = prelu(alpha*acc + bias) -> RN fp16, one 8-byte store per row quad.
 template <bool FULL>
-F2G_DEVINL void epi_fast_chunk_h(const float* __restrict__ sl, __half* __restrict__ cp, size_t cstep,
-                                 int rows_left, float alpha, float4 bias4, float4 slope4) {
+F2G_DEVINL float epi_fast_chunk_h(const float* __restrict__ sl, __half* __restrict__ cp, size_t cstep,
+                                  int rows_left, float alpha, float4 bias4, float4 slope4) {
+  float amax = 0.f;       // fp16 range guard: |x| before the saturating conversion
   float4 xv[8];
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) xv[rr] = *reinterpret_cast<const float4*>(sl + rr * (4 * 36));
@@ -258,8 +274,13 @@ F2G_DEVINL void epi_fast_chunk_h(const float* __restrict__ sl, __half* __restric
     x.z = fmaf(xv[rr].z, alpha, bias4.z); x.w = fmaf(xv[rr].w, alpha, bias4.w);
     x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;
     x.z = x.z > 0.f ? x.z : x.z * slope4.z; x.w = x.w > 0.f ? x.w : x.w * slope4.w;
-    if (FULL || rr * 4 < rows_left) *reinterpret_cast<uint2*>(cp + rr * cstep) = pack_half4(x);
+    if (FULL || rr * 4 < rows_left) {
+      *reinterpret_cast<uint2*>(cp + rr * cstep) = pack_half4(x);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+      amax = (x.x - x.x + x.y - x.y + x.z - x.z + x.w - x.w) == 0.f ? amax : 3.0e38f;    // inf / NaN
+    }
   }
+  return amax;
 }
 
 template <int A_MN, int B_MN, int EPI, int F16>
@@ -314,8 +335,12 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
   pdl_wait();                  // everything above overlapped the previous kernel's tail
   pdl_launch();
 
-  if (warp == 0) {
-    // ------------------------------- TMA producer (both CTAs) --------------------------
+  const int prod = warp == 0 ? 0 : (warp >= P_FIRST_EXTRA_PROD ? warp - P_FIRST_EXTRA_PROD + 1 : -1);
+  if (prod >= 0) {
+    // ------------------------------- TMA producers (both CTAs) -------------------------
+    // Copy ops of one stage: A first (1 K-major box of 128 rows, or PBM/32 MN-major boxes), then B
+    // (1 box of bn/2 rows, or bn/64 MN-major boxes); op i belongs to producer i % P_PROD_WARPS.
+    // Producer 0 of the leader CTA posts the stage's expected byte count (both CTAs' copies).
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -327,17 +352,42 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         const int m_cta = tc.m0 + (int)rank * PBM;
         const int n_cta = tc.n0 + (int)rank * bhalf;
         const uint32_t stage_tx = 2u * (uint32_t)(P_A_BYTES + bhalf * PBK * 4);
-        if (pr.wait) {   // chained consumer: the A rows of this 256-row tile come from a producer
-                         // problem of this launch; wait until all of its tiles over them are stored
+        constexpr int n_a = A_MN ? PBM / 32 : 1;
+        const int n_b = B_MN ? (bhalf >> 5) : 1;
+        const int n_kb = tc.kb1 - tc.kb0;
+        if (prod >= n_a + n_b) {            // nothing to copy for this tile: just keep the ring position
+          stage += n_kb;
+          phase ^= (uint32_t)((stage / P_STAGES) & 1);
+          stage %= P_STAGES;
+          continue;
+        }
+        bool mine_a = false;
+#pragma unroll
+        for (int j = 0; j < n_a; ++j) mine_a |= (j % P_PROD_WARPS) == prod;
+        if (pr.wait && mine_a) {   // chained consumer: the A rows of this 256-row tile come from a producer
+                                   // problem of this launch; wait until all of its tiles over them are stored
           const int* wp = pr.wait + tc.m0 / (2 * PBM);
-          while (ld_acquire_gpu(wp) < pr.wait_count) __nanosleep(64);
+          uint32_t polls = 0;
+          while (ld_acquire_gpu(wp) < pr.wait_count) {
+            __nanosleep(64);
+            if (++polls > P_CHAIN_SPIN_LIMIT) {
+              if (g.watchdog) {
+                volatile int* wd = g.watchdog;
+                wd[1] = tc.prob; wd[2] = tc.m0 / (2 * PBM); wd[3] = ld_acquire_gpu(wp);
+                __threadfence_system();
+                wd[0] = 1;
+                __threadfence_system();
+              }
+              __trap();
+            }
+          }
           fence_proxy_async_all();
         }
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
           uint8_t* sb = sa + P_A_BYTES;
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          if (rank == 0 && prod == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
           const int kc = kb * KELEM;                    // beyond K: TMA zero-fills
           // windowed A (implicit im2col): contraction segment s = one kernel row, which lives
@@ -345,6 +395,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < PBM / 32; ++j) {
+              if ((j % P_PROD_WARPS) != prod) continue;
               int mm = m_cta + 32 * j, kk = kc;
               if (pr.seg_len) {
                 const int s = mm / pr.seg_len;
@@ -353,7 +404,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               }
               tma_load_2d_cg2(sa + j * 4096, &pr.map_a, lbar, mm, kk);
             }
-          } else {
+          } else if (prod == 0) {
             int kca = kc, ma = m_cta;
             if (pr.seg_len) {
               const int s = kc / pr.seg_len;
@@ -364,8 +415,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
           }
           if (B_MN) {
             for (int j = 0; j < (bhalf >> 5); ++j)
-              tma_load_2d_cg2(sb + j * 4096, &pr.map_b, lbar, n_cta + 32 * j, kc);
-          } else {
+              if (((n_a + j) % P_PROD_WARPS) == prod) tma_load_2d_cg2(sb + j * 4096, &pr.map_b, lbar, n_cta + 32 * j, kc);
+          } else if ((n_a % P_PROD_WARPS) == prod) {
             tma_load_2d_cg2(sb, &pr.map_b, lbar, kc, n_cta);
           }
           if (++stage == P_STAGES) {
@@ -479,6 +530,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
 
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
+      float amax_t = 0.f;      // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag)
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= N || (g.dbg & 2)) break;
@@ -502,8 +554,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         if (F16 && (EPI == PEPI_BIAS_ACT || EPI == PEPI_MLP) && chunk_full && c16) {
           const float* sl = scratch + rsub * 36 + 4 * cg;
           __half* hp = reinterpret_cast<__half*>(cbase) + (size_t)(row_base + rsub) * ldc + col;
-          if (rows >= 32) epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4);
-          else epi_fast_chunk_h<false>(sl, hp, (size_t)4 * ldc, rows - rsub, alpha, bias4, slope4);
+          if (rows >= 32) amax_t = fmaxf(amax_t, epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4));
+          else amax_t = fmaxf(amax_t, epi_fast_chunk_h<false>(sl, hp, (size_t)4 * ldc, rows - rsub, alpha, bias4, slope4));
           __syncwarp();
           continue;
         }
@@ -578,6 +630,8 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
             if (c16) {
               *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(cbase) + (size_t)row * ldc + col) =
                   pack_half4(make_float4(x[0], x[1], x[2], x[3]));
+              amax_t = fmaxf(amax_t, fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
+              amax_t = (x[0] - x[0] + x[1] - x[1] + x[2] - x[2] + x[3] - x[3]) == 0.f ? amax_t : 3.0e38f;
               continue;
             }
             float* dst = cbase + (size_t)row * ldc + col;
@@ -609,6 +663,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               if (c16) {
                 reinterpret_cast<__half*>(cbase)[(size_t)row * ldc + col + e] =
                     __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+                amax_t = (x - x) == 0.f ? fmaxf(amax_t, fabsf(x)) : 3.0e38f;
                 continue;
               }
               float* dst = cbase + (size_t)row * ldc + col + e;
@@ -619,6 +674,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         }
         __syncwarp();
       }
+      if (F16 && pr.sat_flag && !(amax_t <= 65504.f)) atomicOr(pr.sat_flag, 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
@@ -918,6 +974,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     if (rc) return rc;
     p.seg_len = d.a_seg_len; p.seg_shift = d.a_seg_shift;
     p.c_f16 = d.c_f16;
+    p.sat_flag = d.c_f16 ? d.sat_flag : nullptr;
     rc = b_mn ? pair_encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
               : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false, f16);
     if (rc) return rc;
@@ -961,6 +1018,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   }
   g.n_problems = n;
   g.total_tiles = tiles;
+  g.watchdog = chained ? chain_watchdog_dev() : nullptr;
   static const int dbg = getenv("F2G_PAIR_DBG") ? atoi(getenv("F2G_PAIR_DBG")) : 0;
   g.dbg = dbg;
 

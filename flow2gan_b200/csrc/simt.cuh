@@ -307,6 +307,12 @@ static inline float atomicAdd(float* p, float v) {
   *p = old + v;
   return old;
 }
+static inline int atomicOr(int* p, int v) {
+  std::lock_guard<std::mutex> lk(f2g::g_atomic_mu);
+  const int old = *p;
+  *p = old | v;
+  return old;
+}
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
 static inline unsigned __brev(unsigned v) {

@@ -51,6 +51,43 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+# Chained GEMM launches (pwconv1 -> pwconv2 through per-row-tile counters, csrc/gemm_pair.cu) need all
+# CTAs of the launch resident: consumer tiles spin until the producer tiles -- possibly in CTAs that
+# are not scheduled yet -- have stored their rows.  Two such launches running at the same time on two
+# streams can starve each other of SMs.  Per device, the host therefore serialises every launch
+# sequence that contains chained launches (an eager `_run`, a graph replay) across streams: the next
+# one waits for an event recorded behind the previous one whenever that was issued on another stream.
+_CHAIN_GUARD: Dict[int, Tuple[torch.cuda.Event, int]] = {}
+
+
+class _chain_guard:
+    """with _chain_guard(device): <issue launches containing chained GEMMs on the current stream>"""
+
+    def __init__(self, device: torch.device):
+        self.cuda = device.type == "cuda"
+        self.idx = device.index if device.index is not None or not self.cuda else torch.cuda.current_device()
+
+    def __enter__(self):
+        # inside an outer capture: one stream by construction
+        self.skip = (not self.cuda) or torch.cuda.is_current_stream_capturing()
+        if self.skip:
+            return self
+        cur = torch.cuda.current_stream(self.idx)
+        prev = _CHAIN_GUARD.get(self.idx)
+        if prev is not None and prev[1] != cur.cuda_stream:
+            cur.wait_event(prev[0])
+        return self
+
+    def __exit__(self, *exc):
+        if not self.skip:
+            cur = torch.cuda.current_stream(self.idx)
+            prev = _CHAIN_GUARD.get(self.idx)
+            ev = prev[0] if prev is not None else torch.cuda.Event()
+            ev.record(cur)
+            _CHAIN_GUARD[self.idx] = (ev, cur.cuda_stream)
+        return False
+
+
 _version_of = operator.attrgetter("_version")
 
 
@@ -127,6 +164,25 @@ class PackedGenerator:
     def stale(self) -> bool:
         return _params_signature(self._plist) != self.signature
 
+    def fp16_weight_error(self) -> float:
+        """Largest relative Frobenius error of the fp16 weight copies handed out so far against their
+        fp32 sources.  11-bit rounding alone gives ~1.4e-4; overflow (inf) or underflow (weights below
+        fp16's 6e-8 subnormal step flushing to zero) shows up as a much larger figure.  One host
+        read-back: called once per plan by the fp16 range guard (generator.py), never per step."""
+        pairs = []
+        for bw in self.ce_blocks + [b for br in self.branches for b in br.blocks]:
+            if bw._half is not None:
+                blk = bw.blk
+                pairs += [(bw._half[0], blk.pwconv1.weight.detach().reshape(bw.H, bw.C)),
+                          (bw._half[1], blk.pwconv2.weight.detach().reshape(bw.C, bw.H))]
+        for br in self.branches:
+            pairs += [(t, getattr(br, nm)) for nm, t in br._halves.items()]
+        if not pairs:
+            return 0.0
+        errs = torch.stack([(h.float() - w).norm() / w.norm().clamp_min(1e-30) for h, w in pairs])
+        errs = torch.nan_to_num(errs, nan=float("inf"))
+        return float(errs.max())
+
     def refresh(self) -> None:
         m = self.model
         first = not self._built
@@ -193,13 +249,13 @@ class PackedGenerator:
         self.signature = _params_signature(self._plist)
 
 
-def _g1(bw: _BlockW, a, h, M, bn=None, done=None):
+def _g1(bw: _BlockW, a, h, M, bn=None, done=None, sat=None):
     bn = bn or BN_G1
     b = bw.blk
     if a.dtype == torch.float16:          # a1 (fp16) x W1 (fp16) -> h (fp16)
         return L.gemm_desc(a.data_ptr(), bw.half()[0].data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C,
                            bw.H, bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
-                           act=L.ACT_PRELU, ab_f16=1, c_f16=1, done_counter=done)
+                           act=L.ACT_PRELU, ab_f16=1, c_f16=1, done_counter=done, sat_flag=L.ptr(sat))
     return L.gemm_desc(a.data_ptr(), bw.W1.data_ptr(), h.data_ptr(), M, bw.H, bw.C, bw.C, bw.C, bw.H,
                        bn=bn, bias=b.pwconv1.bias.data_ptr(), slope=b.act.weight.data_ptr(),
                        act=L.ACT_PRELU, round_tf32=1)
@@ -240,7 +296,8 @@ class InferencePlan:
         self.B, self.Fm, self.T, self.masked = B, Fm, T, masked
         dev = next(model.parameters()).device
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
-        op_dt = torch.float16 if BLOCK_OPERANDS == "f16" else torch.float32
+        self.operands = getattr(model, "_block_operands", None) or BLOCK_OPERANDS
+        op_dt = torch.float16 if self.operands == "f16" else torch.float32
         zo = lambda *s: torch.zeros(*s, device=dev, dtype=op_dt)      # block GEMM operands (a1, h)
         ce = model.cond_encoder
         self.n_mels = ce.cond_dim
@@ -278,8 +335,14 @@ class InferencePlan:
             w.mask = z(w.R) if masked else None
             self.br.append(w)
         # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
-        self.f16 = BLOCK_OPERANDS == "f16"
+        self.f16 = self.operands == "f16"
         self.chained = CHAIN_MLP and self.f16
+        # fp16 range guard: every kernel that converts an operand to fp16 (block prologue: bit 1, GEMM
+        # epilogues with an fp16 destination: bit 0) ORs into this flag when a value leaves +-65504 or is
+        # not finite; it is cleared at the start of every launch sequence and mirrored to pinned host
+        # memory behind it (generator.py reads it and falls back to TF32 operands)
+        self.sat = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.sat_host = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
         self.c0h = zo(self.Rc, self.Cc)
         self.cm_chain = torch.zeros(len(packed.branches) * ((self.Rc + 255) // 256), device=dev, dtype=torch.int32)
         self.ce_chain = torch.zeros((self.Rc + 255) // 256, device=dev, dtype=torch.int32)
@@ -294,6 +357,7 @@ class InferencePlan:
         self._side: Optional[torch.cuda.Stream] = None
         self.graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
         self._seen: Dict[Tuple[int, bool], bool] = {}
+        self._range_checked = False                 # generator.py: fp16 range flag read back after the first call
 
     # ------------------------------------------------------------------ step-invariant part
     def encode_cond(self) -> None:
@@ -309,15 +373,16 @@ class InferencePlan:
             b = bw.blk
             last = li == len(pk.ce_blocks) - 1      # c0 is then only a GEMM operand: RN-round it
             pre = L.block_pre_desc(self.c0, B, Fm, bw.C, bw.C, bw.dwT, b.dwconv.bias, b.norm.bias,
-                                   b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C)
+                                   b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C,
+                                   sat_flag=self.sat)
             if self.chained:
                 L.block_pre_group([pre], zero=self.ce_chain)
                 cnt = self.ce_chain.data_ptr()
-                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M, done=cnt),
+                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M, done=cnt, sat=self.sat),
                               _g2(bw, self.ce_h, self.c0, M, round_out=int(last), wait=cnt)])
             else:
                 L.block_pre_group([pre])
-                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M)])
+                L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M, sat=self.sat)])
                 L.gemm_group([_g2(bw, self.ce_h, self.c0, M, round_out=int(last))])
         self.cond_paths()
 
@@ -327,8 +392,8 @@ class InferencePlan:
         if self.f16:
             # fp16 operands (c0 was RN-rounded to 11 significant bits by the last CondEncoder block, so
             # the conversion is exact); cond_mlp[0] -> PReLU -> cond_mlp[2] is one chained launch
-            self.c0h.copy_(self.c0)
-            if self.chained:
+            self.c0h.copy_(self.c0)                # torch's fp32 -> fp16 conversion overflows to inf: the first
+            if self.chained:                       # consumer GEMM's epilogue then reports a non-finite value
                 self.cm_chain.zero_()
             g0, g2, g3 = [], [], []
             ntile = (Rc + 255) // 256
@@ -339,11 +404,11 @@ class InferencePlan:
                 g0.append(L.gemm_desc(self.c0h.data_ptr(), W0.data_ptr(), w.cm_h.data_ptr(), Rc, bw.ch, bw.cc,
                                       bw.cc, bw.cc, bw.ch, bias=cm[0].bias.data_ptr(),
                                       slope=cm[1].weight.data_ptr(), act=L.ACT_PRELU, ab_f16=1, c_f16=1,
-                                      done_counter=cnt))
+                                      done_counter=cnt, sat_flag=L.ptr(self.sat)))
                 # bias-only epilogue with an fp16 destination = "leaky ReLU with slope 1"
                 g2.append(L.gemm_desc(w.cm_h.data_ptr(), W2.data_ptr(), w.c1.data_ptr(), Rc, bw.cc, bw.ch,
                                       bw.ch, bw.ch, bw.cc, bias=cm[2].bias.data_ptr(), act=L.ACT_LEAKY,
-                                      leaky=1.0, ab_f16=1, c_f16=1, wait_counter=cnt))
+                                      leaky=1.0, ab_f16=1, c_f16=1, wait_counter=cnt, sat_flag=L.ptr(self.sat)))
                 N = bw.nl * bw.C
                 g3.append(L.gemm_desc(w.c1.data_ptr(), Wc.data_ptr(), w.cp.data_ptr(), Rc, N, bw.cc,
                                       bw.cc, bw.cc, N, bias=bw.bcp.data_ptr(), ab_f16=1))
@@ -422,17 +487,18 @@ class InferencePlan:
                 ldc = bw.nl * bw.C
                 pre.append(L.block_pre_desc(w.x, B, w.F, bw.C, bw.C, k.dwT, b.dwconv.bias, b.norm.bias,
                                             b.norm.log_scale, w.mask, w.cp[:, i * bw.C:], ldc, Fm,
-                                            bw.factor, B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C))
+                                            bw.factor, B * Fm, w.ts[:, i * bw.C:], 0, w.a1, bw.C,
+                                            sat_flag=self.sat))
             if self.chained:                # prologues, then pwconv1 -> pwconv2 of all branches: 2 launches
                 L.block_pre_group(pre, zero=self.chain)
                 cnt = [self.chain.data_ptr() + 4 * o for o in self.chain_off]
-                L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R, done=c)
+                L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R, done=c, sat=self.sat)
                               for bw, w, c in zip(pk.branches, self.br, cnt)] +
                              [_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1), wait=c)
                               for bw, w, c in zip(pk.branches, self.br, cnt)])
                 continue
             L.block_pre_group(pre)          # the three branches' prologues: one launch
-            L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R) for bw, w in zip(pk.branches, self.br)])
+            L.gemm_group([_g1(bw.blocks[i], w.a1, w.h, w.R, sat=self.sat) for bw, w in zip(pk.branches, self.br)])
             L.gemm_group([_g2(bw.blocks[i], w.h, w.x, w.R, round_out=int(i == nl - 1))
                           for bw, w in zip(pk.branches, self.br)])
         L.gemm_group([L.gemm_desc(w.x.data_ptr(), bw.Wout.data_ptr(), w.pout.data_ptr(), w.R, bw.nin,
@@ -483,6 +549,8 @@ class InferencePlan:
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
         ts, dt = self._steps
+        if self.f16:
+            self.sat.zero_()
         forked = with_cond and FORK_COND
         if forked:
             # The conditioning path (CondEncoder + cond_mlp + cond_proj: ~20 launches of GEMMs with
@@ -490,7 +558,7 @@ class InferencePlan:
             # evaluation (STFT, in_proj, norms, time MLP: small kernels) are independent: run them
             # on two streams and join before the first block prologue.  Under stream capture the
             # fork/join becomes two parallel branches of the graph.
-            if BLOCK_OPERANDS == "f16":        # lazily built fp16 weights: allocate on the main stream
+            if self.f16:                       # lazily built fp16 weights: allocate on the main stream
                 for bw in self.pk.ce_blocks:
                     bw.half()
                 for bw in self.pk.branches:
@@ -518,6 +586,8 @@ class InferencePlan:
                     w.ts = ts_k
             self.process_blocks()
             self.combine(self.x_audio, True, ts[k], dt, clamp and k == n - 1)
+        if self.f16 and self.sat_host.is_pinned():
+            self.sat_host.copy_(self.sat, non_blocking=True)      # 4 bytes, read by the caller (generator.py)
 
     def set_masks(self, lens: Tensor) -> None:
         self.lens.copy_(lens.to(torch.int32))
@@ -548,22 +618,25 @@ class InferencePlan:
             out.copy_(self.x_audio, non_blocking=True)
             return out
 
+        dev = self.x_audio.device
         if not use_graph:
             self._steps = self._prepare_steps(n)
-            self._run(n, clamp)
+            with _chain_guard(dev):
+                self._run(n, clamp)
             return result()
         g = self.graphs.get(key)
         if g is None and not self._seen.get(key):
-            # first call for this (weights, shape): run eagerly; capture on the second call, so a
-            # training loop whose weights change every iteration never pays for graph capture
+            # first call for this shape: run eagerly; capture on the second call
             self._seen[key] = True
             self._steps = self._prepare_steps(n)
-            self._run(n, clamp)
+            with _chain_guard(dev):
+                self._run(n, clamp)
             return result()
         if g is None:
             x0 = self.x_audio.clone()
             self._steps = self._prepare_steps(n)
-            self._run(n, clamp)                     # warm-up (also sets kernel attributes)
+            with _chain_guard(dev):
+                self._run(n, clamp)                 # warm-up (also sets kernel attributes)
             self.x_audio.copy_(x0)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -573,7 +646,8 @@ class InferencePlan:
         else:
             g, self._steps, self.t_all = g
             self._refresh_time_cache(n)             # weights repacked in place since the capture?
-        g.replay()
+        with _chain_guard(dev):
+            g.replay()
         return result()
 
     def infer_from_cond(self, cond: Tensor, noise: Tensor, lens: Optional[Tensor], n: int,
@@ -584,6 +658,7 @@ class InferencePlan:
         if self.masked:
             self.set_masks(lens)
         self._steps = self._prepare_steps(n)
-        self.cond_paths()
-        self._run(n, clamp, with_cond=False)
+        with _chain_guard(self.x_audio.device):
+            self.cond_paths()
+            self._run(n, clamp, with_cond=False)
         return self.x_audio.clone()

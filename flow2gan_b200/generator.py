@@ -79,6 +79,7 @@ class BaseAudioGenerator(nn.Module):
         self.apply(self._init_weights)
         self._packed: Optional[PackedGenerator] = None
         self._plans: Dict[tuple, InferencePlan] = {}
+        self._block_operands: Optional[str] = None      # None = engine default (fp16); "tf32" after a range fallback
 
     @torch.no_grad()
     def _init_weights(self, m):
@@ -191,9 +192,44 @@ class MelAudioGenerator(BaseAudioGenerator):
             from .train import generator_infer_with_grad
             return generator_infer_with_grad(self, cond, noise, audio_lens, n_timesteps, clamp_pred)
         p = self.plan(cond.shape[0], cond.shape[2], length, audio_lens is not None)
+        capturing = torch.cuda.is_current_stream_capturing()
         with torch.no_grad():
+            if p.f16 and not capturing and int(p.sat_host[0]) != 0:
+                # deferred report of an EARLIER graph replay of this plan (the flag travels to pinned host
+                # memory behind every launch sequence): that result is already with the caller, so say so
+                # loudly, and serve this and all later calls with TF32 operands
+                p = self._fp16_fallback(p, cond, length, audio_lens, "an earlier call")
+            rng = None
+            if noise is None and p.f16 and not capturing and not p._range_checked:
+                rng = torch.cuda.get_rng_state(dev)       # the checked first call may have to be repeated
             # inside an outer stream capture the plan's launches become part of that graph;
             # noise=None: drawn from the global RNG straight into the plan's sample buffer
-            return p.infer(cond, None if noise is None else noise.float(), audio_lens, n_timesteps, clamp_pred,
-                           use_graph=not torch.cuda.is_current_stream_capturing(),
-                           noise_scale=self.init_noise_scale, out=out)
+            y = p.infer(cond, None if noise is None else noise.float(), audio_lens, n_timesteps, clamp_pred,
+                        use_graph=not capturing, noise_scale=self.init_noise_scale, out=out)
+            if p.f16 and not capturing and not p._range_checked:
+                # first call of a plan (it runs eagerly anyway): one 4-byte read-back decides whether this
+                # model / input scale fits fp16 operands; if not, redo the call with TF32 operands
+                p._range_checked = True
+                w_err = self._packed.fp16_weight_error()
+                if w_err > 1e-3:
+                    p.sat.fill_(4)                       # bit 2: weights do not survive the fp16 conversion
+                if int(p.sat.item()) != 0:
+                    p = self._fp16_fallback(p, cond, length, audio_lens, "this call (repeated with TF32 operands)")
+                    if rng is not None:
+                        torch.cuda.set_rng_state(rng, dev)
+                    y = p.infer(cond, None if noise is None else noise.float(), audio_lens, n_timesteps, clamp_pred,
+                                use_graph=False, noise_scale=self.init_noise_scale, out=out)
+            return y
+
+    def _fp16_fallback(self, p: InferencePlan, cond: Tensor, length: int, audio_lens, when: str) -> InferencePlan:
+        """fp16 operands share TF32's 11-bit significand but not its exponent range: when a block operand
+        (prologue output, hidden activation, conditioning row) left +-65504 the kernels saturated it and
+        raised the plan's range flag.  Switch this model to TF32 operands (fp32 containers) for good."""
+        import logging
+        bits = int(p.sat.item()) | int(p.sat_host[0])
+        logging.warning("flow2gan_b200: fp16 block operands out of range (flag %d: %s) in %s -- switching this "
+                        "model to TF32 operands", bits,
+                        " + ".join(n for b, n in ((1, "GEMM epilogue"), (2, "block prologue"), (4, "weights")) if bits & b), when)
+        self._block_operands = "tf32"
+        self._plans = {}
+        return self.plan(cond.shape[0], cond.shape[2], length, audio_lens is not None)

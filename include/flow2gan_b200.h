@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 6
+#define F2G_ABI_VERSION 7
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -99,7 +99,20 @@ typedef struct F2GGemm {
    * CTA-pair kernel only. */
   int* done_counter;
   const int* wait_counter;
+  /* fp16 range guard (c_f16 = 1 only): when any value written to C lies outside +-65504 BEFORE the
+   * saturating conversion (or is not finite), bit 0 of *sat_flag is set (atomicOr).  NULL: no check.
+   * The host layer clears the flag per call and falls back to TF32 operands when it comes back set
+   * (engine.py: fp16 shares TF32's 11-bit significand but not its 8-bit exponent). */
+  int* sat_flag;
 } F2GGemm;
+
+/* Watchdog of chained launches (done_counter / wait_counter): a consumer tile that does not see its
+ * producer counter within ~1 s of polling writes {1, problem, row tile, counter value} to a mapped host
+ * record and traps (the launch fails instead of hanging; f2g_last_error() of the next failing call
+ * carries the record).  Chained launches rely on all their CTAs becoming resident: two of them must
+ * not run concurrently on one device (serialise them across streams -- the Python host layer does,
+ * engine.py::_chain_guard).  Returns the flag; out = the record. */
+int f2g_chain_watchdog(int out[4]);
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
 
@@ -191,6 +204,8 @@ typedef struct F2GBlockPre {
   int out_f16; /* F2G_PRE_OUT_F16 (1): `out` points to fp16 rows (ld_out in elements, multiple of 4),
                   RN-rounded and clamped to +-65504 instead of TF32-rounded fp32 -- operand of an
                   ab_f16 GEMM */
+  int* sat_flag; /* fp16 range guard (out_f16 only): bit 1 of *sat_flag is set when a value lies outside
+                    +-65504 before the clamp (or is not finite); NULL: no check */
 } F2GBlockPre;
 enum { F2G_PRE_OUT_F16 = 1 };
 int f2g_block_pre_group(const F2GBlockPre* problems, int n_problems, void* stream);

@@ -74,6 +74,10 @@ extern "C" int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void*) {
         if (d.row_scale) x *= d.row_scale[m];
         if (d.c_f16) {
           store_half_sat(d.c, (long long)m * d.ldc + n, x);
+          if (d.sat_flag && !(fabsf(x) <= 65504.f)) {      // fp16 range guard (F2GGemm::sat_flag, bit 0)
+#pragma omp atomic
+            *d.sat_flag |= 1;
+          }
           continue;
         }
         float* cp = d.c + (long long)m * d.ldc + n;

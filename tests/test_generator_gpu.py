@@ -111,3 +111,74 @@ def test_infer_harsh_weights_stress():
     err = rel_rms(out.cpu(), ref)
     print("harsh-weights rel-RMS:", err)
     assert err < 3e-3
+
+
+def test_fp16_range_guard_falls_back_to_tf32(caplog):
+    """fp16 operands have TF32's significand but not its exponent range.  Weights whose hidden activation
+    leaves +-65504 (pwconv1 of one block scaled by 3e5, pwconv2 by 1/3e5: PReLU is positively homogeneous,
+    so the block computes the same function) must NOT silently saturate: the range flag raised by the
+    epilogue makes the first call repeat itself with TF32 operands, the model stays in TF32 mode, and the
+    result still meets the 1e-3 gate against the fp32 oracle."""
+    import logging
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    m, sd = _model(g["model_name"], g["sd_spec"], g["sd_seed"])
+    S = 3.0e5
+    pre = "estimators.0.decoder.blocks.3."
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd[pre + "pwconv1.weight"] *= S
+    sd[pre + "pwconv1.bias"] *= S
+    sd[pre + "pwconv2.weight"] /= S
+    m.load_state_dict(sd, strict=False)
+    mel, noise = g["mel"].cuda(), g["noise"].cuda()
+    ref = O.generator_infer(sd, O.generator_config(g["model_name"]), g["mel"], g["noise"], None, 2, False)
+    with caplog.at_level(logging.WARNING):
+        out = m.infer(mel, n_timesteps=2, noise=noise)
+    assert m._block_operands == "tf32", "the range flag did not trigger the TF32 fallback"
+    assert any("out of range" in r.message for r in caplog.records)
+    err = rel_rms(out.cpu(), ref)
+    print("scaled block, after fallback: rel-RMS vs fp32 oracle %.3e" % err)
+    assert err < TOL
+    plan = next(iter(m._plans.values()))
+    assert not plan.f16
+    again = m.infer(mel, n_timesteps=2, noise=noise)            # later calls: TF32 plan, graph capture + replay
+    third = m.infer(mel, n_timesteps=2, noise=noise)
+    assert rel_rms(again.cpu(), ref) < TOL and torch.equal(again, third)
+
+
+def test_fp16_range_flag_reported_by_a_later_call(caplog):
+    """Graph replays cannot be repeated after the fact: their range flag travels to pinned host memory
+    behind the launch sequence and the NEXT call reports it and switches the model to TF32 operands."""
+    import logging
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    m, sd = _model(g["model_name"], g["sd_spec"], g["sd_seed"])
+    mel, noise = g["mel"].cuda(), g["noise"].cuda()
+    a = m.infer(mel, n_timesteps=1, noise=noise)
+    assert m._block_operands is None
+    plan = next(iter(m._plans.values()))
+    assert plan.f16 and int(plan.sat.item()) == 0 and int(plan.sat_host[0]) == 0
+    plan.sat_host[0] = 1                                        # what a saturating replay would have left behind
+    with caplog.at_level(logging.WARNING):
+        b = m.infer(mel, n_timesteps=1, noise=noise)
+    assert m._block_operands == "tf32" and any("earlier call" in r.message for r in caplog.records)
+    assert rel_rms(b.cpu(), g["audio_n1"]) < TOL and rel_rms(a.cpu(), g["audio_n1"]) < TOL
+
+
+def test_fp16_range_guard_catches_weight_underflow(caplog):
+    """Weights far below fp16's subnormal step (a whole matrix scaled by 1e-9, compensated in the next
+    layer's input scale) would flush to zero in the fp16 copies without raising any activation flag: the
+    guard's one-time weight check (relative conversion error per matrix) must catch it."""
+    import logging
+    g = torch.load(os.path.join(GOLDEN, "ref_infer_24k.pt"), weights_only=False)
+    m, sd = _model(g["model_name"], g["sd_spec"], g["sd_seed"])
+    S = 1.0e-9
+    pre = "estimators.2.decoder.blocks.0."
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd[pre + "pwconv1.weight"] *= S
+    sd[pre + "pwconv1.bias"] *= S
+    sd[pre + "pwconv2.weight"] /= S
+    m.load_state_dict(sd, strict=False)
+    ref = O.generator_infer(sd, O.generator_config(g["model_name"]), g["mel"], g["noise"], None, 1, False)
+    with caplog.at_level(logging.WARNING):
+        out = m.infer(g["mel"].cuda(), n_timesteps=1, noise=g["noise"].cuda())
+    assert m._block_operands == "tf32" and any("weights" in r.message for r in caplog.records)
+    assert rel_rms(out.cpu(), ref) < TOL

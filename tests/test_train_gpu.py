@@ -118,6 +118,69 @@ def test_two_step_sampler_grads_vs_oracle_autograd():
     _assert_grads(errs)
 
 
+def test_fm_loss_train_mode_branch_dropout_vs_oracle(monkeypatch):
+    """Train-mode branch dropout (generator.py:145-162): with the three draws pinned (which branch, whether
+    to drop, per batch element) the CUDA forward + backward must match the oracle's autograd run with the
+    same per-sample branch weights -- dropped branches contribute neither to the prediction nor to the
+    gradients, the two kept branches are rescaled by 3/2."""
+    import random
+    import flow2gan_b200.train as TR
+    g = torch.load(os.path.join(GOLDEN, "ref_fm_loss_24k.pt"), weights_only=False)
+    m, sd = _model(g["model_name"], g["sd_spec"], 4242)
+    m.train()
+    m.branch_dropout = 0.05
+    Bn = g["audio"].shape[0]
+    idx = torch.tensor([(2 * i + 1) % 3 for i in range(Bn)])                   # dropped branch per element
+    drop = torch.tensor([[0.01 if i % 2 == 0 else 0.9] for i in range(Bn)])     # < 0.05 -> element i drops
+    calls = []
+    real_randint, real_rand = torch.randint, torch.rand
+
+    def fake_randint(lo, hi, size, **kw):
+        calls.append(("randint", tuple(size)))
+        assert (lo, hi, tuple(size)) == (0, 3, (Bn,))
+        return idx.to(kw.get("device", "cpu"))
+
+    def fake_rand(size, **kw):
+        calls.append(("rand", tuple(size)))
+        assert tuple(size) == (Bn, 1)
+        return drop.to(kw.get("device", "cpu"))
+
+    monkeypatch.setattr(TR.torch, "randint", fake_randint)
+    monkeypatch.setattr(TR.torch, "rand", fake_rand)
+    rr = random.random
+    random.random = lambda: 0.99          # limit_param_value off
+    try:
+        loss = m(cond=g["mel"].cuda(), audio=g["audio"].cuda(), audio_lens=g["lens"].cuda(),
+                 noise=g["noise"].cuda(), t=g["t"].cuda())
+        loss.backward()
+    finally:
+        random.random = rr
+        monkeypatch.setattr(TR.torch, "randint", real_randint)
+        monkeypatch.setattr(TR.torch, "rand", real_rand)
+    assert calls == [("randint", (Bn,)), ("rand", (Bn, 1))], calls              # the reference's draw order
+    mask = torch.ones(Bn, 3)
+    mask[torch.arange(Bn), idx] = 0.0
+    weight = torch.where(drop < 0.05, mask * 1.5, torch.ones_like(mask))
+    assert bool((weight == 0).any())
+    cfg = O.generator_config(g["model_name"])
+    leaves = {k: v.clone().requires_grad_(not (k.endswith("window") or k.endswith(".fb"))) for k, v in sd.items()}
+    for k, v in m.state_dict().items():
+        if k not in leaves:
+            leaves[k] = v.detach().cpu()
+    ref = O.fm_loss(leaves, cfg, g["mel"], g["audio"], g["lens"], g["noise"], g["t"], branch_weight=weight)
+    rel = abs(float(loss.detach()) - float(ref.detach())) / float(ref.detach())
+    print("fm loss with branch dropout", float(loss.detach()), "oracle", float(ref.detach()), "rel", rel)
+    assert rel < 2e-3
+    ref.backward()
+    errs = {}
+    for k, p in m.named_parameters():
+        r = leaves[k].grad
+        if r is None or p.grad is None or float(r.double().norm()) < 1e-9:
+            continue
+        errs[k] = (float((p.grad.cpu() - r).double().norm() / r.double().norm()), float(r.double().norm()))
+    _assert_grads(errs)
+
+
 @pytest.mark.parametrize("n_fft,hop", [(128, 64), (512, 256), (1024, 256), (64, 16)])
 def test_stft_adjoint_identity(n_fft, hop):
     """<STFT x, G> == <x, STFT^T G> and the same for the iSTFT pair (size-independent property)."""

@@ -60,9 +60,12 @@ def test_cached_time_path_keeps_inference_output_bit_identical(tmp_path):
 
 def test_tf32_block_operands_match_fp16_block_operands(tmp_path):
     """F2G_BLOCK_OPERANDS=tf32 (fp32-container operands, 8-bit exponent) against the default fp16 operands
-    (same 11-bit significand): inside the fp16 range the two builds differ only by accumulation order."""
+    (same 11-bit significand).  Measured on a B200 (tools/arm_matrix.py, profiles/r02_switches.md): the two
+    builds sit at the SAME distance from the fp32 CPU oracle (5.737e-4 / 5.735e-4 rel-RMS, 2 ODE steps at the
+    bench shape) and 5.36e-4 apart from each other -- two realisations of the same 11-bit operand rounding
+    (RN-even conversions vs cvt.rna packing, different MMA K grouping), neither closer to the reference."""
     f16 = _run_arm(tmp_path, "f16", {"F2G_BLOCK_OPERANDS": "f16"})
     tf32 = _run_arm(tmp_path, "tf32", {"F2G_BLOCK_OPERANDS": "tf32"})
     rel = float((f16 - tf32).double().pow(2).mean().sqrt() / tf32.double().pow(2).mean().sqrt())
     print("fp16 vs tf32 block operands, 2-step bench shape: rel-RMS", rel)
-    assert rel < 5e-4, rel
+    assert rel < 8e-4, rel

@@ -23,8 +23,14 @@
     }                                                                                \
   } while (0)
 
-constexpr int STAGES = 4;
-constexpr int CHUNK = 32 * 1024;          // bytes per stage = one GEMM pipeline stage per CTA
+#ifndef PROBE_STAGES
+#define PROBE_STAGES 4
+#endif
+#ifndef PROBE_CHUNK_KB
+#define PROBE_CHUNK_KB 32
+#endif
+constexpr int STAGES = PROBE_STAGES;
+constexpr int CHUNK = PROBE_CHUNK_KB * 1024;          // bytes per stage (32 KB = one GEMM pipeline stage per CTA)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -135,6 +141,22 @@ __global__ void probe_kernel(const uint8_t* __restrict__ src, size_t n_chunks, i
   cluster_sync();          // no CTA exits while a peer may still signal its barriers
 }
 
+// Plain LDG ingest: every thread streams 16-byte loads of an L2-resident buffer (8 independent loads in
+// flight per thread), results folded into a register so nothing is optimised away.
+__global__ void __launch_bounds__(1024, 1) ldg_kernel(const uint4* __restrict__ src, size_t n_vec, int iters, unsigned* sink) {
+  unsigned acc = 0;
+  size_t i = ((size_t)blockIdx.x * 7919u * 1024u + threadIdx.x) % n_vec;
+  for (int it = 0; it < iters; ++it) {
+    uint4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (i + (size_t)j * 1024) % n_vec);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+    i = (i + 8 * 1024) % n_vec;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
 static float run(const uint8_t* src, size_t n_chunks, int mode, int csz, int sms, int iters, int* ctas_out) {
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(32);
@@ -192,6 +214,27 @@ int main() {
       printf("cluster %d  %s  %3d CTAs  %8.3f ms  delivered %8.1f GB/s  = %5.1f B/clk/SM\n", csz, names[mode], ctas,
              ms, gbs, gbs * 1e9 / ctas / (khz * 1e3));
     }
+  {  // LDG path, L2-resident 32 MB
+    unsigned* sink = nullptr;
+    CHECK(cudaMalloc(&sink, 4));
+    const int it2 = 512;
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0));
+    CHECK(cudaEventCreate(&e1));
+    const size_t n_vec = n_chunks * CHUNK / 16;
+    ldg_kernel<<<sms, 1024>>>(reinterpret_cast<const uint4*>(src), n_vec, 16, sink);
+    CHECK(cudaDeviceSynchronize());
+    CHECK(cudaEventRecord(e0));
+    ldg_kernel<<<sms, 1024>>>(reinterpret_cast<const uint4*>(src), n_vec, it2, sink);
+    CHECK(cudaEventRecord(e1));
+    CHECK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double bytes = (double)sms * 1024 * it2 * 8 * 16;
+    const double gbs = bytes / (ms * 1e-3) / 1e9;
+    printf("LDG.128 x8 per thread, 1024 thr/SM  %3d CTAs  %8.3f ms  delivered %8.1f GB/s  = %5.1f B/clk/SM\n", sms, ms,
+           gbs, gbs * 1e9 / sms / (khz * 1e3));
+  }
   CHECK(cudaFree(src));
   return 0;
 }

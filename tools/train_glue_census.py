@@ -34,7 +34,8 @@ lens = torch.full((bench.B,), 24000, device=dev, dtype=torch.int64)
 for _ in range(2):
     tr.step(audio, lens)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True,
+             experimental_config=torch._C._profiler._ExperimentalConfig(verbose=True)) as prof:     # stacks need verbose
     for _ in range(2):
         tr.step(audio, lens)
     torch.cuda.synchronize()
@@ -49,6 +50,9 @@ for ev in prof.events():
         if "flow2gan_b200" in fr and "_lib.py" not in fr:
             site = fr.split("flow2gan_b200" + os.sep)[-1].strip()
             break
+    else:
+        if ev.stack:
+            site = "(autograd / torch) " + str(ev.name)[:40]
     for k in kernels:
         s = sites[site]
         s[0] += 1
