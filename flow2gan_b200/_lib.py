@@ -104,7 +104,7 @@ _SIGS = {
     "f2g_check_device": ([], _i),
     "f2g_chain_watchdog": ([C.POINTER(_i)], _i),
     "f2g_gemm_tf32": ([C.POINTER(F2GGemm), _i, _fp], _i),
-    "f2g_stft": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _i, _f, _fp, _i, _i, _fp], _i),
+    "f2g_stft": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _i, _f, _fp, _i, _i, _fp, _fp], _i),
     "f2g_dc_peak": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_irfft_frames": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_ola_combine": ([C.POINTER(_fp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _fp, _fp,
@@ -130,7 +130,7 @@ _SIGS = {
     "f2g_istft_bwd_spec": ([_fp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp], _i),
     "f2g_stft_bwd_frames": ([_fp, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_stft_bwd_fold": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
-    "f2g_spec_loss_bwd": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _f, _fp, _i, _fp, _fp], _i),
+    "f2g_spec_loss_bwd": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _f, _fp, _i, _fp, _fp, _fp], _i),
     "f2g_colsum": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
@@ -261,10 +261,37 @@ def gemm_replay(arr, n) -> None:
     _check(lib().f2g_gemm_tf32(arr, n, stream()))
 
 
+_FB_RANGES = {}
+
+
+def fb_ranges(fb: torch.Tensor) -> torch.Tensor:
+    """int32 (n_filt + n_bins, 2) support ranges of a filterbank fb (n_bins, n_filt) for the banded
+    contraction of f2g_stft / f2g_spec_loss_bwd (include/flow2gan_b200.h).  Computed once per buffer (one
+    host round trip at first use -- the eager warm-up call, never under stream capture)."""
+    key = (fb.data_ptr(), tuple(fb.shape), fb._version, str(fb.device))
+    r = _FB_RANGES.get(key)
+    if r is None:
+        nz = (fb.detach() != 0).cpu()
+        nb, nf = nz.shape
+
+        def rng(mask):                     # mask (items, positions) -> [first, last + 1) per item, (0, 0) if empty
+            anyv = mask.any(1)
+            pos = torch.arange(mask.shape[1])
+            first = torch.where(mask, pos, mask.shape[1]).min(1).values
+            last = torch.where(mask, pos, -1).max(1).values + 1
+            return torch.stack([torch.where(anyv, first, 0), torch.where(anyv, last, 0)], 1)
+        r = torch.cat([rng(nz.t()), rng(nz)], 0).to(torch.int32).contiguous().to(fb.device)
+        if len(_FB_RANGES) > 64:
+            _FB_RANGES.clear()
+        _FB_RANGES[key] = r
+    return r
+
+
 def stft(audio, B, T, ld_audio, n_fft, hop, mode, out, ld_out, *, pre=None, fb=None, n_filt=0,
          log_clip=0.0, round_tf32=0):
+    rng = fb_ranges(fb) if fb is not None else None
     _check(lib().f2g_stft(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(pre), ptr(fb), n_filt,
-                          log_clip, ptr(out), ld_out, round_tf32, stream()))
+                          log_clip, ptr(out), ld_out, round_tf32, ptr(rng), stream()))
 
 
 def _spec_problems(problems):
@@ -443,7 +470,7 @@ def stft_bwd_fold(frames_grad, B, T, n_fft, hop, frames, dx, accumulate):
 
 def spec_loss_bwd(audio, B, T, ld_audio, n_fft, hop, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out):
     _check(lib().f2g_spec_loss_bwd(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(fb), n_filt,
-                                   float(log_clip), ptr(dF), ld_dF, ptr(frames_out), stream()))
+                                   float(log_clip), ptr(dF), ld_dF, ptr(frames_out), ptr(fb_ranges(fb)), stream()))
 
 
 def colsum(x, ld, rows, cols, out):

