@@ -372,8 +372,8 @@ def gan_train_bench(dev, dist, world, pairs=3, n_timesteps=1):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     roof = None
-    if int(os.environ.get("RANK", "0")) == 0:
-        try:
+    if world == 1:          # single process only: the extra eager / profiled pairs would leave the other ranks'
+        try:                # collectives without a partner
             from flow2gan_b200 import _lib as L
             # (a) FLOPs as executed: the pair's GEMM descriptors, recorded on one eager D + G iteration
             was = tr.use_graph
@@ -460,7 +460,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that stops participating must fail the run in minutes, not hold 8 GPUs for the 10-minute default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from flow2gan_b200 import _lib as L
     L.lib()

@@ -79,11 +79,16 @@ def _worker(rank, world, port, q):
         sub = _phase_grads(gan, audio, noise, train_disc)
         nbytes = GradBuckets(sub.parameters()).allreduce_mean()
         if rank == 0:
-            out["d" if train_disc else "g"] = ({k: p.grad.detach().cpu() for k, p in sub.named_parameters() if p.grad is not None}, nbytes)
+            # numpy arrays travel through the queue by value (torch tensors would be passed as shared-memory
+            # handles that die with this process)
+            out["d" if train_disc else "g"] = ({k: p.grad.detach().cpu().numpy() for k, p in sub.named_parameters()
+                                                if p.grad is not None}, nbytes)
     if rank == 0:
         q.put((same, out))
     dist.barrier()
     cleanup_dist()
+    q.close()
+    q.join_thread()            # flush the feeder thread before the process exits
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -110,6 +115,7 @@ def test_nccl_grad_allreduce_equals_single_rank_on_concatenated_batch():
         sub = _phase_grads(gan, audio, noise, train_disc)
         ref = {k: p.grad.detach().cpu() for k, p in sub.named_parameters() if p.grad is not None}
         grads, nbytes = got[ph]
+        grads = {k: torch.from_numpy(v) for k, v in grads.items()}
         assert nbytes == sum(p.numel() for p in sub.parameters() if p.requires_grad) * 4
         assert set(grads) == set(ref)
         num = sum(float((grads[k] - ref[k]).double().pow(2).sum()) for k in ref)

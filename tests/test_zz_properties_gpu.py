@@ -101,7 +101,7 @@ def test_parity_on_trained_weight_proxy():
           % (loss, moved[0][0], moved[len(moved) // 2][0], moved[-1][0], moved[-1][1]))
     assert moved[len(moved) // 2][0] > 0.05, "the proxy weights did not move away from the initialisation"
     mel_fn = LogMelSpectrogram(24000, 1024, 256, 100).cuda()
-    mel = mel_fn(audio[:4, : 40 * 256]).cpu()
+    mel = mel_fn(audio[:4, : 40 * 256])[:, :, :40].cpu()       # 1 + T // hop frames -> the 40 whole hops
     noise = noise_input(4, 40 * 256, seed=8)
     cfg = O.generator_config("mel_24k_base")
     errs = {}

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests/test_nccl_gpu.py tests/test_zz_properties_gpu.py::test_parity_on_trained_weight_proxy -q --tb=short -p no:cacheprovider -s 2>&1 | grep -E "passed|failed|FAILED|rank|proxy|after|Error|assert" | cut -c1-250
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
 python - <<'P'
 import json
 for l in open('gpurun_out/bench_n2.json'):
