@@ -16,6 +16,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("F2G_BRINGUP", "0") == "1":       # tools/ only: timing-experiment knobs read the environment
+    NVCC_FLAGS.append("-DF2G_BRINGUP")
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(CSRC), "..", "include")):

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   if (!live) return;
   const float gain = expf(*P.bn_log_scale);
   const float inv_c = 1.0f / (float)C;
-  float amax = 0.f;      // fp16 range guard: largest |value| handed to the saturating conversion
+  uint32_t sat_acc = 0;  // fp16 range guard: running per-half maximum of the converted |bits| (common.cuh)
 #pragma unroll
   for (int s = 0; s < PRE_S; ++s) {
     const int t = t0 + s;
@@ -213,14 +213,14 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
     z.x *= 1.f + sc.x; z.y *= 1.f + sc.y; z.z *= 1.f + sc.z; z.w *= 1.f + sc.w;
     if (P.out_f16) {   // operand of a kind::f16 GEMM: same 11-bit significand as the TF32 rounding
       __half* o = reinterpret_cast<__half*>(P.out) + (rb + t) * (size_t)P.ld_out + c;
-      *reinterpret_cast<uint2*>(o) = pack_half4(z);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(z.x), fabsf(z.y)), fmaxf(fabsf(z.z), fabsf(z.w))));
-      amax = (z.x - z.x + z.y - z.y + z.z - z.z + z.w - z.w) == 0.f ? amax : 3.0e38f;     // inf / NaN
+      const uint2 hw = pack_half4(z);
+      *reinterpret_cast<uint2*>(o) = hw;
+      sat_acc = half2_track(half2_track(sat_acc, hw.x), hw.y);
     } else {
       st4(P.out + (rb + t) * P.ld_out + c, make_float4(tf32_rna(z.x), tf32_rna(z.y), tf32_rna(z.z), tf32_rna(z.w)));
     }
   }
-  if (P.sat_flag && !(amax <= 65504.f)) atomicOr(P.sat_flag, 2);
+  if (P.sat_flag && half2_out_of_range(sat_acc)) atomicOr(P.sat_flag, 2);
 }
 
 // Batched small dense layers (up to 4 independent problems per launch, blockIdx.y = problem):
@@ -355,7 +355,7 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
   memset(&a, 0, sizeof(a));
   a.n = n;
   // sliding-window length per lane / resident CTAs per SM (F2G_PRE_VARIANT: bring-up sweep)
-  static const int variant = getenv("F2G_PRE_VARIANT") ? atoi(getenv("F2G_PRE_VARIANT")) : 0;
+  static const int variant = bringup_int("F2G_PRE_VARIANT", 0);
   const int S = variant == 1 ? 2 : (variant == 2 ? 2 : (variant == 3 ? 8 : 4));
   int ctas = 0;
   for (int i = 0; i < n; ++i) {

@@ -20,6 +20,18 @@ namespace f2g {
 enum { F2G_OK = 0, F2G_EINVAL = -1, F2G_EDRIVER = -2, F2G_EARCH = -3 };
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+// Bring-up / timing-experiment knobs (tile-schedule variants, epilogue stubs, descriptor experiments) exist
+// only in a -DF2G_BRINGUP build (F2G_BRINGUP=1 python -m flow2gan_b200._build --force, used by tools/);
+// the product library ignores the environment and always takes the default.
+#ifdef F2G_BRINGUP
+#include <stdlib.h>
+static inline int bringup_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+#else
+static inline int bringup_int(const char*, int dflt) { return dflt; }
+#endif
 int* chain_watchdog_dev();   // mapped pinned {flag, problem, row tile, counter} (api.cu), nullptr if unavailable
 
 // ---------------------------------------------------------------------------------------
@@ -48,6 +60,12 @@ F2G_DEVINL uint32_t pack_half2_sat(float a, float b) {
 F2G_DEVINL uint2 pack_half4(float4 v) {
   return make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
 }
+// fp16 range guard on the CONVERTED words: the saturating conversion maps everything beyond the finite
+// range to +-65504 (0x7bff) and NaN to NaN (> 0x7c00), so the running per-half maximum of |bits| reaching
+// 0x7bff means "a value was clamped, is not finite, or sat exactly on the limit" -- one LOP3 + one VMAX
+// per two values instead of float compares per value.
+F2G_DEVINL uint32_t half2_track(uint32_t acc, uint32_t w) { return __vmaxu2(acc, w & 0x7fff7fffu); }
+F2G_DEVINL bool half2_out_of_range(uint32_t acc) { return (acc & 0xffffu) >= 0x7bffu || (acc >> 16) >= 0x7bffu; }
 
 F2G_DEVINL float warp_sum(float v) {
 #pragma unroll

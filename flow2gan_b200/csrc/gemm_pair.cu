@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include "gemm_tf32.h"
 
-#include <stdlib.h>
 
 namespace f2g {
 
@@ -39,7 +38,7 @@ constexpr int P_PROD_WARPS = 3;       // 12 warps per CTA: register allocation i
 constexpr int P_FIRST_EXTRA_PROD = 2 + P_EPI_WARPS;            // warp index of producer 1
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS + 32 * (P_PROD_WARPS - 1);
 constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 36 * 4;
-constexpr int P_PARAM_BYTES = 3 * 256 * 4;
+constexpr int P_PARAM_BYTES = 2 * 3 * 256 * 4;     // bias / slope / residual-scale of a tile's columns, two tiles (double buffer)
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + P_PARAM_BYTES;
 constexpr int P_TMEM_COLS = 512;
 constexpr int P_MAX_SCHED = 1024;
@@ -187,8 +186,21 @@ F2G_DEVINL void umma_commit_cg2(uint64_t* bar) {
 
 // PEPI_MLP (fp16 operands only): per problem either BIAS_ACT with an fp16 destination or BIAS_RES --
 // the two halves of a chained pwconv1 -> pwconv2 launch, both on their fast paths.
+#ifdef F2G_BRINGUP
+#define F2G_PROF_DECL long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_c = clock64()
+#define F2G_PROF(slot) do { const long long n_ = clock64(); prof_t[slot] += n_ - prof_c; prof_c = n_; } while (0)
+#else
+#define F2G_PROF_DECL do { } while (0)
+#define F2G_PROF(slot) do { } while (0)
+#endif
+
 enum { PEPI_GENERIC = 0, PEPI_BIAS_ACT = 1, PEPI_BIAS_RES = 2, PEPI_PLAIN = 3, PEPI_MLP = 4 };
 
+F2G_DEVINL float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 F2G_DEVINL int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -261,9 +273,8 @@ F2G_DEVINL void epi_fast_chunk(const float* __restrict__ sl, float* __restrict__
 // BIAS_ACT chunk with an fp16 destination (the hidden activation of a ConvNeXt block, which only
 // the next GEMM reads): x = prelu(alpha*acc + bias) -> RN fp16, one 8-byte store per row quad.
 template <bool FULL>
-F2G_DEVINL float epi_fast_chunk_h(const float* __restrict__ sl, __half* __restrict__ cp, size_t cstep,
-                                  int rows_left, float alpha, float4 bias4, float4 slope4) {
-  float amax = 0.f;       // fp16 range guard: |x| before the saturating conversion
+F2G_DEVINL uint32_t epi_fast_chunk_h(const float* __restrict__ sl, __half* __restrict__ cp, size_t cstep,
+                                     int rows_left, float alpha, float4 bias4, float4 slope4, uint32_t sat_acc) {
   float4 xv[8];
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) xv[rr] = *reinterpret_cast<const float4*>(sl + rr * (4 * 36));
@@ -272,15 +283,15 @@ F2G_DEVINL float epi_fast_chunk_h(const float* __restrict__ sl, __half* __restri
     float4 x;
     x.x = fmaf(xv[rr].x, alpha, bias4.x); x.y = fmaf(xv[rr].y, alpha, bias4.y);
     x.z = fmaf(xv[rr].z, alpha, bias4.z); x.w = fmaf(xv[rr].w, alpha, bias4.w);
-    x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;
+    x.x = x.x > 0.f ? x.x : x.x * slope4.x; x.y = x.y > 0.f ? x.y : x.y * slope4.y;      // NaN propagates
     x.z = x.z > 0.f ? x.z : x.z * slope4.z; x.w = x.w > 0.f ? x.w : x.w * slope4.w;
     if (FULL || rr * 4 < rows_left) {
-      *reinterpret_cast<uint2*>(cp + rr * cstep) = pack_half4(x);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
-      amax = (x.x - x.x + x.y - x.y + x.z - x.z + x.w - x.w) == 0.f ? amax : 3.0e38f;    // inf / NaN
+      const uint2 hw = pack_half4(x);
+      *reinterpret_cast<uint2*>(cp + rr * cstep) = hw;
+      sat_acc = half2_track(half2_track(sat_acc, hw.x), hw.y);     // fp16 range guard (common.cuh)
     }
   }
-  return amax;
+  return sat_acc;
 }
 
 template <int A_MN, int B_MN, int EPI, int F16>
@@ -479,18 +490,46 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     const int q = warp & 3;
     const int half = ew >> 2;
     float* const scratch = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES) + ew * (32 * 36);
-    float* const sparam = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES);
+    float* const sparam0 = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES);
     const int cg = lane & 7, rsub = lane >> 3;
     const int et = ew * 32 + lane;
     const uint32_t lead_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t lead_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     int ab = 0;
     uint32_t ab_phase = 0;
+    F2G_PROF_DECL;
+    // Per-tile bookkeeping runs ONE TILE AHEAD (measured with the bring-up cycle profile: tile decode 550
+    // + parameter staging 640 cycles per tile sat between the end of one tile and the wait for the next
+    // accumulator, 15 % of an epilogue-bound tile): tile i+1 is decoded and its bias / slope /
+    // residual-scale columns are fetched into the other half of the parameter buffer while tile i's
+    // accumulator is still being produced; the barrier that ends tile i publishes them.
+    auto tile_at = [&](int ti) { return g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs; };
+    auto stage_params = [&](const PTile& t, float* sp) {
+      const PProblem& p = g.p[t.prob];
+      const float* const bias_p = p.bias;
+      const float* const slope_p = p.slope;
+      const float* const rsc_p = p.res_scale;
+      const float leaky = p.leaky;
+      const int bn = p.bn, nn = p.N;
+      for (int c = et; c < bn; c += 32 * P_EPI_WARPS) {
+        const int colc = t.n0 + c;
+        const bool okc = colc < nn;
+        sp[c] = (bias_p && okc) ? __ldg(bias_p + colc) : 0.f;
+        sp[256 + c] = (slope_p && okc) ? __ldg(slope_p + colc) : leaky;
+        sp[512 + c] = (rsc_p && okc) ? __ldg(rsc_p + colc) : 1.f;
+      }
+    };
+    PTile tc = {0, 0, 0, 0, 0};
+    if (my_tiles > 0) {
+      tc = pdecode(g, tile_at(0));
+      stage_params(tc, sparam0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (int ti = 0; ti < my_tiles; ++ti) {
-        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
-      const PTile tc = pdecode(g, tile);
       const PProblem& pr = g.p[tc.prob];
       const int BN = pr.bn;
+      float* const sparam = sparam0 + (ti & 1) * 768;
+      F2G_PROF(0);
       const int n0 = tc.n0;
       const int row_base = tc.m0 + (int)rank * PBM + q * 32;
       const int N = pr.N, ldc = pr.ldc, ld_res = pr.ld_res, ld_gate = pr.ld_gate, ld_pre = pr.ld_pre;
@@ -511,32 +550,31 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       const bool vec_gate = !gate_p || (((ld_gate & 3) == 0) && ((reinterpret_cast<uintptr_t>(gate_p) & 15) == 0));
       const bool vec_pre = !pre_p || (((ld_pre & 3) == 0) && ((reinterpret_cast<uintptr_t>(pre_p) & 15) == 0));
       const bool vec_all = vec_c && vec_res && vec_gate && vec_pre;
+      int* const done_p = pr.done;
+      const int done_idx = tc.m0 / (2 * PBM);
+      int* const sat_p = pr.sat_flag;
 
-      // stage bias / slope / residual-scale of this tile's BN columns (overlaps the main loop)
-      {
-        const float* const bias_p = pr.bias;
-        const float* const slope_p = pr.slope;
-        const float* const rsc_p = pr.res_scale;
-        const float leaky = pr.leaky;
-        for (int c = et; c < BN; c += 32 * P_EPI_WARPS) {
-          const int colc = n0 + c;
-          const bool okc = colc < N;
-          sparam[c] = (bias_p && okc) ? __ldg(bias_p + colc) : 0.f;
-          sparam[256 + c] = (slope_p && okc) ? __ldg(slope_p + colc) : leaky;
-          sparam[512 + c] = (rsc_p && okc) ? __ldg(rsc_p + colc) : 1.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+      // the next tile's decode + parameter columns, under this tile's main loop
+      PTile tn = tc;
+      if (ti + 1 < my_tiles) {
+        tn = pdecode(g, tile_at(ti + 1));
+        stage_params(tn, sparam0 + ((ti + 1) & 1) * 768);
       }
+      F2G_PROF(1);
 
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
-      float amax_t = 0.f;      // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag)
+      F2G_PROF(2);
+      uint32_t sat_acc = 0;    // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag; common.cuh)
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= N || (g.dbg & 2)) break;
+        // (issuing the next chunk's tcgen05.ld here, before this chunk's LDS / math / stores, was measured:
+        // no change -- the TMEM read is not what the epilogue waits for; profiles/r02_gemm_probes.md)
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * 256 + c0, v);
         tmem_ld_wait();
+        F2G_PROF(3);
         if (rows <= 0 || (g.dbg & 1)) continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -546,17 +584,22 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         __syncwarp();
         const int col = n0 + c0 + 4 * cg;
         const int ncol = min(4, N - col);
-        const float4 bias4 = *reinterpret_cast<const float4*>(sparam + c0 + 4 * cg);
-        const float4 slope4 = *reinterpret_cast<const float4*>(sparam + 256 + c0 + 4 * cg);
-        const float4 rsc4 = *reinterpret_cast<const float4*>(sparam + 512 + c0 + 4 * cg);
+        // opaque 128-bit loads: left to itself the compiler sinks the slope load into the PReLU selects as
+        // 32 predicated LDS.32 per chunk -- a shared-memory round trip inside every
+        // FFMA -> compare -> multiply -> convert chain
+        const float4 bias4 = lds_f4(sparam + c0 + 4 * cg);
+        const float4 slope4 = lds_f4(sparam + 256 + c0 + 4 * cg);
+        const float4 rsc4 = lds_f4(sparam + 512 + c0 + 4 * cg);
         const bool chunk_full = vec_all && (n0 + c0 + 32 <= N) && split_k == 1;   // warp-uniform
 
         if (F16 && (EPI == PEPI_BIAS_ACT || EPI == PEPI_MLP) && chunk_full && c16) {
           const float* sl = scratch + rsub * 36 + 4 * cg;
           __half* hp = reinterpret_cast<__half*>(cbase) + (size_t)(row_base + rsub) * ldc + col;
-          if (rows >= 32) amax_t = fmaxf(amax_t, epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4));
-          else amax_t = fmaxf(amax_t, epi_fast_chunk_h<false>(sl, hp, (size_t)4 * ldc, rows - rsub, alpha, bias4, slope4));
+          F2G_PROF(4);
+          if (rows >= 32) sat_acc = epi_fast_chunk_h<true>(sl, hp, (size_t)4 * ldc, 32, alpha, bias4, slope4, sat_acc);
+          else sat_acc = epi_fast_chunk_h<false>(sl, hp, (size_t)4 * ldc, rows - rsub, alpha, bias4, slope4, sat_acc);
           __syncwarp();
+          F2G_PROF(5);
           continue;
         }
         constexpr int EF = EPI == PEPI_MLP ? PEPI_BIAS_RES : EPI;   // fp32-destination fast path
@@ -628,10 +671,9 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               x[0] *= rs; x[1] *= rs; x[2] *= rs; x[3] *= rs;
             }
             if (c16) {
-              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(cbase) + (size_t)row * ldc + col) =
-                  pack_half4(make_float4(x[0], x[1], x[2], x[3]));
-              amax_t = fmaxf(amax_t, fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
-              amax_t = (x[0] - x[0] + x[1] - x[1] + x[2] - x[2] + x[3] - x[3]) == 0.f ? amax_t : 3.0e38f;
+              const uint2 hw = pack_half4(make_float4(x[0], x[1], x[2], x[3]));
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(cbase) + (size_t)row * ldc + col) = hw;
+              sat_acc = half2_track(half2_track(sat_acc, hw.x), hw.y);
               continue;
             }
             float* dst = cbase + (size_t)row * ldc + col;
@@ -661,9 +703,9 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
               if (res_p) x = fmaf(rsc[e], __ldg(res_p + (size_t)row * ld_res + col + e), x);
               if (rowsc_p) x *= __ldg(rowsc_p + row);
               if (c16) {
-                reinterpret_cast<__half*>(cbase)[(size_t)row * ldc + col + e] =
-                    __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-                amax_t = (x - x) == 0.f ? fmaxf(amax_t, fabsf(x)) : 3.0e38f;
+                const uint32_t hw = pack_half2_sat(x, 0.f);
+                reinterpret_cast<unsigned short*>(cbase)[(size_t)row * ldc + col + e] = (unsigned short)(hw & 0xffffu);
+                sat_acc = half2_track(sat_acc, hw);
                 continue;
               }
               float* dst = cbase + (size_t)row * ldc + col + e;
@@ -674,18 +716,29 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
         }
         __syncwarp();
       }
-      if (F16 && pr.sat_flag && !(amax_t <= 65504.f)) atomicOr(pr.sat_flag, 1);
+      F2G_PROF(6);
+      if (F16 && sat_p && half2_out_of_range(sat_acc)) atomicOr(sat_p, 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // staged parameters may be overwritten now
-      if (et == 0 && pr.done) {   // all 256 epilogue threads' stores precede the barrier: publish them
+      // one barrier per tile: the next tile's staged parameters become visible, this tile's buffer half
+      // may be refilled (by the tile after next), and all 256 threads' stores precede the publish below
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0 && done_p) {
         __threadfence();
-        atomicAdd(pr.done + tc.m0 / (2 * PBM), 1);
+        atomicAdd(done_p + done_idx, 1);
       }
       ab ^= 1;
       if (ab == 0) ab_phase ^= 1;
+      tc = tn;
+      F2G_PROF(7);
     }
+#ifdef F2G_BRINGUP
+    if ((g.dbg & 16) && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 5))
+      printf("epi prof warp %d tiles %d cycles: decode %lld params+bar %lld wait_mma %lld ldtm %lld sts+lds_params %lld "
+             "chunk_math+stg %lld other_paths %lld tile_end %lld\n", ew, my_tiles, prof_t[0], prof_t[1], prof_t[2],
+             prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7]);
+#endif
   }
 
   // Neither CTA may exit (or free TMEM) while its peer can still signal its barriers / read its
@@ -861,12 +914,11 @@ static int pair_launch(PGroup& g, cudaStream_t stream) {
       cudaGetLastError();
       nc = sms / 2;
     }
-    const char* ov = getenv("F2G_PAIRS");
-    if (ov) nc = atoi(ov);
+    nc = bringup_int("F2G_PAIRS", nc);
     max_pairs = nc < 1 ? 1 : nc;
   }
   const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
-  static const int no_sched = getenv("F2G_PAIR_RR") ? atoi(getenv("F2G_PAIR_RR")) : 0;
+  static const int no_sched = bringup_int("F2G_PAIR_RR", 0);
   if (!no_sched) build_schedule(g, pairs);
   cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(P_THREADS), (size_t)P_SMEM_BYTES, stream, g);
   if (le != cudaSuccess) {
@@ -911,7 +963,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   // tiles (>= 64 columns) until the group has at least ~one tile per pair.
   int bns[F2G_GEMM_MAX_PROBLEMS];
   {
-    static const int fill = getenv("F2G_PAIR_FILL") ? atoi(getenv("F2G_PAIR_FILL")) : 1;
+    static const int fill = bringup_int("F2G_PAIR_FILL", 1);
     const int step = b_mn ? 64 : 32;
     // Chained consumer problems take the caller's N tile (F2GGemm::bn) instead of the byte-optimal
     // one: narrower tiles for the problems the LPT schedule places last shorten the tail of the
@@ -1019,7 +1071,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   g.n_problems = n;
   g.total_tiles = tiles;
   g.watchdog = chained ? chain_watchdog_dev() : nullptr;
-  static const int dbg = getenv("F2G_PAIR_DBG") ? atoi(getenv("F2G_PAIR_DBG")) : 0;
+  static const int dbg = bringup_int("F2G_PAIR_DBG", 0);
   g.dbg = dbg;
 
   int epi = -1;
@@ -1040,7 +1092,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     epi = (epi == -1 || epi == e) ? e : PEPI_GENERIC;
   }
   if (f16 && epi == PEPI_GENERIC && mlp_ok) epi = PEPI_MLP;   // mixed pwconv1 / pwconv2 problems
-  static const int force_generic = getenv("F2G_PAIR_FORCE_GENERIC") ? atoi(getenv("F2G_PAIR_FORCE_GENERIC")) : 0;
+  static const int force_generic = bringup_int("F2G_PAIR_FORCE_GENERIC", 0);
   if (force_generic) epi = PEPI_GENERIC;     // timing experiments only
   if (f16) {   // K-major only; the three epilogues the inference blocks use
     if (epi == PEPI_BIAS_ACT) return pair_launch<0, 0, PEPI_BIAS_ACT, 1>(g, stream);

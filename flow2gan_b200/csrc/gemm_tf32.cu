@@ -496,12 +496,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D fp32 tensor map, 128B swizzle.  dims/strides innermost first; box = {32, box_rows}.
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+static int env_int(const char* name, int dflt) { return bringup_int(name, dflt); }   // -DF2G_BRINGUP builds only
 
-static int env_int(const char* name, int dflt);
 static int encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
                      uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();

@@ -14,24 +14,32 @@
 namespace f2g {
 
 constexpr int LOSS_THREADS = 256;
-constexpr int LOSS_PER_THREAD = 8;
+constexpr int LOSS_PER_THREAD = 8;       // units per thread; a unit = one element (scalar terms) or one float4 (vector terms)
 constexpr int LOSS_CHUNK = LOSS_THREADS * LOSS_PER_THREAD;
-constexpr int LOSS_MAX_TERMS = 24;     // 24 x 128 B descriptors + prefix table < 4 KB of kernel params
+constexpr int LOSS_MAX_TERMS = 24;     // 24 x 128 B descriptors + tables < 4 KB of kernel params
 
 struct LossArgs {
   F2GLossTerm t[LOSS_MAX_TERMS];
   int block_begin[LOSS_MAX_TERMS + 1];
+  // vector terms: innermost dimension contiguous in both operands, a multiple of 4 long, every other
+  // stride / the base addresses 16-byte aligned -> one index decomposition and one 128-bit access per
+  // four elements (the feature maps are channel-last views: C = 32..1024 innermost).  The index math is
+  // unsigned 32-bit (numel < 2^31, checked on the host): the 64-bit divisions of the first version cost
+  // ~600 instructions per element and left the kernels ALU-bound at a tenth of the HBM rate.
+  unsigned char vec[LOSS_MAX_TERMS];
   int n;
 };
 
-F2G_SIMT_DEV long long loss_offset(const F2GLossTerm& t, const long long* __restrict__ stride, long long i) {
-  const long long i3 = i % t.dims[3];
-  i /= t.dims[3];
-  const long long i2 = i % t.dims[2];
-  i /= t.dims[2];
-  const long long i1 = i % t.dims[1];
-  const long long i0 = i / t.dims[1];
-  return i0 * stride[0] + i1 * stride[1] + i2 * stride[2] + i3 * stride[3];
+// logical index (in units) -> element offset; d3 = innermost extent in units
+F2G_SIMT_DEV long long loss_offset(const F2GLossTerm& t, const long long* __restrict__ stride, unsigned i, unsigned d3,
+                                   unsigned unit) {
+  const unsigned i3 = i % d3;
+  i /= d3;
+  const unsigned i2 = i % (unsigned)t.dims[2];
+  i /= (unsigned)t.dims[2];
+  const unsigned i1 = i % (unsigned)t.dims[1];
+  const unsigned i0 = i / (unsigned)t.dims[1];
+  return (long long)i0 * stride[0] + (long long)i1 * stride[1] + (long long)i2 * stride[2] + (long long)(i3 * unit) * stride[3];
 }
 
 F2G_SIMT_DEV int loss_find_term(const LossArgs& a, int block) {
@@ -40,20 +48,40 @@ F2G_SIMT_DEV int loss_find_term(const LossArgs& a, int block) {
   return ti;
 }
 
+F2G_SIMT_DEV float loss_elem_fwd(const F2GLossTerm& t, float av, float bv) {
+  return t.mode == F2G_LOSS_L1 ? fabsf(av - bv) : fmaxf(1.0f + simt_fmul(t.sign, av), 0.0f);
+}
+F2G_SIMT_DEV float loss_elem_bwd(const F2GLossTerm& t, float av, float bv, float g) {
+  if (t.mode == F2G_LOSS_L1) {
+    const float diff = bv - av;                       // d|b - a| / db = sign(b - a), sign(0) = 0
+    return diff > 0.f ? g : (diff < 0.f ? -g : 0.f);
+  }
+  // torch.clamp(x, min=0) passes the gradient where x >= 0
+  return (1.0f + simt_fmul(t.sign, av) >= 0.0f) ? simt_fmul(t.sign, g) : 0.f;
+}
+
 // out[0] += sum over the launch's terms (out is zeroed by the entry point before the first group)
 F2G_KERNEL void loss_terms_fwd_kernel(const F2G_GRID_CONSTANT LossArgs a, float* __restrict__ out) {
   const int ti = loss_find_term(a, (int)blockIdx.x);
   const F2GLossTerm& t = a.t[ti];
-  const long long base = (long long)((int)blockIdx.x - a.block_begin[ti]) * LOSS_CHUNK;
+  const bool vec = a.vec[ti] != 0;
+  const unsigned unit = vec ? 4u : 1u;
+  const unsigned units = (unsigned)(t.numel / unit), d3 = (unsigned)t.dims[3] / unit;
+  const unsigned base = (unsigned)((int)blockIdx.x - a.block_begin[ti]) * LOSS_CHUNK;
+  const bool l1 = t.mode == F2G_LOSS_L1;
   float acc = 0.f;
   for (int k = 0; k < LOSS_PER_THREAD; ++k) {
-    const long long i = base + (long long)k * LOSS_THREADS + threadIdx.x;
-    if (i >= t.numel) break;
-    const float av = t.a[loss_offset(t, t.stride_a, i)];
-    if (t.mode == F2G_LOSS_L1) {
-      acc += fabsf(av - t.b[loss_offset(t, t.stride_b, i)]);
+    const unsigned i = base + (unsigned)k * LOSS_THREADS + threadIdx.x;
+    if (i >= units) break;
+    const float* ap = t.a + loss_offset(t, t.stride_a, i, d3, unit);
+    const float* bp = l1 ? t.b + loss_offset(t, t.stride_b, i, d3, unit) : ap;
+    if (vec) {
+      const float4 av = *reinterpret_cast<const float4*>(ap);
+      const float4 bv = *reinterpret_cast<const float4*>(bp);
+      acc += (loss_elem_fwd(t, av.x, bv.x) + loss_elem_fwd(t, av.y, bv.y)) +
+             (loss_elem_fwd(t, av.z, bv.z) + loss_elem_fwd(t, av.w, bv.w));
     } else {
-      acc += fmaxf(1.0f + simt_fmul(t.sign, av), 0.0f);
+      acc += loss_elem_fwd(t, *ap, *bp);
     }
   }
   simt_block_sum(simt_fmul(acc, t.scale), out);
@@ -63,21 +91,26 @@ F2G_KERNEL void loss_terms_fwd_kernel(const F2G_GRID_CONSTANT LossArgs a, float*
 F2G_KERNEL void loss_terms_bwd_kernel(const F2G_GRID_CONSTANT LossArgs a, const float* __restrict__ gout) {
   const int ti = loss_find_term(a, (int)blockIdx.x);
   const F2GLossTerm& t = a.t[ti];
-  const long long base = (long long)((int)blockIdx.x - a.block_begin[ti]) * LOSS_CHUNK;
+  const bool vec = a.vec[ti] != 0;
+  const unsigned unit = vec ? 4u : 1u;
+  const unsigned units = (unsigned)(t.numel / unit), d3 = (unsigned)t.dims[3] / unit;
+  const unsigned base = (unsigned)((int)blockIdx.x - a.block_begin[ti]) * LOSS_CHUNK;
+  const bool l1 = t.mode == F2G_LOSS_L1;
   const float g = simt_fmul(gout[0], t.scale);
   for (int k = 0; k < LOSS_PER_THREAD; ++k) {
-    const long long i = base + (long long)k * LOSS_THREADS + threadIdx.x;
-    if (i >= t.numel) break;
-    const float av = t.a[loss_offset(t, t.stride_a, i)];
-    float d;
-    if (t.mode == F2G_LOSS_L1) {
-      const float diff = t.b[loss_offset(t, t.stride_b, i)] - av;      // d|b - a| / db = sign(b - a), sign(0) = 0
-      d = diff > 0.f ? g : (diff < 0.f ? -g : 0.f);
+    const unsigned i = base + (unsigned)k * LOSS_THREADS + threadIdx.x;
+    if (i >= units) break;
+    const float* ap = t.a + loss_offset(t, t.stride_a, i, d3, unit);
+    const float* bp = l1 ? t.b + loss_offset(t, t.stride_b, i, d3, unit) : ap;
+    if (vec) {
+      const float4 av = *reinterpret_cast<const float4*>(ap);
+      const float4 bv = *reinterpret_cast<const float4*>(bp);
+      *reinterpret_cast<float4*>(t.grad + (size_t)i * 4) =
+          make_float4(loss_elem_bwd(t, av.x, bv.x, g), loss_elem_bwd(t, av.y, bv.y, g),
+                      loss_elem_bwd(t, av.z, bv.z, g), loss_elem_bwd(t, av.w, bv.w, g));
     } else {
-      // torch.clamp(x, min=0) passes the gradient where x >= 0
-      d = (1.0f + simt_fmul(t.sign, av) >= 0.0f) ? simt_fmul(t.sign, g) : 0.f;
+      t.grad[i] = loss_elem_bwd(t, *ap, *bp, g);
     }
-    t.grad[i] = d;
   }
 }
 
@@ -96,9 +129,22 @@ static int loss_fill_args(const F2GLossTerm* terms, int n, int backward, LossArg
       set_error("f2g_loss_terms: term %d dims do not multiply to numel", i);
       return -1;
     }
+    if (t.numel >= (1ll << 31)) {
+      set_error("f2g_loss_terms: term %d has %lld elements (limit 2^31 - 1)", i, t.numel);
+      return -1;
+    }
+    bool vec = t.dims[3] % 4 == 0 && t.stride_a[3] == 1 && (reinterpret_cast<uintptr_t>(t.a) & 15) == 0 &&
+               (!backward || (reinterpret_cast<uintptr_t>(t.grad) & 15) == 0);
+    for (int d = 0; d < 3; ++d) vec = vec && t.stride_a[d] % 4 == 0;
+    if (t.mode == F2G_LOSS_L1) {
+      vec = vec && t.stride_b[3] == 1 && (reinterpret_cast<uintptr_t>(t.b) & 15) == 0;
+      for (int d = 0; d < 3; ++d) vec = vec && t.stride_b[d] % 4 == 0;
+    }
     a->t[i] = t;
+    a->vec[i] = vec ? 1 : 0;
     a->block_begin[i] = blocks;
-    blocks += (int)((t.numel + LOSS_CHUNK - 1) / LOSS_CHUNK);
+    const long long units = t.numel / (vec ? 4 : 1);
+    blocks += (int)((units + LOSS_CHUNK - 1) / LOSS_CHUNK);
   }
   for (int i = n; i <= LOSS_MAX_TERMS; ++i) a->block_begin[i] = blocks;
   return blocks;

@@ -146,6 +146,7 @@ static inline void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static inline int check_launch(const char*) { return 0; }
+static inline int bringup_int(const char*, int dflt) { return dflt; }   // no timing knobs on the host
 alignas(128) inline unsigned char g_dyn_smem[228 * 1024];     // "dynamic shared memory" of the running block
 inline std::mutex g_atomic_mu;
 
@@ -383,6 +384,7 @@ F2G_SIMT_DEV float tf32_rna(float x) {
 }
 // cvt.rn.satfinite.f16x2.f32: nearest-even, clamped to the finite fp16 range
 F2G_SIMT_DEV unsigned short half_bits_sat(float v) {
+  if (v != v) return 0x7fffu;                      // NaN stays NaN (as the hardware conversion does)
   v = fminf(fmaxf(v, -65504.0f), 65504.0f);
   const _Float16 h = (_Float16)v;
   unsigned short b;
@@ -393,6 +395,13 @@ F2G_SIMT_DEV uint2 pack_half4(float4 v) {
   return make_uint2((unsigned)half_bits_sat(v.x) | ((unsigned)half_bits_sat(v.y) << 16),
                     (unsigned)half_bits_sat(v.z) | ((unsigned)half_bits_sat(v.w) << 16));
 }
+F2G_SIMT_DEV unsigned half2_track(unsigned acc, unsigned w) {
+  w &= 0x7fff7fffu;
+  const unsigned lo = (acc & 0xffffu) > (w & 0xffffu) ? (acc & 0xffffu) : (w & 0xffffu);
+  const unsigned hi = (acc >> 16) > (w >> 16) ? (acc >> 16) : (w >> 16);
+  return lo | (hi << 16);
+}
+F2G_SIMT_DEV bool half2_out_of_range(unsigned acc) { return (acc & 0xffffu) >= 0x7bffu || (acc >> 16) >= 0x7bffu; }
 F2G_SIMT_DEV float half_bits_to_float(unsigned short b) {
   _Float16 h;
   memcpy(&h, &b, 2);

@@ -512,7 +512,7 @@ static int spec_group_fill(SpecGroupArgs& g, const F2GSpecProblem* probs, int np
 // The warp-per-frame kernels cover n_fft 128..1024 (F2G_FFT_SMEM=1 forces the shared-memory
 // Stockham kernels -- A/B testing).
 static bool spec_group_warp_ok(const F2GSpecProblem* probs, int np) {
-  static const int force_smem = getenv("F2G_FFT_SMEM") ? atoi(getenv("F2G_FFT_SMEM")) : 0;
+  static const int force_smem = bringup_int("F2G_FFT_SMEM", 0);
   if (force_smem) return false;
   for (int i = 0; i < np; ++i) {
     const int n = probs[i].n_fft;

@@ -24,8 +24,8 @@ from . import _lib as L
 import operator
 import os
 
-BN_G1 = int(os.environ.get("F2G_BN1", "128"))   # N tile of pwconv1-like GEMMs (wide N)
-BN_G2 = int(os.environ.get("F2G_BN2", "128"))   # N tile of pwconv2-like GEMMs (N = channels)
+BN_G1 = 128   # N-tile hint of pwconv1-like GEMMs (wide N); the CTA-pair kernel picks the byte-optimal tile
+BN_G2 = 128   # N-tile hint of pwconv2-like GEMMs (N = channels) unless the problem is a chained consumer
 
 # Operand type of the ConvNeXt-block contractions (pwconv1 / pwconv2) at inference.
 #   "f16"  (default): fp16 operands, fp32 accumulate (tcgen05 kind::f16).  fp16 has the SAME 11-bit
@@ -335,17 +335,19 @@ class InferencePlan:
             w.mask = z(w.R) if masked else None
             self.br.append(w)
         # chained pwconv1 -> pwconv2 launches: one counter per 256-row tile (cleared by block_pre)
+        n_ce = (self.Rc + 255) // 256
+        self._flags = torch.zeros(n_ce + 1, device=dev, dtype=torch.int32)       # [CondEncoder chain counters | range flag]
+        self.ce_chain = self._flags[:n_ce]
         self.f16 = self.operands == "f16"
         self.chained = CHAIN_MLP and self.f16
         # fp16 range guard: every kernel that converts an operand to fp16 (block prologue: bit 1, GEMM
         # epilogues with an fp16 destination: bit 0) ORs into this flag when a value leaves +-65504 or is
         # not finite; it is cleared at the start of every launch sequence and mirrored to pinned host
         # memory behind it (generator.py reads it and falls back to TF32 operands)
-        self.sat = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.sat = self._flags[n_ce:]                 # cleared by the first CondEncoder prologue launch of a run
         self.sat_host = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
         self.c0h = zo(self.Rc, self.Cc)
         self.cm_chain = torch.zeros(len(packed.branches) * ((self.Rc + 255) // 256), device=dev, dtype=torch.int32)
-        self.ce_chain = torch.zeros((self.Rc + 255) // 256, device=dev, dtype=torch.int32)
         offs, tot = [], 0
         for w in self.br:
             offs.append(tot)
@@ -376,7 +378,8 @@ class InferencePlan:
                                    b.norm.log_scale, None, None, 0, 0, 1, 0, None, 0, self.ce_a1, bw.C,
                                    sat_flag=self.sat)
             if self.chained:
-                L.block_pre_group([pre], zero=self.ce_chain)
+                # the first prologue of the run also clears the range flag behind the counters
+                L.block_pre_group([pre], zero=self._flags if li == 0 else self.ce_chain)
                 cnt = self.ce_chain.data_ptr()
                 L.gemm_group([_g1(bw, self.ce_a1, self.ce_h, M, done=cnt, sat=self.sat),
                               _g2(bw, self.ce_h, self.c0, M, round_out=int(last), wait=cnt)])
@@ -549,8 +552,8 @@ class InferencePlan:
 
     def _run(self, n: int, clamp: bool, with_cond: bool = True) -> None:
         ts, dt = self._steps
-        if self.f16:
-            self.sat.zero_()
+        if self.f16 and not (with_cond and self.chained):
+            self.sat.zero_()                         # otherwise cleared by the CondEncoder's first prologue launch
         forked = with_cond and FORK_COND
         if forked:
             # The conditioning path (CondEncoder + cond_mlp + cond_proj: ~20 launches of GEMMs with
@@ -586,8 +589,6 @@ class InferencePlan:
                     w.ts = ts_k
             self.process_blocks()
             self.combine(self.x_audio, True, ts[k], dt, clamp and k == n - 1)
-        if self.f16 and self.sat_host.is_pinned():
-            self.sat_host.copy_(self.sat, non_blocking=True)      # 4 bytes, read by the caller (generator.py)
 
     def set_masks(self, lens: Tensor) -> None:
         self.lens.copy_(lens.to(torch.int32))
@@ -613,6 +614,10 @@ class InferencePlan:
         key = (n, bool(clamp))
 
         def result() -> Tensor:
+            if self.f16 and self.sat_host.is_pinned() and not torch.cuda.is_current_stream_capturing():
+                # the range flag follows every launch sequence to pinned host memory (4 bytes, outside the
+                # graph: a D2H node would sit on the replay's critical path); generator.py reads it
+                self.sat_host.copy_(self.sat, non_blocking=True)
             if out is None:
                 return self.x_audio.clone()
             out.copy_(self.x_audio, non_blocking=True)

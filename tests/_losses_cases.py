@@ -46,7 +46,7 @@ def case_l1_terms(dev):
     xs2 = [x.detach().clone().requires_grad_(True) for x in xs]
     got = l1_terms(refs, xs)        # refs keep every stride pattern; dense permuted xs keep theirs too
     want = sum(F.l1_loss(r.detach(), x) for r, x in zip(refs, xs2))
-    assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want)), (float(got), float(want))
+    assert abs(float(got) - float(want)) <= 5e-6 * abs(float(want)), (float(got), float(want))
     (got * 0.37).backward()
     (want * 0.37).backward()
     for i, (a, b) in enumerate(zip(xs, xs2)):
@@ -85,7 +85,7 @@ def case_hinge_terms(dev):
     b = [s.clone().requires_grad_(True) for s in scores]
     got = hinge_terms(a, signs)
     want = sum(torch.mean(torch.clamp(1 + sg * s, min=0)) for s, sg in zip(b, signs))
-    assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want))
+    assert abs(float(got) - float(want)) <= 5e-6 * abs(float(want))
     (got * 1.7).backward()
     (want * 1.7).backward()
     for i, (x, y) in enumerate(zip(a, b)):
