@@ -132,6 +132,9 @@ _SIGS = {
     "f2g_stft_bwd_fold": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
     "f2g_spec_loss_bwd": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _i, _f, _fp, _i, _fp, _fp, _fp], _i),
     "f2g_colsum": ([_fp, _i, _i, _i, _fp, _fp], _i),
+    "f2g_conv_small_fwd": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _fp], _i),
+    "f2g_conv_small_bwd": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _fp, _fp,
+                            _fp, _fp], _i),
     "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_conv_w_pack": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
@@ -471,6 +474,17 @@ def stft_bwd_fold(frames_grad, B, T, n_fft, hop, frames, dx, accumulate):
 def spec_loss_bwd(audio, B, T, ld_audio, n_fft, hop, mode, fb, n_filt, log_clip, dF, ld_dF, frames_out):
     _check(lib().f2g_spec_loss_bwd(ptr(audio), B, T, ld_audio, n_fft, hop, mode, ptr(fb), n_filt,
                                    float(log_clip), ptr(dF), ld_dF, ptr(frames_out), ptr(fb_ranges(fb)), stream()))
+
+
+def conv_small_fwd(x, Nb, H, W, Cin, pitches, w, bias, Co, kh, kw, sh, sw, ph, pw, leaky, y):
+    _check(lib().f2g_conv_small_fwd(ptr(x), Nb, H, W, Cin, pitches[0], pitches[1], pitches[2], ptr(w), ptr(bias), Co,
+                                    kh, kw, sh, sw, ph, pw, float(-1.0 if leaky is None else leaky), ptr(y), stream()))
+
+
+def conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gw_packed, gb, dx):
+    _check(lib().f2g_conv_small_bwd(ptr(x), Nb, H, W, Cin, pitches[0], pitches[1], pitches[2], ptr(w), Co, kh, kw,
+                                    sh, sw, ph, pw, float(-1.0 if leaky is None else leaky), ptr(dy), ptr(y),
+                                    ptr(gw_packed), ptr(gb), ptr(dx), stream()))
 
 
 def colsum(x, ld, rows, cols, out):

@@ -166,6 +166,200 @@ __global__ void conv_w_pack_kernel(const float* __restrict__ src, int Co, int Ci
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Direct convolution for the FIRST layer of every discriminator stack (Cin = 1: DiscriminatorP, the
+// (5,1) stride-3 conv run along the contiguous axis; Cin = 2: DiscriminatorR, (3,9) on [re, im]),
+// Cout = 32, LeakyReLU fused (flow2gan/models/discriminators.py:65,171).  K = kh*kw*Cin <= 64, so a
+// GEMM formulation has to MATERIALISE an im2col matrix 27-54x the size of the input (1 GB per D+G pair,
+// 20 % of the pair's GPU time for 2 % of its FLOPs, tools/train_glue_census.py) -- here the taps are
+// read from the input itself (L1-resident), in fp32 (no TF32 rounding on this layer at all).
+// Thread = (output pixel, 4 output channels): 8 lanes per pixel, 128-byte coalesced pixel rows.
+// ---------------------------------------------------------------------------------------------
+struct SmallConv {
+  int Nb, H, W, Ho, Wo;
+  long long pitch_n, pitch_h, pitch_w;      // input strides in elements (channel stride 1)
+  int kh, kw, sh, sw, ph, pw;
+  float leaky;                              // < 0: no activation
+};
+constexpr int SC_CO = 32;
+constexpr int SC_MAX_K = 64;
+constexpr int SC_THREADS = 256;
+
+// weights (Co, Cin, kh, kw) -> shared [k = (s*kw + t)*CIN + ci][co]
+template <int CIN>
+F2G_SIMT_DEV void sc_load_weights(const float* __restrict__ w, int kh, int kw, float* sw_) {
+  const int taps = kh * kw;
+  for (int i = threadIdx.x; i < taps * CIN * SC_CO; i += blockDim.x) {
+    const int co = i % SC_CO, k = i / SC_CO;
+    const int ci = k % CIN, tap = k / CIN;
+    sw_[i] = w[((long long)co * CIN + ci) * taps + tap];
+  }
+}
+
+template <int CIN>
+F2G_KERNEL void conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ bias, SmallConv g, float* __restrict__ y) {
+  __shared__ float sw_[SC_MAX_K * SC_CO];
+  sc_load_weights<CIN>(w, g.kh, g.kw, sw_);
+  __syncthreads();
+  const long long M = (long long)g.Nb * g.Ho * g.Wo;
+  const int q = threadIdx.x & 7;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * q);
+  for (long long p = (long long)blockIdx.x * (SC_THREADS / 8) + (threadIdx.x >> 3); p < M;
+       p += (long long)gridDim.x * (SC_THREADS / 8)) {
+    const int wo = (int)(p % g.Wo);
+    const long long t = p / g.Wo;
+    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
+    const float* xb = x + n * g.pitch_n;
+    float4 acc = b4;
+    for (int s = 0; s < g.kh; ++s) {
+      const int h = ho * g.sh - g.ph + s;
+      if (h < 0 || h >= g.H) continue;
+      for (int tt = 0; tt < g.kw; ++tt) {
+        const int wi = wo * g.sw - g.pw + tt;
+        if (wi < 0 || wi >= g.W) continue;
+        const float* xp = xb + h * g.pitch_h + wi * g.pitch_w;
+        const float* wp = sw_ + ((s * g.kw + tt) * CIN) * SC_CO + 4 * q;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float xv = xp[ci];
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * SC_CO);
+          acc.x = fmaf(xv, w4.x, acc.x); acc.y = fmaf(xv, w4.y, acc.y);
+          acc.z = fmaf(xv, w4.z, acc.z); acc.w = fmaf(xv, w4.w, acc.w);
+        }
+      }
+    }
+    if (g.leaky >= 0.f) {
+      acc.x = acc.x > 0.f ? acc.x : acc.x * g.leaky; acc.y = acc.y > 0.f ? acc.y : acc.y * g.leaky;
+      acc.z = acc.z > 0.f ? acc.z : acc.z * g.leaky; acc.w = acc.w > 0.f ? acc.w : acc.w * g.leaky;
+    }
+    *reinterpret_cast<float4*>(y + p * SC_CO + 4 * q) = acc;
+  }
+}
+
+// dz = dy * act'(y): LeakyReLU passes slope where the OUTPUT is <= 0 (same sign as the pre-activation)
+F2G_SIMT_DEV float4 sc_dz(const float* __restrict__ dy, const float* __restrict__ y, long long off, float leaky) {
+  float4 d = *reinterpret_cast<const float4*>(dy + off);
+  if (leaky >= 0.f) {
+    const float4 o = *reinterpret_cast<const float4*>(y + off);
+    d.x *= o.x > 0.f ? 1.f : leaky; d.y *= o.y > 0.f ? 1.f : leaky;
+    d.z *= o.z > 0.f ? 1.f : leaky; d.w *= o.w > 0.f ? 1.f : leaky;
+  }
+  return d;
+}
+
+// Weight + bias gradient.  Thread = (tap group kq in [0, 32), channel quad q): it owns taps kq and kq+32 for
+// its 4 channels and walks over the block's share of output pixels; one atomicAdd per owned value at the
+// end (grid = a few hundred blocks).  gw is the PACKED layout [k][co]; gb[co].
+template <int CIN>
+F2G_KERNEL void conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                        const float* __restrict__ y, SmallConv g, float* __restrict__ gw,
+                                        float* __restrict__ gb) {
+  const int K = g.kh * g.kw * CIN;
+  const int q = threadIdx.x & 7, kq = threadIdx.x >> 3;
+  const long long M = (long long)g.Nb * g.Ho * g.Wo;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, ab = a0;
+  int s0 = 0, t0 = 0, c0 = 0, s1 = 0, t1 = 0, c1 = 0;
+  const bool on0 = kq < K, on1 = kq + 32 < K;
+  if (on0) { c0 = kq % CIN; t0 = (kq / CIN) % g.kw; s0 = (kq / CIN) / g.kw; }
+  if (on1) { c1 = (kq + 32) % CIN; t1 = ((kq + 32) / CIN) % g.kw; s1 = ((kq + 32) / CIN) / g.kw; }
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long p_begin = (long long)blockIdx.x * per, p_end = p_begin + per < M ? p_begin + per : M;
+  int wo = 0, ho = 0, n = 0;
+  if (p_begin < M) {
+    wo = (int)(p_begin % g.Wo);
+    const long long t = p_begin / g.Wo;
+    ho = (int)(t % g.Ho); n = (int)(t / g.Ho);
+  }
+  for (long long p = p_begin; p < p_end; ++p) {
+    const float4 d = sc_dz(dy, y, p * SC_CO + 4 * q, g.leaky);
+    if (kq == 0) { ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w; }
+    const float* xb = x + n * g.pitch_n;
+    if (on0) {
+      const int h = ho * g.sh - g.ph + s0, wi = wo * g.sw - g.pw + t0;
+      if (h >= 0 && h < g.H && wi >= 0 && wi < g.W) {
+        const float xv = xb[h * g.pitch_h + wi * g.pitch_w + c0];
+        a0.x = fmaf(xv, d.x, a0.x); a0.y = fmaf(xv, d.y, a0.y); a0.z = fmaf(xv, d.z, a0.z); a0.w = fmaf(xv, d.w, a0.w);
+      }
+    }
+    if (on1) {
+      const int h = ho * g.sh - g.ph + s1, wi = wo * g.sw - g.pw + t1;
+      if (h >= 0 && h < g.H && wi >= 0 && wi < g.W) {
+        const float xv = xb[h * g.pitch_h + wi * g.pitch_w + c1];
+        a1.x = fmaf(xv, d.x, a1.x); a1.y = fmaf(xv, d.y, a1.y); a1.z = fmaf(xv, d.z, a1.z); a1.w = fmaf(xv, d.w, a1.w);
+      }
+    }
+    if (++wo == g.Wo) { wo = 0; if (++ho == g.Ho) { ho = 0; ++n; } }
+  }
+  if (on0) {
+    float* o = gw + kq * SC_CO + 4 * q;
+    atomicAdd(o, a0.x); atomicAdd(o + 1, a0.y); atomicAdd(o + 2, a0.z); atomicAdd(o + 3, a0.w);
+  }
+  if (on1) {
+    float* o = gw + (kq + 32) * SC_CO + 4 * q;
+    atomicAdd(o, a1.x); atomicAdd(o + 1, a1.y); atomicAdd(o + 2, a1.z); atomicAdd(o + 3, a1.w);
+  }
+  if (kq == 0 && gb) {
+    float* o = gb + 4 * q;
+    atomicAdd(o, ab.x); atomicAdd(o + 1, ab.y); atomicAdd(o + 2, ab.z); atomicAdd(o + 3, ab.w);
+  }
+}
+
+// Input gradient (needed only when the waveform itself carries a gradient: the fake half of the G phase).
+// Thread = (input pixel, channel quad): gathers every tap that read the pixel, 8-lane butterfly at the end.
+template <int CIN>
+F2G_KERNEL void conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                        const float* __restrict__ w, SmallConv g, float* __restrict__ dx) {
+  __shared__ float sw_[SC_MAX_K * SC_CO];
+  sc_load_weights<CIN>(w, g.kh, g.kw, sw_);
+  __syncthreads();
+  const long long P = (long long)g.Nb * g.H * g.W;
+  const int q = threadIdx.x & 7;
+  const long long span = (long long)gridDim.x * (SC_THREADS / 8);
+  const long long rounds = (P + span - 1) / span;          // every lane runs the same number of rounds (shuffles)
+  for (long long r = 0; r < rounds; ++r) {
+    const long long p = r * span + (long long)blockIdx.x * (SC_THREADS / 8) + (threadIdx.x >> 3);
+    float acc[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+    int wi = 0, h = 0, n = 0;
+    if (p < P) {
+      wi = (int)(p % g.W);
+      const long long t = p / g.W;
+      h = (int)(t % g.H); n = (int)(t / g.H);
+      for (int s = 0; s < g.kh; ++s) {
+        const int hn = h + g.ph - s;
+        if (hn < 0 || hn % g.sh != 0) continue;
+        const int ho = hn / g.sh;
+        if (ho >= g.Ho) continue;
+        for (int tt = 0; tt < g.kw; ++tt) {
+          const int wn = wi + g.pw - tt;
+          if (wn < 0 || wn % g.sw != 0) continue;
+          const int wo = wn / g.sw;
+          if (wo >= g.Wo) continue;
+          const long long m = ((long long)n * g.Ho + ho) * g.Wo + wo;
+          const float4 d = sc_dz(dy, y, m * SC_CO + 4 * q, g.leaky);
+          const float* wp = sw_ + ((s * g.kw + tt) * CIN) * SC_CO + 4 * q;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * SC_CO);
+            acc[ci] = fmaf(d.x, w4.x, fmaf(d.y, w4.y, fmaf(d.z, w4.z, fmaf(d.w, w4.w, acc[ci]))));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float v = acc[ci];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (q == 0 && p < P) dx[p * CIN + ci] = v;
+    }
+  }
+}
+
 }  // namespace f2g
 
 using namespace f2g;
@@ -217,6 +411,62 @@ __global__ void conv_w_pack_dgrad_kernel(const float* __restrict__ w, int Co, in
     if (co < Co) v = w[(((long long)co * Ci + ci) * kh + s) * kw + p + sw * (ntp - 1 - jj)];
     out[i] = tf32_rna(v);
   }
+}
+
+static int sc_fill(SmallConv& g, int Nb, int H, int W, long long pitch_n, long long pitch_h, long long pitch_w,
+                   int kh, int kw, int sh, int sw, int ph, int pw, int Cin, int Co, float leaky, const char* who) {
+  g.Nb = Nb; g.H = H; g.W = W; g.pitch_n = pitch_n; g.pitch_h = pitch_h; g.pitch_w = pitch_w;
+  g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.ph = ph; g.pw = pw; g.leaky = leaky;
+  g.Ho = (H + 2 * ph - kh) / sh + 1;
+  g.Wo = (W + 2 * pw - kw) / sw + 1;
+  if ((Cin != 1 && Cin != 2) || Co != SC_CO || kh * kw * Cin > SC_MAX_K || g.Ho < 1 || g.Wo < 1 || sh < 1 || sw < 1) {
+    set_error("%s: needs Cin in {1, 2}, Cout = 32, kh*kw*Cin <= 64 (Cin=%d Cout=%d kh=%d kw=%d)", who, Cin, Co, kh, kw);
+    return F2G_EINVAL;
+  }
+  return 0;
+}
+
+static int sc_grid(long long pixels) {
+  long long b = (pixels + SC_THREADS / 8 - 1) / (SC_THREADS / 8);
+  const long long cap = 148LL * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+extern "C" int f2g_conv_small_fwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
+                                  long long pitch_w, const float* w, const float* bias, int Co, int kh, int kw,
+                                  int sh, int sw, int ph, int pw, float leaky, float* y, void* stream) {
+  SmallConv g;
+  if (int rc = sc_fill(g, Nb, H, W, pitch_n, pitch_h, pitch_w, kh, kw, sh, sw, ph, pw, Cin, Co, leaky, "f2g_conv_small_fwd"))
+    return rc;
+  const int grid = sc_grid((long long)Nb * g.Ho * g.Wo);
+  if (Cin == 1) F2G_LAUNCH_COOP(conv_small_fwd_kernel<1>, grid, SC_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y);
+  else F2G_LAUNCH_COOP(conv_small_fwd_kernel<2>, grid, SC_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y);
+  return check_launch("f2g_conv_small_fwd");
+}
+
+extern "C" int f2g_conv_small_bwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
+                                  long long pitch_w, const float* w, int Co, int kh, int kw, int sh, int sw, int ph,
+                                  int pw, float leaky, const float* dy, const float* y, float* gw_packed, float* gb,
+                                  float* dx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SmallConv g;
+  if (int rc = sc_fill(g, Nb, H, W, pitch_n, pitch_h, pitch_w, kh, kw, sh, sw, ph, pw, Cin, Co, leaky, "f2g_conv_small_bwd"))
+    return rc;
+  if (gw_packed) {        // caller zeroed gw_packed (kh*kw*Cin x 32) and gb (32)
+    const long long M = (long long)Nb * g.Ho * g.Wo;
+    long long blocks = M / 512;                        // >= 512 pixels per block: few atomics, long FMA runs
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+    if (Cin == 1) F2G_LAUNCH_COOP(conv_small_wgrad_kernel<1>, (int)blocks, SC_THREADS, stream, x, dy, y, g, gw_packed, gb);
+    else F2G_LAUNCH_COOP(conv_small_wgrad_kernel<2>, (int)blocks, SC_THREADS, stream, x, dy, y, g, gw_packed, gb);
+    if (int rc = check_launch("f2g_conv_small_bwd(wgrad)")) return rc;
+  }
+  if (dx) {
+    const int grid = sc_grid((long long)Nb * H * W);
+    if (Cin == 1) F2G_LAUNCH_COOP(conv_small_dgrad_kernel<1>, grid, SC_THREADS, stream, dy, y, w, g, dx);
+    else F2G_LAUNCH_COOP(conv_small_dgrad_kernel<2>, grid, SC_THREADS, stream, dy, y, w, g, dx);
+    if (int rc = check_launch("f2g_conv_small_bwd(dgrad)")) return rc;
+  }
+  return F2G_OK;
 }
 
 extern "C" int f2g_im2col2d(const float* x, const F2GConv2d* p, float* col, int round_tf32, void* stream) {

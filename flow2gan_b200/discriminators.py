@@ -1,7 +1,8 @@
 """Multi-Period and Multi-Resolution discriminators with the reference's module tree / parameter
 names (flow2gan/models/discriminators.py:18-219; weight_norm disabled there, :13-15), computed on
-channel-last tensors: every Conv2d = im2col gather + tcgen05 TF32 GEMM (+bias+LeakyReLU fused in
-the epilogue); backward = act adjoint + split-K wgrad GEMM + dgrad GEMM + col2im (csrc/conv.cu)."""
+channel-last tensors: the wide convs are windowed ("implicit im2col") tcgen05 TF32 GEMMs (convwin.py),
+the first layer of every stack (Cin = 1 / 2) is a direct fp32 convolution (csrc/conv.cu::conv_small_*);
+the gather (im2col + GEMM + col2im) path remains as the general fallback and A/B reference."""
 from __future__ import annotations
 
 import os
@@ -87,6 +88,48 @@ class _Conv2dCLFn(torch.autograd.Function):
         return gx, gW, gb, None, None, None, None, None, None
 
 
+class _ConvSmallFn(torch.autograd.Function):
+    """First layer of a discriminator stack (Cin = 1 or 2 -> 32 channels, LeakyReLU): direct fp32
+    convolution (csrc/conv.cu::conv_small_*), no im2col matrix, no TF32 rounding.  x: channel-last
+    (Nb, H, W, Cin) view with unit channel stride; returns (Nb, Ho, Wo, 32)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, sh: int, sw: int, ph: int, pw: int,
+                leaky: Optional[float]):
+        Nb, H, W, Cin = x.shape
+        Co, _, kh, kw = weight.shape
+        assert x.stride(3) == 1 and x.dtype == torch.float32
+        w = weight.detach().contiguous()
+        Ho = (H + 2 * ph - kh) // sh + 1
+        Wo = (W + 2 * pw - kw) // sw + 1
+        y = torch.empty(Nb * Ho * Wo, Co, device=x.device, dtype=torch.float32)
+        pitches = (x.stride(0), x.stride(1), x.stride(2))
+        L.conv_small_fwd(x, Nb, H, W, Cin, pitches, w, bias.detach(), Co, kh, kw, sh, sw, ph, pw, leaky, y)
+        ctx.saved = (x.detach(), w, y, (Nb, H, W, Cin, Co, kh, kw, sh, sw, ph, pw, Ho, Wo), pitches, leaky)
+        return y.view(Nb, Ho, Wo, Co)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, w, y, dims, pitches, leaky = ctx.saved
+        Nb, H, W, Cin, Co, kh, kw, sh, sw, ph, pw, Ho, Wo = dims
+        dy = dy.contiguous()
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        K = kh * kw * Cin
+        acc = torch.zeros(K * Co + Co, device=dy.device, dtype=torch.float32) if need_w else None
+        gwp = acc[:K * Co] if need_w else None
+        gbv = acc[K * Co:] if need_w else None
+        dx = torch.empty(Nb, H, W, Cin, device=dy.device, dtype=torch.float32) if need_x else None
+        L.conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gwp, gbv, dx)
+        gW = gwp.view(kh, kw, Cin, Co).permute(3, 2, 0, 1).contiguous() if ctx.needs_input_grad[1] else None
+        gb = gbv if ctx.needs_input_grad[2] else None
+        return dx, gW, gb, None, None, None, None, None
+
+
+def _small_ok(x: Tensor, w: Tensor) -> bool:
+    return (x.shape[3] in (1, 2) and w.shape[0] == 32 and w.shape[2] * w.shape[3] * x.shape[3] <= 64
+            and x.stride(3) == 1 and x.dtype == torch.float32)
+
+
 def _pack_cache(conv: nn.Conv2d, weight: Tensor, key: str) -> dict:
     """GEMM-ready weight layouts of one Conv2d, kept on the module and rebuilt IN PLACE only when the
     parameter's version (optimizer steps bump it) or storage changed: a D+G iteration pair runs every
@@ -116,6 +159,8 @@ def conv2d_cl(x: Tensor, conv: nn.Conv2d, leaky: Optional[float], train_weights:
         sh, sw, ph, pw = sw, sh, pw, ph
     if _USE_WINDOWED and convwin.supports(x.shape[3], w.shape[2], w.shape[3], sh, sw):
         return convwin.conv2d_win(x, w, b, sw, ph, pw, leaky, _pack_cache(conv, w, "win%d" % swap_hw))
+    if _USE_WINDOWED and _small_ok(x, w):          # first layers (Cin = 1 / 2): direct convolution, no im2col
+        return _ConvSmallFn.apply(x, w, b, sh, sw, ph, pw, leaky)
     return _Conv2dCLFn.apply(x, w, b, sh, sw, ph, pw, leaky, _pack_cache(conv, w, "col%d" % swap_hw))
 
 

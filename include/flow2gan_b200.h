@@ -314,6 +314,22 @@ int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft,
                       const float* fb, int n_filt, float log_clip, const float* dF, int ld_dF,
                       float* frames_out, const int* fb_ranges, void* stream);
 
+/* Direct convolution of the discriminators' FIRST layers (torch.nn.Conv2d(1, 32, (5,1), (3,1)) of
+ * DiscriminatorP, discriminators.py:65, run here along the contiguous axis; Conv2d(2, 32, (3,9)) of
+ * DiscriminatorR, :171) with the LeakyReLU fused, fp32 SIMT: Cin in {1, 2}, Cout = 32, kh*kw*Cin <= 64.
+ * x: channel-last (Nb, H, W, Cin) view with element strides (pitch_n, pitch_h, pitch_w), channel stride 1;
+ * w, bias: the parameter tensors (Co, Cin, kh, kw) / (Co); y: (Nb*Ho*Wo, 32) contiguous; leaky < 0: no
+ * activation.  bwd: dy / y contiguous (rows, 32); gw_packed (kh*kw*Cin, 32) [k = (s*kw + t)*Cin + ci][co] and
+ * gb (32) are ACCUMULATED into (zero them first; NULL gw_packed: no weight gradient); dx (Nb, H, W, Cin)
+ * contiguous or NULL. */
+int f2g_conv_small_fwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
+                       long long pitch_w, const float* w, const float* bias, int Co, int kh, int kw, int sh, int sw,
+                       int ph, int pw, float leaky, float* y, void* stream);
+int f2g_conv_small_bwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
+                       long long pitch_w, const float* w, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                       float leaky, const float* dy, const float* y, float* gw_packed, float* gb, float* dx,
+                       void* stream);
+
 /* out[c] += sum_r x[r*ld + c]  (bias gradients). */
 int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream);
 
