@@ -134,7 +134,7 @@ _SIGS = {
     "f2g_colsum": ([_fp, _i, _i, _i, _fp, _fp], _i),
     "f2g_conv_small_fwd": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _fp], _i),
     "f2g_conv_small_bwd": ([_fp, _i, _i, _i, _i, _ll, _ll, _ll, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _fp, _fp,
-                            _fp, _fp], _i),
+                            _fp, _fp, _ll, _fp], _i),
     "f2g_im2col2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_col2im2d": ([_fp, C.POINTER(F2GConv2d), _fp, _i, _fp], _i),
     "f2g_conv_w_pack": ([_fp, _i, _i, _i, _i, _i, _fp, _i, _fp], _i),
@@ -481,10 +481,12 @@ def conv_small_fwd(x, Nb, H, W, Cin, pitches, w, bias, Co, kh, kw, sh, sw, ph, p
                                     kh, kw, sh, sw, ph, pw, float(-1.0 if leaky is None else leaky), ptr(y), stream()))
 
 
-def conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gw_packed, gb, dx):
+def conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gw_packed, gb, dx,
+                   scratch=None):
     _check(lib().f2g_conv_small_bwd(ptr(x), Nb, H, W, Cin, pitches[0], pitches[1], pitches[2], ptr(w), Co, kh, kw,
                                     sh, sw, ph, pw, float(-1.0 if leaky is None else leaky), ptr(dy), ptr(y),
-                                    ptr(gw_packed), ptr(gb), ptr(dx), stream()))
+                                    ptr(gw_packed), ptr(gb), ptr(dx), ptr(scratch),
+                                    0 if scratch is None else scratch.numel(), stream()))
 
 
 def colsum(x, ld, rows, cols, out):

@@ -185,6 +185,10 @@ struct SmallConv {
 constexpr int SC_CO = 32;
 constexpr int SC_MAX_K = 64;
 constexpr int SC_THREADS = 256;
+constexpr int SCW_THREADS = 64;
+constexpr int SCW_TILE = 32;
+constexpr int SCW_TAPS = 7;
+constexpr int SCW_MAX_PATCH = 3 * ((SCW_TILE - 1) * 3 + 9) * 2 + 64;     // kh <= 3 rows, sw <= 3, kw <= 9, Cin <= 2
 
 // weights (Co, Cin, kh, kw) -> shared [k = (s*kw + t)*CIN + ci][co]
 template <int CIN>
@@ -197,44 +201,69 @@ F2G_SIMT_DEV void sc_load_weights(const float* __restrict__ w, int kh, int kw, f
   }
 }
 
+// Forward.  Block = 64 threads = 8 channel quads x 8 pixel groups and owns a tile of 32 consecutive output
+// pixels of one output row: the zero-padded input patch is staged in shared memory once, a thread then
+// produces 4 pixels x 4 channels (one LDS.128 of weights + 4 LDS.32 of taps per 16 FMA, no bounds tests).
+constexpr int SCF_THREADS = 64;
 template <int CIN>
 F2G_KERNEL void conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                      const float* __restrict__ bias, SmallConv g, float* __restrict__ y) {
+                                      const float* __restrict__ bias, SmallConv g, float* __restrict__ y,
+                                      int tiles_per_row, long long n_tiles) {
   __shared__ float sw_[SC_MAX_K * SC_CO];
+  __shared__ float s_x[SCW_MAX_PATCH];
   sc_load_weights<CIN>(w, g.kh, g.kw, sw_);
-  __syncthreads();
-  const long long M = (long long)g.Nb * g.Ho * g.Wo;
-  const int q = threadIdx.x & 7;
+  const int q = threadIdx.x & 7, pg = threadIdx.x >> 3;           // pixels pg, pg + 8, pg + 16, pg + 24 of the tile
   const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * q);
-  for (long long p = (long long)blockIdx.x * (SC_THREADS / 8) + (threadIdx.x >> 3); p < M;
-       p += (long long)gridDim.x * (SC_THREADS / 8)) {
-    const int wo = (int)(p % g.Wo);
-    const long long t = p / g.Wo;
-    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
-    const float* xb = x + n * g.pitch_n;
-    float4 acc = b4;
-    for (int s = 0; s < g.kh; ++s) {
-      const int h = ho * g.sh - g.ph + s;
-      if (h < 0 || h >= g.H) continue;
+  const int patch_w = (SCW_TILE - 1) * g.sw + g.kw;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_per_row);
+    const long long row = tile / tiles_per_row;
+    const int ho = (int)(row % g.Ho), n = (int)(row / g.Ho);
+    const int wo0 = tx * SCW_TILE;
+    __syncthreads();
+    {
+      const float* xb = x + n * g.pitch_n;
+      const int h0 = ho * g.sh - g.ph, w0 = wo0 * g.sw - g.pw;
+      for (int i = threadIdx.x; i < g.kh * patch_w * CIN; i += SCF_THREADS) {
+        const int ci = i % CIN, col = (i / CIN) % patch_w, rr = (i / CIN) / patch_w;
+        const int h = h0 + rr, wi = w0 + col;
+        s_x[i] = (h >= 0 && h < g.H && wi >= 0 && wi < g.W) ? xb[h * g.pitch_h + wi * g.pitch_w + ci] : 0.f;
+      }
+    }
+    __syncthreads();
+    float4 acc[4] = {b4, b4, b4, b4};
+    const int jstep = 8 * g.sw * CIN;
+    for (int ss = 0; ss < g.kh; ++ss) {
+      const float* xrow = s_x + (ss * patch_w + pg * g.sw) * CIN;
+      const float* wrow = sw_ + ss * g.kw * CIN * SC_CO + 4 * q;
+#pragma unroll 3
       for (int tt = 0; tt < g.kw; ++tt) {
-        const int wi = wo * g.sw - g.pw + tt;
-        if (wi < 0 || wi >= g.W) continue;
-        const float* xp = xb + h * g.pitch_h + wi * g.pitch_w;
-        const float* wp = sw_ + ((s * g.kw + tt) * CIN) * SC_CO + 4 * q;
+        const float* xp = xrow + tt * CIN;
+        const float* wp = wrow + tt * CIN * SC_CO;
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          const float xv = xp[ci];
           const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * SC_CO);
-          acc.x = fmaf(xv, w4.x, acc.x); acc.y = fmaf(xv, w4.y, acc.y);
-          acc.z = fmaf(xv, w4.z, acc.z); acc.w = fmaf(xv, w4.w, acc.w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xv = xp[j * jstep + ci];
+            acc[j].x = fmaf(xv, w4.x, acc[j].x); acc[j].y = fmaf(xv, w4.y, acc[j].y);
+            acc[j].z = fmaf(xv, w4.z, acc[j].z); acc[j].w = fmaf(xv, w4.w, acc[j].w);
+          }
         }
       }
     }
-    if (g.leaky >= 0.f) {
-      acc.x = acc.x > 0.f ? acc.x : acc.x * g.leaky; acc.y = acc.y > 0.f ? acc.y : acc.y * g.leaky;
-      acc.z = acc.z > 0.f ? acc.z : acc.z * g.leaky; acc.w = acc.w > 0.f ? acc.w : acc.w * g.leaky;
+    float* yrow = y + (row * g.Wo + wo0) * SC_CO + 4 * q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int px = pg + 8 * j;
+      if (wo0 + px >= g.Wo) continue;
+      float4 a = acc[j];
+      if (g.leaky >= 0.f) {
+        a.x = a.x > 0.f ? a.x : a.x * g.leaky; a.y = a.y > 0.f ? a.y : a.y * g.leaky;
+        a.z = a.z > 0.f ? a.z : a.z * g.leaky; a.w = a.w > 0.f ? a.w : a.w * g.leaky;
+      }
+      *reinterpret_cast<float4*>(yrow + px * SC_CO) = a;
     }
-    *reinterpret_cast<float4*>(y + p * SC_CO + 4 * q) = acc;
   }
 }
 
@@ -249,98 +278,164 @@ F2G_SIMT_DEV float4 sc_dz(const float* __restrict__ dy, const float* __restrict_
   return d;
 }
 
-// Weight + bias gradient.  Thread = (tap group kq in [0, 32), channel quad q): it owns taps kq and kq+32 for
-// its 4 channels and walks over the block's share of output pixels; one atomicAdd per owned value at the
-// end (grid = a few hundred blocks).  gw is the PACKED layout [k][co]; gb[co].
+// Weight + bias gradient.  Block = 64 threads = 8 channel quads x 8 tap groups; a thread owns 7 taps
+// (7 * 8 = 56 >= K) of its 4 channels = 28 accumulators.  The block walks over tiles of 32 consecutive
+// output pixels of one output row: dz = dy * act'(y) (32 x 32) and the zero-padded input patch the tile's
+// taps touch are staged in shared memory once, then every pixel costs one LDS.128 + 7 LDS.32 + 28 FMA per
+// thread with no bounds tests.  Partial sums go to part[block][K*32 + 32] (no atomics: the reduction
+// kernel below adds the blocks in a fixed order, so the gradient is bit-reproducible).
+
 template <int CIN>
 F2G_KERNEL void conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                        const float* __restrict__ y, SmallConv g, float* __restrict__ gw,
-                                        float* __restrict__ gb) {
+                                        const float* __restrict__ y, SmallConv g, float* __restrict__ part,
+                                        int tiles_per_row, long long n_tiles) {
+  __shared__ float s_dz[SCW_TILE * SC_CO];
+  __shared__ float s_x[SCW_MAX_PATCH];
   const int K = g.kh * g.kw * CIN;
-  const int q = threadIdx.x & 7, kq = threadIdx.x >> 3;
-  const long long M = (long long)g.Nb * g.Ho * g.Wo;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, ab = a0;
-  int s0 = 0, t0 = 0, c0 = 0, s1 = 0, t1 = 0, c1 = 0;
-  const bool on0 = kq < K, on1 = kq + 32 < K;
-  if (on0) { c0 = kq % CIN; t0 = (kq / CIN) % g.kw; s0 = (kq / CIN) / g.kw; }
-  if (on1) { c1 = (kq + 32) % CIN; t1 = ((kq + 32) / CIN) % g.kw; s1 = ((kq + 32) / CIN) / g.kw; }
-  const long long per = (M + gridDim.x - 1) / gridDim.x;
-  const long long p_begin = (long long)blockIdx.x * per, p_end = p_begin + per < M ? p_begin + per : M;
-  int wo = 0, ho = 0, n = 0;
-  if (p_begin < M) {
-    wo = (int)(p_begin % g.Wo);
-    const long long t = p_begin / g.Wo;
-    ho = (int)(t % g.Ho); n = (int)(t / g.Ho);
+  const int q = threadIdx.x & 7, kg = threadIdx.x >> 3;
+  const int patch_w = (SCW_TILE - 1) * g.sw + g.kw;              // input columns a tile's taps touch
+  int off[SCW_TAPS];                                              // patch offset of each owned tap (pixel 0)
+  bool on[SCW_TAPS];
+#pragma unroll
+  for (int j = 0; j < SCW_TAPS; ++j) {
+    const int k = kg * SCW_TAPS + j;
+    on[j] = k < K;
+    const int ci = k % CIN, tap = k / CIN;
+    const int tt = tap % g.kw, ss = tap / g.kw;
+    off[j] = on[j] ? (ss * patch_w + tt) * CIN + ci : 0;
   }
-  for (long long p = p_begin; p < p_end; ++p) {
-    const float4 d = sc_dz(dy, y, p * SC_CO + 4 * q, g.leaky);
-    if (kq == 0) { ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w; }
-    const float* xb = x + n * g.pitch_n;
-    if (on0) {
-      const int h = ho * g.sh - g.ph + s0, wi = wo * g.sw - g.pw + t0;
-      if (h >= 0 && h < g.H && wi >= 0 && wi < g.W) {
-        const float xv = xb[h * g.pitch_h + wi * g.pitch_w + c0];
-        a0.x = fmaf(xv, d.x, a0.x); a0.y = fmaf(xv, d.y, a0.y); a0.z = fmaf(xv, d.z, a0.z); a0.w = fmaf(xv, d.w, a0.w);
+  float acc[SCW_TAPS][4];
+#pragma unroll
+  for (int j = 0; j < SCW_TAPS; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int step = SCW_TILE > 0 ? g.sw * CIN : 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_per_row);
+    const long long row = tile / tiles_per_row;                   // (n, ho)
+    const int ho = (int)(row % g.Ho), n = (int)(row / g.Ho);
+    const int wo0 = tx * SCW_TILE;
+    const int npx = g.Wo - wo0 < SCW_TILE ? g.Wo - wo0 : SCW_TILE;
+    __syncthreads();                                              // previous tile fully consumed
+    {   // dz tile: pixels beyond the row end contribute zeros
+      const long long m0 = (row * g.Wo + wo0) * SC_CO;
+      for (int i = threadIdx.x; i < SCW_TILE * SC_CO / 4; i += SCW_THREADS) {
+        const int px = i >> 3;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px < npx) d = sc_dz(dy, y, m0 + (long long)i * 4, g.leaky);
+        *reinterpret_cast<float4*>(s_dz + i * 4) = d;
+      }
+      // input patch with the zero padding materialised
+      const float* xb = x + n * g.pitch_n;
+      const int h0 = ho * g.sh - g.ph, w0 = wo0 * g.sw - g.pw;
+      for (int i = threadIdx.x; i < g.kh * patch_w * CIN; i += SCW_THREADS) {
+        const int ci = i % CIN, col = (i / CIN) % patch_w, rr = (i / CIN) / patch_w;
+        const int h = h0 + rr, wi = w0 + col;
+        s_x[i] = (h >= 0 && h < g.H && wi >= 0 && wi < g.W) ? xb[h * g.pitch_h + wi * g.pitch_w + ci] : 0.f;
       }
     }
-    if (on1) {
-      const int h = ho * g.sh - g.ph + s1, wi = wo * g.sw - g.pw + t1;
-      if (h >= 0 && h < g.H && wi >= 0 && wi < g.W) {
-        const float xv = xb[h * g.pitch_h + wi * g.pitch_w + c1];
-        a1.x = fmaf(xv, d.x, a1.x); a1.y = fmaf(xv, d.y, a1.y); a1.z = fmaf(xv, d.z, a1.z); a1.w = fmaf(xv, d.w, a1.w);
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < SCW_TILE; ++px) {
+      const float4 d = *reinterpret_cast<const float4*>(s_dz + px * SC_CO + 4 * q);
+      if (kg == 0) { ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w; }
+      const float* xp = s_x + px * step;
+#pragma unroll
+      for (int j = 0; j < SCW_TAPS; ++j) {
+        const float xv = xp[off[j]];
+        acc[j][0] = fmaf(xv, d.x, acc[j][0]); acc[j][1] = fmaf(xv, d.y, acc[j][1]);
+        acc[j][2] = fmaf(xv, d.z, acc[j][2]); acc[j][3] = fmaf(xv, d.w, acc[j][3]);
       }
     }
-    if (++wo == g.Wo) { wo = 0; if (++ho == g.Ho) { ho = 0; ++n; } }
   }
-  if (on0) {
-    float* o = gw + kq * SC_CO + 4 * q;
-    atomicAdd(o, a0.x); atomicAdd(o + 1, a0.y); atomicAdd(o + 2, a0.z); atomicAdd(o + 3, a0.w);
-  }
-  if (on1) {
-    float* o = gw + (kq + 32) * SC_CO + 4 * q;
-    atomicAdd(o, a1.x); atomicAdd(o + 1, a1.y); atomicAdd(o + 2, a1.z); atomicAdd(o + 3, a1.w);
-  }
-  if (kq == 0 && gb) {
-    float* o = gb + 4 * q;
-    atomicAdd(o, ab.x); atomicAdd(o + 1, ab.y); atomicAdd(o + 2, ab.z); atomicAdd(o + 3, ab.w);
+  float* o = part + (long long)blockIdx.x * (K * SC_CO + SC_CO);
+#pragma unroll
+  for (int j = 0; j < SCW_TAPS; ++j)
+    if (on[j])
+      *reinterpret_cast<float4*>(o + (kg * SCW_TAPS + j) * SC_CO + 4 * q) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+  if (kg == 0) *reinterpret_cast<float4*>(o + K * SC_CO + 4 * q) = ab;
+}
+
+// gw[i] += sum_b part[b][i]  (i < K*32: packed weight gradient, then 32 bias sums).  Block = 32 values x 8
+// slices of the partial records; the slices are added in a fixed order (bit-reproducible).
+F2G_KERNEL void conv_small_wgrad_reduce_kernel(const float* __restrict__ part, int n_blocks, int n_vals,
+                                               float* __restrict__ gw, float* __restrict__ gb, int n_w) {
+  __shared__ float red[8][32];
+  const int v = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + v;
+  float s = 0.f;
+  if (i < n_vals)
+    for (int b = sl; b < n_blocks; b += 8) s += part[(long long)b * n_vals + i];
+  red[sl][v] = s;
+  __syncthreads();
+  if (sl == 0 && i < n_vals) {
+    float t = red[0][v];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][v];
+    if (i < n_w) gw[i] += t;
+    else if (gb) gb[i - n_w] += t;
   }
 }
 
 // Input gradient (needed only when the waveform itself carries a gradient: the fake half of the G phase).
-// Thread = (input pixel, channel quad): gathers every tap that read the pixel, 8-lane butterfly at the end.
+// Block = 256 threads = 32 consecutive input pixels of one input row x 8 channel quads.  dz = dy * act'(y) of
+// the (<= 3) output rows x (<= 41) output columns whose taps read the tile is staged in shared memory once;
+// every pixel then gathers its taps from there (LDS only), 8-lane butterfly at the end.
+constexpr int SCD_COLS = 41;
 template <int CIN>
 F2G_KERNEL void conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                        const float* __restrict__ w, SmallConv g, float* __restrict__ dx) {
+                                        const float* __restrict__ w, SmallConv g, float* __restrict__ dx,
+                                        int tiles_per_row, long long n_tiles) {
   __shared__ float sw_[SC_MAX_K * SC_CO];
+  __shared__ float s_dz[3 * SCD_COLS * SC_CO];
+  __shared__ int s_ho[3];
   sc_load_weights<CIN>(w, g.kh, g.kw, sw_);
-  __syncthreads();
-  const long long P = (long long)g.Nb * g.H * g.W;
-  const int q = threadIdx.x & 7;
-  const long long span = (long long)gridDim.x * (SC_THREADS / 8);
-  const long long rounds = (P + span - 1) / span;          // every lane runs the same number of rounds (shuffles)
-  for (long long r = 0; r < rounds; ++r) {
-    const long long p = r * span + (long long)blockIdx.x * (SC_THREADS / 8) + (threadIdx.x >> 3);
+  const int q = threadIdx.x & 7, px = threadIdx.x >> 3;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_per_row);
+    const long long row = tile / tiles_per_row;                  // (n, h)
+    const int h = (int)(row % g.H), n = (int)(row / g.H);
+    const int wi0 = tx * SCW_TILE;
+    // output columns whose window can touch input columns [wi0, wi0 + 32)
+    int lo_num = wi0 + g.pw - (g.kw - 1);
+    int wo_lo = lo_num <= 0 ? 0 : (lo_num + g.sw - 1) / g.sw;
+    int wo_hi = (wi0 + SCW_TILE - 1 + g.pw) / g.sw;
+    if (wo_hi > g.Wo - 1) wo_hi = g.Wo - 1;
+    const int ncols = wo_hi - wo_lo + 1;                          // <= SCD_COLS (kw <= 9, sw >= 1)
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      const int ss = threadIdx.x;
+      const int hn = h + g.ph - ss;
+      int ho = -1;
+      if (ss < g.kh && hn >= 0 && hn % g.sh == 0 && hn / g.sh < g.Ho) ho = hn / g.sh;
+      s_ho[ss] = ho;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.kh * ncols * 8; i += SC_THREADS) {
+      const int qq = i & 7, c = (i >> 3) % ncols, ss = (i >> 3) / ncols;
+      const int ho = s_ho[ss];
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ho >= 0) d = sc_dz(dy, y, (((long long)n * g.Ho + ho) * g.Wo + wo_lo + c) * SC_CO + 4 * qq, g.leaky);
+      *reinterpret_cast<float4*>(s_dz + (ss * SCD_COLS + c) * SC_CO + 4 * qq) = d;
+    }
+    __syncthreads();
+    const int wi = wi0 + px;
     float acc[CIN];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
-    int wi = 0, h = 0, n = 0;
-    if (p < P) {
-      wi = (int)(p % g.W);
-      const long long t = p / g.W;
-      h = (int)(t % g.H); n = (int)(t / g.H);
-      for (int s = 0; s < g.kh; ++s) {
-        const int hn = h + g.ph - s;
-        if (hn < 0 || hn % g.sh != 0) continue;
-        const int ho = hn / g.sh;
-        if (ho >= g.Ho) continue;
+    if (wi < g.W) {
+      for (int ss = 0; ss < g.kh; ++ss) {
+        if (s_ho[ss] < 0) continue;
         for (int tt = 0; tt < g.kw; ++tt) {
           const int wn = wi + g.pw - tt;
-          if (wn < 0 || wn % g.sw != 0) continue;
-          const int wo = wn / g.sw;
-          if (wo >= g.Wo) continue;
-          const long long m = ((long long)n * g.Ho + ho) * g.Wo + wo;
-          const float4 d = sc_dz(dy, y, m * SC_CO + 4 * q, g.leaky);
-          const float* wp = sw_ + ((s * g.kw + tt) * CIN) * SC_CO + 4 * q;
+          if (wn < 0) continue;
+          int wo = wn;
+          if (g.sw != 1) {                       // strided conv (DiscriminatorP): only every sw-th tap lands on an output
+            if (wn % g.sw != 0) continue;
+            wo = wn / g.sw;
+          }
+          if (wo > wo_hi) continue;
+          const float4 d = *reinterpret_cast<const float4*>(s_dz + (ss * SCD_COLS + wo - wo_lo) * SC_CO + 4 * q);
+          const float* wp = sw_ + ((ss * g.kw + tt) * CIN) * SC_CO + 4 * q;
 #pragma unroll
           for (int ci = 0; ci < CIN; ++ci) {
             const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * SC_CO);
@@ -355,7 +450,7 @@ F2G_KERNEL void conv_small_dgrad_kernel(const float* __restrict__ dy, const floa
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (q == 0 && p < P) dx[p * CIN + ci] = v;
+      if (q == 0 && wi < g.W) dx[(row * g.W + wi) * CIN + ci] = v;
     }
   }
 }
@@ -426,44 +521,64 @@ static int sc_fill(SmallConv& g, int Nb, int H, int W, long long pitch_n, long l
   return 0;
 }
 
-static int sc_grid(long long pixels) {
-  long long b = (pixels + SC_THREADS / 8 - 1) / (SC_THREADS / 8);
-  const long long cap = 148LL * 16;
-  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
-}
-
 extern "C" int f2g_conv_small_fwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
                                   long long pitch_w, const float* w, const float* bias, int Co, int kh, int kw,
                                   int sh, int sw, int ph, int pw, float leaky, float* y, void* stream) {
   SmallConv g;
   if (int rc = sc_fill(g, Nb, H, W, pitch_n, pitch_h, pitch_w, kh, kw, sh, sw, ph, pw, Cin, Co, leaky, "f2g_conv_small_fwd"))
     return rc;
-  const int grid = sc_grid((long long)Nb * g.Ho * g.Wo);
-  if (Cin == 1) F2G_LAUNCH_COOP(conv_small_fwd_kernel<1>, grid, SC_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y);
-  else F2G_LAUNCH_COOP(conv_small_fwd_kernel<2>, grid, SC_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y);
+  if (kh > 3 || sw > 3 || kw > 9) {
+    set_error("f2g_conv_small_fwd: needs kh <= 3, kw <= 9, sw <= 3 (kh=%d kw=%d sw=%d)", kh, kw, sw);
+    return F2G_EINVAL;
+  }
+  const int tiles_per_row = (g.Wo + SCW_TILE - 1) / SCW_TILE;
+  const long long n_tiles = (long long)Nb * g.Ho * tiles_per_row;
+  const int grid = (int)(n_tiles < 148 * 32 ? n_tiles : 148 * 32);
+  if (Cin == 1)
+    F2G_LAUNCH_COOP(conv_small_fwd_kernel<1>, grid, SCF_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y, tiles_per_row, n_tiles);
+  else
+    F2G_LAUNCH_COOP(conv_small_fwd_kernel<2>, grid, SCF_THREADS, static_cast<cudaStream_t>(stream), x, w, bias, g, y, tiles_per_row, n_tiles);
   return check_launch("f2g_conv_small_fwd");
 }
 
 extern "C" int f2g_conv_small_bwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
                                   long long pitch_w, const float* w, int Co, int kh, int kw, int sh, int sw, int ph,
                                   int pw, float leaky, const float* dy, const float* y, float* gw_packed, float* gb,
-                                  float* dx, void* stream_) {
+                                  float* dx, float* scratch, long long scratch_floats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SmallConv g;
   if (int rc = sc_fill(g, Nb, H, W, pitch_n, pitch_h, pitch_w, kh, kw, sh, sw, ph, pw, Cin, Co, leaky, "f2g_conv_small_bwd"))
     return rc;
-  if (gw_packed) {        // caller zeroed gw_packed (kh*kw*Cin x 32) and gb (32)
-    const long long M = (long long)Nb * g.Ho * g.Wo;
-    long long blocks = M / 512;                        // >= 512 pixels per block: few atomics, long FMA runs
-    blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-    if (Cin == 1) F2G_LAUNCH_COOP(conv_small_wgrad_kernel<1>, (int)blocks, SC_THREADS, stream, x, dy, y, g, gw_packed, gb);
-    else F2G_LAUNCH_COOP(conv_small_wgrad_kernel<2>, (int)blocks, SC_THREADS, stream, x, dy, y, g, gw_packed, gb);
+  if (gw_packed) {        // caller zeroed gw_packed (kh*kw*Cin x 32) and gb (32); scratch: see the header
+    const int K = kh * kw * Cin, n_vals = K * SC_CO + SC_CO;
+    if (kh > 3 || sw > 3 || kw > 9 || !scratch || scratch_floats < (long long)n_vals) {
+      set_error("f2g_conv_small_bwd: weight gradient needs kh <= 3, sw <= 3, kw <= 9 and a scratch buffer of >= %d floats",
+                n_vals);
+      return F2G_EINVAL;
+    }
+    const int tiles_per_row = (g.Wo + SCW_TILE - 1) / SCW_TILE;
+    const long long n_tiles = (long long)Nb * g.Ho * tiles_per_row;
+    long long blocks = n_tiles < 148 * 8 ? n_tiles : 148 * 8;
+    if (blocks > scratch_floats / n_vals) blocks = scratch_floats / n_vals;
+    if (Cin == 1)
+      F2G_LAUNCH_COOP(conv_small_wgrad_kernel<1>, (int)blocks, SCW_THREADS, stream, x, dy, y, g, scratch, tiles_per_row, n_tiles);
+    else
+      F2G_LAUNCH_COOP(conv_small_wgrad_kernel<2>, (int)blocks, SCW_THREADS, stream, x, dy, y, g, scratch, tiles_per_row, n_tiles);
     if (int rc = check_launch("f2g_conv_small_bwd(wgrad)")) return rc;
+    F2G_LAUNCH_COOP(conv_small_wgrad_reduce_kernel, (n_vals + 31) / 32, 256, stream, scratch, (int)blocks, n_vals, gw_packed,
+                    gb, K * SC_CO);
+    if (int rc = check_launch("f2g_conv_small_bwd(wgrad reduce)")) return rc;
   }
   if (dx) {
-    const int grid = sc_grid((long long)Nb * H * W);
-    if (Cin == 1) F2G_LAUNCH_COOP(conv_small_dgrad_kernel<1>, grid, SC_THREADS, stream, dy, y, w, g, dx);
-    else F2G_LAUNCH_COOP(conv_small_dgrad_kernel<2>, grid, SC_THREADS, stream, dy, y, w, g, dx);
+    if (kh > 3 || kw > 9) {
+      set_error("f2g_conv_small_bwd: input gradient needs kh <= 3, kw <= 9 (kh=%d kw=%d)", kh, kw);
+      return F2G_EINVAL;
+    }
+    const int tiles_per_row = (W + SCW_TILE - 1) / SCW_TILE;
+    const long long n_tiles = (long long)Nb * H * tiles_per_row;
+    const int grid = (int)(n_tiles < 148 * 16 ? n_tiles : 148 * 16);
+    if (Cin == 1) F2G_LAUNCH_COOP(conv_small_dgrad_kernel<1>, grid, SC_THREADS, stream, dy, y, w, g, dx, tiles_per_row, n_tiles);
+    else F2G_LAUNCH_COOP(conv_small_dgrad_kernel<2>, grid, SC_THREADS, stream, dy, y, w, g, dx, tiles_per_row, n_tiles);
     if (int rc = check_launch("f2g_conv_small_bwd(dgrad)")) return rc;
   }
   return F2G_OK;

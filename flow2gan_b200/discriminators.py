@@ -119,15 +119,19 @@ class _ConvSmallFn(torch.autograd.Function):
         gwp = acc[:K * Co] if need_w else None
         gbv = acc[K * Co:] if need_w else None
         dx = torch.empty(Nb, H, W, Cin, device=dy.device, dtype=torch.float32) if need_x else None
-        L.conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gwp, gbv, dx)
+        scratch = None
+        if need_w:       # one partial record per block of the weight-gradient kernel (deterministic reduction)
+            tiles = Nb * Ho * ((Wo + 31) // 32)
+            scratch = torch.empty(min(tiles, 148 * 8) * (K * Co + Co), device=dy.device, dtype=torch.float32)
+        L.conv_small_bwd(x, Nb, H, W, Cin, pitches, w, Co, kh, kw, sh, sw, ph, pw, leaky, dy, y, gwp, gbv, dx, scratch)
         gW = gwp.view(kh, kw, Cin, Co).permute(3, 2, 0, 1).contiguous() if ctx.needs_input_grad[1] else None
         gb = gbv if ctx.needs_input_grad[2] else None
         return dx, gW, gb, None, None, None, None, None
 
 
-def _small_ok(x: Tensor, w: Tensor) -> bool:
-    return (x.shape[3] in (1, 2) and w.shape[0] == 32 and w.shape[2] * w.shape[3] * x.shape[3] <= 64
-            and x.stride(3) == 1 and x.dtype == torch.float32)
+def _small_ok(x: Tensor, w: Tensor, sw: int = 1) -> bool:
+    return (x.shape[3] in (1, 2) and w.shape[0] == 32 and w.shape[2] * w.shape[3] * x.shape[3] <= 56
+            and w.shape[2] <= 3 and w.shape[3] <= 9 and sw <= 3 and x.stride(3) == 1 and x.dtype == torch.float32)
 
 
 def _pack_cache(conv: nn.Conv2d, weight: Tensor, key: str) -> dict:
@@ -159,7 +163,7 @@ def conv2d_cl(x: Tensor, conv: nn.Conv2d, leaky: Optional[float], train_weights:
         sh, sw, ph, pw = sw, sh, pw, ph
     if _USE_WINDOWED and convwin.supports(x.shape[3], w.shape[2], w.shape[3], sh, sw):
         return convwin.conv2d_win(x, w, b, sw, ph, pw, leaky, _pack_cache(conv, w, "win%d" % swap_hw))
-    if _USE_WINDOWED and _small_ok(x, w):          # first layers (Cin = 1 / 2): direct convolution, no im2col
+    if _USE_WINDOWED and _small_ok(x, w, sw):      # first layers (Cin = 1 / 2): direct convolution, no im2col
         return _ConvSmallFn.apply(x, w, b, sh, sw, ph, pw, leaky)
     return _Conv2dCLFn.apply(x, w, b, sh, sw, ph, pw, leaky, _pack_cache(conv, w, "col%d" % swap_hw))
 

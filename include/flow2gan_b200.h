@@ -321,14 +321,15 @@ int f2g_spec_loss_bwd(const float* audio, int B, int T, int ld_audio, int n_fft,
  * w, bias: the parameter tensors (Co, Cin, kh, kw) / (Co); y: (Nb*Ho*Wo, 32) contiguous; leaky < 0: no
  * activation.  bwd: dy / y contiguous (rows, 32); gw_packed (kh*kw*Cin, 32) [k = (s*kw + t)*Cin + ci][co] and
  * gb (32) are ACCUMULATED into (zero them first; NULL gw_packed: no weight gradient); dx (Nb, H, W, Cin)
- * contiguous or NULL. */
+ * contiguous or NULL.  The weight gradient is reduced without atomics (bit-reproducible): `scratch` receives one
+ * partial record of kh*kw*Cin*32 + 32 floats per block (as many blocks as fit, <= 2368). */
 int f2g_conv_small_fwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
                        long long pitch_w, const float* w, const float* bias, int Co, int kh, int kw, int sh, int sw,
                        int ph, int pw, float leaky, float* y, void* stream);
 int f2g_conv_small_bwd(const float* x, int Nb, int H, int W, int Cin, long long pitch_n, long long pitch_h,
                        long long pitch_w, const float* w, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
                        float leaky, const float* dy, const float* y, float* gw_packed, float* gb, float* dx,
-                       void* stream);
+                       float* scratch, long long scratch_floats, void* stream);
 
 /* out[c] += sum_r x[r*ld + c]  (bias gradients). */
 int f2g_colsum(const float* x, int ld, int rows, int cols, float* out, void* stream);
