@@ -79,8 +79,8 @@ typedef struct F2GGemm {
   int a_seg_len, a_seg_shift, a_rows;
   /* Half-width operands (tcgen05 kind::f16, fp32 accumulate).  IEEE fp16 carries the same 11-bit
    * significand as TF32, so for operands inside the fp16 range the products are the ones the TF32
-   * path forms -- at half the bytes through the L2->SM fabric (which bounds this kernel) and
-   * twice the tensor issue rate.  ab_f16 = 1: a and b point to fp16 (__half) matrices, K-major
+   * path forms -- at half the operand bytes through shared memory and twice the tensor issue rate
+   * (measured: both operand types sit at the same distance from the fp32 oracle).  ab_f16 = 1: a and b point to fp16 (__half) matrices, K-major
    * only (a_mn = b_mn = 0), lda / ldb in ELEMENTS (multiples of 8), 16 B-aligned pointers.
    * c_f16 = 1: C is stored as fp16 (round-to-nearest, clamped to +-65504), ldc in elements
    * (multiple of 8); needs a bias+activation or bias-only epilogue (no res / gate / accumulate /

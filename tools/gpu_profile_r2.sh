@@ -11,7 +11,7 @@ timeout 1200 $N --metrics gpu__time_duration.sum --cache-control none --csv --lo
 timeout 900 $N --set full --import-source on -k regex:gemm_ -c 20 -f -o gpurun_out/prof_gemm_step python tools/one_step.py > gpurun_out/ncu_full.log 2>&1
 timeout 900 $N --set full -k regex:"block_pre|stft_group_warp|irfft_group_warp|ola_combine|biasnorm|linear_small|im2col_cf" -c 24 -f -o gpurun_out/prof_hbm_step python tools/one_step.py > gpurun_out/ncu_hbm1.log 2>&1
 # (3) --set full: HBM-bound kernels of the train pair, two launches each
-for k in act_bwd_win act_bwd_vec adam_update adam_reduce block_bwd_c block_bwd_a pad2d im2col2d spec_loss_bwd stft_kernel loss_terms_fwd loss_terms_bwd conv_w_pack; do
+for k in act_bwd_win act_bwd_vec adam_update adam_reduce block_bwd_c block_bwd_a pad2d conv_small_fwd conv_small_wgrad_kernel conv_small_dgrad spec_loss_bwd stft_kernel loss_terms_fwd loss_terms_bwd; do
   timeout 600 $N --set full -k regex:$k -c 2 -f -o gpurun_out/prof_hbm_train_$k python tools/one_train_pair.py > gpurun_out/ncu_hbm_$k.log 2>&1
 done
 # (4) data-path / model-average kernels
