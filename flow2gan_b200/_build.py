@@ -16,6 +16,8 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("F2G_EPI_WARPS"):                  # experiment: epilogue warps per CTA of the CTA-pair GEMM (8 / 16)
+    NVCC_FLAGS.append("-DF2G_EPI_WARPS=" + os.environ["F2G_EPI_WARPS"])
 if os.environ.get("F2G_BRINGUP", "0") == "1":       # tools/ only: timing-experiment knobs read the environment
     NVCC_FLAGS.append("-DF2G_BRINGUP")
 

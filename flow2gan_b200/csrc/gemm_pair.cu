@@ -26,8 +26,15 @@ constexpr int PBM = 128;                       // rows per CTA (pair tile = 256 
 constexpr int PBK = 32;                        // 32 fp32 = one 128 B swizzle row
 constexpr int P_A_BYTES = PBM * PBK * 4;       // 16 KB
 constexpr int P_STAGE_BYTES = 2 * P_A_BYTES;   // A + up to 128 B-tile rows
-constexpr int P_STAGES = 5;
-constexpr int P_EPI_WARPS = 8;
+// -DF2G_EPI_WARPS=16 (with F2G_EPI_WARPS=16 python -m flow2gan_b200._build --force) builds a 20-warp CTA with four
+// epilogue warps per scheduler (96 registers, 4 stages).  Measured round 2: identical launch and per-tile times --
+// the epilogue is not limited by per-warp latency either (profiles/r02_gemm_probes.md).  Default 8.
+#ifndef F2G_EPI_WARPS
+#define F2G_EPI_WARPS 8
+#endif
+constexpr int P_STAGES = F2G_EPI_WARPS > 8 ? 4 : 5;      // 16 epilogue warps need 74 KB of transpose scratch
+constexpr int P_EPI_WARPS = F2G_EPI_WARPS;               // multiple of 4: one warp per TMEM lane quarter and column group
+constexpr int P_EPI_GROUPS = P_EPI_WARPS / 4;
 // TMA producer warps: warp 0 plus P_PROD_WARPS - 1 warps behind the epilogue warps.  One elected thread
 // needs ~270 cycles per (wait, expect_tx, cp.async.bulk) round (tools/tma_rate_probe.cu: 0.137 us per
 // copy per issuing warp, independent of the copy size up to 16 KB, scaling linearly with the number of
@@ -488,7 +495,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     // warp instruction covers four full 128 B row segments.
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int half = ew >> 2;                    // column group: chunks half, half + P_EPI_GROUPS, ...
     float* const scratch = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES) + ew * (32 * 36);
     float* const sparam0 = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES);
     const int cg = lane & 7, rsub = lane >> 3;
@@ -523,7 +530,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     if (my_tiles > 0) {
       tc = pdecode(g, tile_at(0));
       stage_params(tc, sparam0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
     }
     for (int ti = 0; ti < my_tiles; ++ti) {
       const PProblem& pr = g.p[tc.prob];
@@ -567,7 +574,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       F2G_PROF(2);
       uint32_t sat_acc = 0;    // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag; common.cuh)
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      for (int c0 = half * 32; c0 < BN; c0 += 32 * P_EPI_GROUPS) {
         if (n0 + c0 >= N || (g.dbg & 2)) break;
         // (issuing the next chunk's tcgen05.ld here, before this chunk's LDS / math / stores, was measured:
         // no change -- the TMEM read is not what the epilogue waits for; profiles/r02_gemm_probes.md)
@@ -723,7 +730,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
       // one barrier per tile: the next tile's staged parameters become visible, this tile's buffer half
       // may be refilled (by the tile after next), and all 256 threads' stores precede the publish below
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
       if (et == 0 && done_p) {
         __threadfence();
         atomicAdd(done_p + done_idx, 1);

@@ -16,5 +16,12 @@ for k in act_bwd_win act_bwd_vec adam_update adam_reduce block_bwd_c block_bwd_a
 done
 # (4) data-path / model-average kernels
 timeout 600 $N --set full -k regex:"average_update|gain_resample|pcm16_encode" -c 4 -f -o gpurun_out/prof_hbm_datapath python tools/one_datapath.py > gpurun_out/ncu_hbm_dp.log 2>&1
-tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_hbm1.log gpurun_out/ncu_hbm_dp.log
-ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
+# (5) summarise ON THE BOX (only gpurun_out/ comes back, 64 MiB at most): tables + JSON into gpurun_out/profiles_out/,
+#     then drop the raw reports except the GEMM capture (source-level view of the dominant kernel)
+export F2G_PROFILES_OUT=gpurun_out/profiles_out
+python tools/summarize_profiles.py r02 > /dev/null
+python tools/summarize_hbm.py r02 gpurun_out/prof_hbm_step.ncu-rep gpurun_out/prof_hbm_train_*.ncu-rep gpurun_out/prof_hbm_datapath.ncu-rep > /dev/null
+ncu -i gpurun_out/prof_gemm_step.ncu-rep --page source --csv > gpurun_out/profiles_out/r02_gemm_step_source.csv 2>/dev/null
+rm -f gpurun_out/prof_hbm_*.ncu-rep
+for f in gpurun_out/ncu_full.log gpurun_out/ncu_hbm1.log gpurun_out/ncu_hbm_dp.log; do tail -n 2 $f; done
+ls -la gpurun_out/*.ncu-rep gpurun_out/profiles_out | awk '{print $5, $9}'

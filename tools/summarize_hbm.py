@@ -48,7 +48,8 @@ md = [f"# HBM-bound kernels, `ncu --set full --clock-control none`, round {tag}"
 for d in out:
     md.append(f"| `{d['kernel'][:48]}` | {d['grid']} x {d['block']} | {d['us']:.1f} | {d['dram_read_mb']:.2f} | {d['dram_write_mb']:.2f} | "
               f"{d['dram_gbs']:.0f} | {d['frac_of_hbm_peak']:.2f} | {d['l2_pct']:.0f} | {d['warps_active_pct']:.0f} | {d['regs']} | {'; '.join(d['top_stalls'])} |")
-os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-open(os.path.join(ROOT, "profiles", f"{tag}_hbm_kernels.md"), "w").write("\n".join(md) + "\n")
-json.dump(out, open(os.path.join(ROOT, "profiles", f"{tag}_hbm_kernels.json"), "w"), indent=1)
+OUTD = os.environ.get("F2G_PROFILES_OUT", os.path.join(ROOT, "profiles"))
+os.makedirs(OUTD, exist_ok=True)
+open(os.path.join(OUTD, f"{tag}_hbm_kernels.md"), "w").write("\n".join(md) + "\n")
+json.dump(out, open(os.path.join(OUTD, f"{tag}_hbm_kernels.json"), "w"), indent=1)
 print("\n".join(md))

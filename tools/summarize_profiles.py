@@ -3,7 +3,7 @@
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-OUT = os.path.join(ROOT, "profiles"); os.makedirs(OUT, exist_ok=True)
+OUT = os.environ.get("F2G_PROFILES_OUT", os.path.join(ROOT, "profiles")); os.makedirs(OUT, exist_ok=True)
 G = os.path.join(ROOT, "gpurun_out")
 
 def launch_table(path):
@@ -46,7 +46,8 @@ def raw_metrics(rep):
 
 md = [f"# ncu summaries, round {tag}", ""]
 for name, title in (("launches_step.csv", "1-step inference (`tools/one_step.py`, eager, bench shape): every launch, `--metrics gpu__time_duration.sum --clock-control none`"),
-                    ("launches_train.csv", "GAN D+G iteration pair (`tools/one_train_pair.py`, bs 16 x 24000)")):
+                    ("launches_step_warm.csv", "the same step with `--cache-control none` (caches left warm between kernels: closer to the in-graph times)"),
+                    ("launches_train.csv", "GAN D+G iteration pair (`tools/one_train_pair.py`, bs 16 x 24000), `--cache-control none`")):
     p = os.path.join(G, name)
     if os.path.exists(p):
         n, tot, tab = launch_table(p)
