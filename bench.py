@@ -156,18 +156,22 @@ def import_reference():
     return flow2gan
 
 
-def _best_threads(call, candidates=(8, 16, 32)):
+def _best_threads(call, candidates=(8, 12, 16, 24, 32)):
     """The reference's CPU path (mkldnn convs on short sequences) stops scaling well before a big
-    host's core count (measured on the 128-core B200 host: 16 threads 0.40 s/call, 64 threads
-    0.88 s, 128 threads > 20 s) -- give the baseline its best thread count."""
+    host's core count (measured on the 128-core B200 host: 16 threads 0.21-0.27 s per bs-16 call, 8 threads
+    0.40 s, 64 threads 0.88 s, 128 threads > 20 s) -- give the baseline its best thread count, chosen on the
+    full-size call (best of two timed calls per candidate after one warm-up)."""
     ncpu = os.cpu_count() or 1
     best, cores = None, 1
     for th in sorted({min(ncpu, c) for c in candidates}):
         torch.set_num_threads(th)
         call()
-        t0 = time.perf_counter()
-        call()
-        dt = time.perf_counter() - t0
+        dt = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            call()
+            d = time.perf_counter() - t0
+            dt = d if dt is None or d < dt else dt
         if best is None or dt < best:
             best, cores = dt, th
     torch.set_num_threads(cores)
@@ -210,7 +214,7 @@ def cpu_reference_rate(n_timesteps: int, iters: int, warmup: int = 1):
         kind = "port"
     times = []
     with torch.inference_mode():
-        cores = _best_threads(lambda: call(4))
+        cores = _best_threads(call)
         for i in range(warmup + iters):
             t0 = time.perf_counter()
             call()

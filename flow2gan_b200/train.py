@@ -21,7 +21,42 @@ from . import _lib as L
 from .engine import BN_G1, BN_G2, PackedGenerator
 
 
+# Zero-initialised accumulators of one backward call (bias / slope / norm-parameter gradients, split-K
+# weight gradients ...: ~400 small tensors per generator backward) are carved out of ONE zero-filled
+# buffer instead of one fill launch each.  The buffer is allocated per backward call and never reused:
+# gradients that autograd keeps (views of it) stay valid for as long as they are referenced.
+_ARENA = None            # [flat fp32 tensor, next free element] while a backward call is running
+_ARENA_FLOATS = 3 << 20      # 12 MB: one fill of ~2 us instead of ~400 x 1.3 us
+_ARENA_MAX_ITEM = 1 << 18
+
+
+class _zero_arena:
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __enter__(self):
+        global _ARENA
+        self.prev = _ARENA
+        _ARENA = [torch.zeros(_ARENA_FLOATS, device=self.dev, dtype=torch.float32), 0]
+
+    def __exit__(self, *exc):
+        global _ARENA
+        _ARENA = self.prev
+        return False
+
+
 def _z(*shape, dev):
+    if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+        shape = tuple(shape[0])
+    n = 1
+    for d in shape:
+        n *= int(d)
+    a = _ARENA
+    if a is not None and 0 < n <= _ARENA_MAX_ITEM and a[0].device == torch.device(dev):
+        start = (a[1] + 63) & ~63                       # 256-byte aligned slices
+        if start + n <= a[0].numel():
+            a[1] = start + n
+            return a[0][start:start + n].view(tuple(int(d) for d in shape))
     return torch.zeros(*shape, device=dev, dtype=torch.float32)
 
 
@@ -238,6 +273,11 @@ class _CondEncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dc0: Tensor):
+        with _zero_arena(dc0.device):
+            return _CondEncoderFn._backward(ctx, dc0)
+
+    @staticmethod
+    def _backward(ctx, dc0: Tensor):
         model = ctx.model
         pk: PackedGenerator = model._packed
         ce = model.cond_encoder
@@ -341,6 +381,11 @@ class _ProcessModelFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpred: Tensor):
+        with _zero_arena(dpred.device):
+            return _ProcessModelFn._backward(ctx, dpred)
+
+    @staticmethod
+    def _backward(ctx, dpred: Tensor):
         model = ctx.model
         pk: PackedGenerator = model._packed
         c0, brs, emb, wgt, B, T, Fm = ctx.saved
