@@ -73,6 +73,7 @@ struct BlockPreArgs {
 template <int PRE_S, int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __grid_constant__ BlockPreArgs a) {
   __shared__ float red[PRE_MAX_TL * PRE_S][8];
+  __shared__ float4 stage[PRE_S + 2][PRE_THREADS];   // per-thread slots: cond rows, time scale, norm bias
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < 4; ++i)
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   float4 cv[PRE_S];
   float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
   float ssq[PRE_S];
+  float log_scale = 0.f;
 #pragma unroll
   for (int s = 0; s < PRE_S; ++s) {
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,6 +133,27 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
         }
       }
     }
+    // everything the epilogue of this thread needs, as LDGSTS into its own shared-memory slots: in
+    // flight together with the window, no registers held, no second L2 round trip after the taps
+    if (P.cond) {
+      // conditioning row of token t: frame t / factor (factor is 1, 2 or 4 in every released
+      // config: shift), or the all-zero row past the last mel frame
+      const int fsh = a.fshift[pi];
+      const int t_cond = P.cond_T * P.factor;
+      const float* cbase = P.cond + c;
+#pragma unroll
+      for (int s = 0; s < PRE_S; ++s) {
+        const int t = t0 + s;
+        if (t < T) {
+          const int fr = fsh >= 0 ? (t >> fsh) : t / P.factor;
+          const int crow = t < t_cond ? bi * P.cond_T + fr : P.zero_row;
+          cp_async16(&stage[s][threadIdx.x], cbase + (size_t)crow * P.ld_cond);
+        }
+      }
+    }
+    if (P.tscale) cp_async16(&stage[PRE_S][threadIdx.x], P.tscale + (size_t)bi * P.ld_ts + c);
+    cp_async16(&stage[PRE_S + 1][threadIdx.x], P.bn_bias + c);
+    log_scale = *P.bn_log_scale;
     const float4 b0 = ld4(P.dw_b + c);
 #pragma unroll
     for (int s = 0; s < PRE_S; ++s) acc[s] = b0;
@@ -145,25 +168,16 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
         acc[s].w = fmaf(xv[s + k].w, w.w, acc[s].w);
       }
     }
-    // the window registers are dead now: fetch the conditioning rows under the reduction
+    // conditioning rows, time scale and norm bias were requested before the window (below): they
+    // arrived under the window's round trip
+    cp_async_wait_all();
     if (P.cond) {
-      // conditioning row of token t: frame t / factor (factor is 1, 2 or 4 in every released
-      // config: shift), or the all-zero row past the last mel frame
-      const int fsh = a.fshift[pi];
-      const int t_cond = P.cond_T * P.factor;
-      const float* cbase = P.cond + c;
 #pragma unroll
-      for (int s = 0; s < PRE_S; ++s) {
-        const int t = t0 + s;
-        if (t < T) {
-          const int fr = fsh >= 0 ? (t >> fsh) : t / P.factor;
-          const int crow = t < t_cond ? bi * P.cond_T + fr : P.zero_row;
-          cv[s] = ld4(cbase + (size_t)crow * P.ld_cond);
-        }
-      }
+      for (int s = 0; s < PRE_S; ++s)
+        if (t0 + s < T) cv[s] = stage[s][threadIdx.x];
     }
-    if (P.tscale) sc = ld4(P.tscale + (size_t)bi * P.ld_ts + c);
-    const float4 bb = ld4(P.bn_bias + c);
+    if (P.tscale) sc = stage[PRE_S][threadIdx.x];
+    const float4 bb = stage[PRE_S + 1][threadIdx.x];
 #pragma unroll
     for (int s = 0; s < PRE_S; ++s) {
       const float d0 = acc[s].x - bb.x, d1 = acc[s].y - bb.y, d2 = acc[s].z - bb.z, d3 = acc[s].w - bb.w;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) block_pre_kernel(const __gr
   }
   __syncthreads();
   if (!live) return;
-  const float gain = expf(*P.bn_log_scale);
+  const float gain = expf(log_scale);
   const float inv_c = 1.0f / (float)C;
   uint32_t sat_acc = 0;  // fp16 range guard: running per-half maximum of the converted |bits| (common.cuh)
 #pragma unroll
@@ -354,9 +368,8 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
   BlockPreArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n;
-  // sliding-window length per lane / resident CTAs per SM (F2G_PRE_VARIANT: bring-up sweep)
-  static const int variant = bringup_int("F2G_PRE_VARIANT", 0);
-  const int S = variant == 1 ? 2 : (variant == 2 ? 2 : (variant == 3 ? 8 : 4));
+  // sliding-window length per lane 4, two resident CTAs per SM (round-1 sweep: <2,3>, <2,2>, <8,1> lost)
+  const int S = 4;
   int ctas = 0;
   for (int i = 0; i < n; ++i) {
     F2GBlockPre p = probs[i];
@@ -382,9 +395,6 @@ extern "C" int f2g_block_pre_group(const F2GBlockPre* probs, int n, void* stream
   }
   for (int i = n; i <= 4; ++i) a.cta_begin[i] = ctas;
   void (*kern)(BlockPreArgs) = block_pre_kernel<4, 2>;
-  if (variant == 1) kern = block_pre_kernel<2, 3>;
-  if (variant == 2) kern = block_pre_kernel<2, 2>;
-  if (variant == 3) kern = block_pre_kernel<8, 1>;
   cudaError_t le = launch_pdl(kern, dim3(ctas), dim3(PRE_THREADS), 0, static_cast<cudaStream_t>(stream), a);
   if (le != cudaSuccess) {
     set_error("f2g_block_pre launch: %s", cudaGetErrorString(le));

@@ -32,7 +32,7 @@ constexpr int P_STAGE_BYTES = 2 * P_A_BYTES;   // A + up to 128 B-tile rows
 #ifndef F2G_EPI_WARPS
 #define F2G_EPI_WARPS 8
 #endif
-constexpr int P_STAGES = F2G_EPI_WARPS > 8 ? 4 : 5;      // 16 epilogue warps need 74 KB of transpose scratch
+constexpr int P_STAGES = F2G_EPI_WARPS > 8 ? 4 : 5;      // 16 epilogue warps need 80 KB of epilogue scratch
 constexpr int P_EPI_WARPS = F2G_EPI_WARPS;               // multiple of 4: one warp per TMEM lane quarter and column group
 constexpr int P_EPI_GROUPS = P_EPI_WARPS / 4;
 // TMA producer warps: warp 0 plus P_PROD_WARPS - 1 warps behind the epilogue warps.  One elected thread
@@ -44,7 +44,10 @@ constexpr int P_EPI_GROUPS = P_EPI_WARPS / 4;
 constexpr int P_PROD_WARPS = 3;       // 12 warps per CTA: register allocation is per 4 warps (13 warps cost the budget of 16)
 constexpr int P_FIRST_EXTRA_PROD = 2 + P_EPI_WARPS;            // warp index of producer 1
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS + 32 * (P_PROD_WARPS - 1);
-constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 36 * 4;
+// per epilogue warp: a 32 x 36 fp32 transpose pad (4608 B) or one 32-row x 128 B swizzled fp16 box for a TMA store
+// (4096 B, 1024 B aligned: SWIZZLE_128B keys on address bits 7..9)
+constexpr int P_SCRATCH_WARP_BYTES = 5120;
+constexpr int P_SCRATCH_BYTES = P_EPI_WARPS * P_SCRATCH_WARP_BYTES;
 constexpr int P_PARAM_BYTES = 2 * 3 * 256 * 4;     // bias / slope / residual-scale of a tile's columns, two tiles (double buffer)
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES + P_PARAM_BYTES;
 constexpr int P_TMEM_COLS = 512;
@@ -54,6 +57,7 @@ constexpr int P_MAX_PAIRS = 78;
 struct alignas(64) PProblem {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_c;        // fp16 destination as 64-column x 32-row store boxes (tma_c)
   float* c;
   float* c_pre;
   const float* bias;
@@ -74,6 +78,7 @@ struct alignas(64) PProblem {
   const int* wait;
   int wait_count;
   int* sat_flag;            // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag)
+  int tma_c;                // bias+activation -> fp16 tiles leave through TMA stores (epilogue below)
 };
 
 struct alignas(64) PGroup {
@@ -86,7 +91,7 @@ struct alignas(64) PGroup {
   // group idle.  use_sched == 0: plain round-robin (tile = pair + i * npairs).
   int use_sched;
   uint16_t pair_off[P_MAX_PAIRS + 2];
-  uint16_t sched[P_MAX_SCHED];
+  uint32_t sched[P_MAX_SCHED];   // host-decoded tiles: problem (3 bits) | K split (9) | row tile (10) | column tile (10)
   int dbg;   // bring-up (F2G_PAIR_DBG): bit0 = epilogue drains TMEM but stores nothing,
              // bit1 = epilogue skips TMEM loads too
   int* watchdog;   // mapped pinned host ints {flag, problem, row tile, counter seen} or nullptr
@@ -118,6 +123,23 @@ F2G_DEVINL PTile pdecode(const PGroup& g, int tile) {
   t.kb0 = ks * g.p[pi].kb_per;
   t.kb1 = min(t.kb0 + g.p[pi].kb_per, g.p[pi].kb_total);
   return t;
+}
+
+// A scheduled tile, decoded on the host (build_schedule): the in-kernel decode above -- a search over the
+// problems and three integer divisions -- was ~600 cycles per tile on the epilogue warps' critical path.
+F2G_DEVINL PTile pdecode_packed(const PGroup& g, uint32_t e) {
+  PTile t;
+  t.prob = (int)(e & 7u);
+  const PProblem& p = g.p[t.prob];
+  const int ks = (int)((e >> 3) & 511u);
+  t.m0 = (int)((e >> 12) & 1023u) * (2 * PBM);
+  t.n0 = (int)(e >> 22) * p.bn;
+  t.kb0 = ks * p.kb_per;
+  t.kb1 = min(t.kb0 + p.kb_per, p.kb_total);
+  return t;
+}
+F2G_DEVINL PTile ptile(const PGroup& g, int s_off, int ti, int pair, int npairs) {
+  return g.use_sched ? pdecode_packed(g, g.sched[s_off + ti]) : pdecode(g, pair + ti * npairs);
 }
 
 // ------------------------------- cluster / cta_group::2 PTX ---------------------------------
@@ -200,6 +222,37 @@ F2G_DEVINL void umma_commit_cg2(uint64_t* bar) {
 #define F2G_PROF_DECL do { } while (0)
 #define F2G_PROF(slot) do { } while (0)
 #endif
+
+// TMA store of one shared-memory box (bulk async-group completion), and the waits on this thread's groups:
+// .read = the source buffers may be overwritten; plain = the global writes are complete.
+F2G_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+F2G_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+F2G_DEVINL void tma_store_wait_done() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// non-blocking phase test (try_wait may suspend the thread for a system-dependent time before it says no)
+F2G_DEVINL bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+F2G_DEVINL void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+F2G_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+F2G_DEVINL void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 enum { PEPI_GENERIC = 0, PEPI_BIAS_ACT = 1, PEPI_BIAS_RES = 2, PEPI_PLAIN = 3, PEPI_MLP = 4 };
 
@@ -330,6 +383,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     for (int i = 0; i < g.n_problems; ++i) {
       tma_prefetch_desc(&g.p[i].map_a);
       tma_prefetch_desc(&g.p[i].map_b);
+      if (g.p[i].tma_c) tma_prefetch_desc(&g.p[i].map_c);
     }
     for (int s = 0; s < P_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -363,8 +417,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
-        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
-        const PTile tc = pdecode(g, tile);
+        const PTile tc = ptile(g, s_off, ti, pair, npairs);
         const PProblem& pr = g.p[tc.prob];
         const int bhalf = pr.bn >> 1;
         const int m_cta = tc.m0 + (int)rank * PBM;
@@ -458,8 +511,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       int ab = 0;
       uint32_t ab_phase = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
-        const int tile = g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs;
-        const PTile tc = pdecode(g, tile);
+        const PTile tc = ptile(g, s_off, ti, pair, npairs);
         const uint32_t idesc = F16 ? make_idesc_f16(2 * PBM, g.p[tc.prob].bn)
                                    : make_idesc_tf32(2 * PBM, g.p[tc.prob].bn, A_MN, B_MN);
         mbar_wait(&tmem_empty_bar[ab], ab_phase ^ 1);
@@ -496,7 +548,7 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int half = ew >> 2;                    // column group: chunks half, half + P_EPI_GROUPS, ...
-    float* const scratch = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES) + ew * (32 * 36);
+    float* const scratch = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + ew * P_SCRATCH_WARP_BYTES);
     float* const sparam0 = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + P_SCRATCH_BYTES);
     const int cg = lane & 7, rsub = lane >> 3;
     const int et = ew * 32 + lane;
@@ -510,7 +562,9 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     // accumulator, 15 % of an epilogue-bound tile): tile i+1 is decoded and its bias / slope /
     // residual-scale columns are fetched into the other half of the parameter buffer while tile i's
     // accumulator is still being produced; the barrier that ends tile i publishes them.
-    auto tile_at = [&](int ti) { return g.use_sched ? (int)g.sched[s_off + ti] : pair + ti * npairs; };
+    // the columns are fetched with 4-byte LDGSTS: the warp does not wait for them (measured: the plain
+    // load -> STS version cost ~900 cycles per tile on the epilogue's critical path); complete before the
+    // barrier that publishes the buffer (cp_async_wait_all below)
     auto stage_params = [&](const PTile& t, float* sp) {
       const PProblem& p = g.p[t.prob];
       const float* const bias_p = p.bias;
@@ -521,15 +575,51 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       for (int c = et; c < bn; c += 32 * P_EPI_WARPS) {
         const int colc = t.n0 + c;
         const bool okc = colc < nn;
-        sp[c] = (bias_p && okc) ? __ldg(bias_p + colc) : 0.f;
-        sp[256 + c] = (slope_p && okc) ? __ldg(slope_p + colc) : leaky;
-        sp[512 + c] = (rsc_p && okc) ? __ldg(rsc_p + colc) : 1.f;
+        if (bias_p && okc) cp_async4(sp + c, bias_p + colc); else sp[c] = 0.f;
+        if (slope_p && okc) cp_async4(sp + 256 + c, slope_p + colc); else sp[256 + c] = leaky;
+        if (rsc_p && okc) cp_async4(sp + 512 + c, rsc_p + colc); else sp[512 + c] = 1.f;
+      }
+    };
+    // TMA-store epilogue (PProblem::tma_c) state of this warp: lane 0 owns the bulk async-groups of the warp's
+    // stores.  `stg_busy`: a store may still be reading the staging box; `pend_done`: counter of a finished
+    // producer tile whose publish waits for the completion of its stores -- deferred so that nobody stalls on
+    // the write latency, but never past a point where this CTA could block on its own consumers (below).
+    int* pend_done = nullptr;
+    bool stg_busy = false;
+    // publish the pending tile once its stores are complete, allowing the `keep` most recent groups (this
+    // tile's own boxes) to stay in flight: the completion of a TMA store takes ~1.4 us (measured: waiting for
+    // it right after the tile cost 2700 cycles per tile), so a producer tile is published one tile late --
+    // or at once when this CTA is about to idle or to depend on it
+    auto publish = [&](int keep) {
+      if (lane == 0) {
+        if (keep >= 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+        else if (keep == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+        else tma_store_wait_done();
+        F2G_PROF(6);
+        // the completed stores are in L2, the point of coherence of every reader of this launch (TMA loads of
+        // the consumer tiles, after ld.acquire.gpu + fence.proxy.async): a relaxed L2 atomic behind the
+        // completion orders the publish after the data.  (A release fence here -- MEMBAR.ALL.GPU -- also
+        // waited for this tile's in-flight stores: +1400 cycles per tile.)
+        if (g.dbg & 32) { fence_proxy_async_all(); __threadfence(); }
+        atomicAdd(pend_done, 1);
+      }
+      pend_done = nullptr;
+      if (keep == 0) stg_busy = false;
+      __syncwarp();
+    };
+    auto store_sync = [&]() {              // everything of this warp retired: nothing pending, staging box free
+      if (pend_done) publish(0);
+      else if (stg_busy) {
+        if (lane == 0) tma_store_wait_read();
+        stg_busy = false;
+        __syncwarp();
       }
     };
     PTile tc = {0, 0, 0, 0, 0};
     if (my_tiles > 0) {
-      tc = pdecode(g, tile_at(0));
+      tc = ptile(g, s_off, 0, pair, npairs);
       stage_params(tc, sparam0);
+      cp_async_wait_all();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
     }
     for (int ti = 0; ti < my_tiles; ++ti) {
@@ -564,15 +654,91 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       // the next tile's decode + parameter columns, under this tile's main loop
       PTile tn = tc;
       if (ti + 1 < my_tiles) {
-        tn = pdecode(g, tile_at(ti + 1));
+        tn = ptile(g, s_off, ti + 1, pair, npairs);
         stage_params(tn, sparam0 + ((ti + 1) & 1) * 768);
       }
       F2G_PROF(1);
 
+      // TMA-store path: per problem -- except for the last such tile before this pair turns to tiles that may
+      // wait for it (or runs out of tiles): a TMA store completes ~1.4 us after its issue, plain stores behind
+      // a fence are visible in a third of that, and at the phase boundary of a chained launch that latency is
+      // MMA idle time (measured: 34 us of chain waits per inference step against 18 us)
+      const bool tma_c = F16 && (EPI == PEPI_BIAS_ACT || EPI == PEPI_MLP) && pr.tma_c != 0 &&
+                         (done_p == nullptr || (ti + 1 < my_tiles && g.p[tn.prob].tma_c != 0));
+      // a pending publish must not wait behind an accumulator that may itself be waiting for it (a consumer
+      // tile of this launch whose A rows this CTA produced): if the accumulator is not ready yet, publish now
+      if (pend_done && !mbar_test(&tmem_full_bar[ab], ab_phase)) store_sync();
       mbar_wait(&tmem_full_bar[ab], ab_phase);
       tc_fence_after();
       F2G_PROF(2);
       uint32_t sat_acc = 0;    // fp16 range guard of a c_f16 destination (F2GGemm::sat_flag; common.cuh)
+      bool released = false;   // TMEM buffer already handed back (store path: after the last tcgen05.ld)
+      int boxes = 0;           // store groups this warp commits in this tile (rows <= 0: none, the count is unused)
+      if (!tma_c && (pend_done || stg_busy)) store_sync();
+      if (tma_c) {
+        // bias + PReLU -> fp16 tile through TMA stores.  The SM's shared-memory pipe is what short-K tiles are
+        // bound by (the operand ring alone uses ~80 % of it, profiles/r02_gemm_probes.md): this path moves
+        // 2 + 2 bytes per output through it (fp16 staging write + the store engine's read) instead of
+        // 4 + 4 (fp32 transpose) + 2 (STG), and needs no transpose at all: lane = row, the thread converts
+        // its 64 columns in registers (column parameters as broadcast LDS.128) and writes its 128 B row
+        // of a SWIZZLE_128B box; lane 0 issues one 32-row x 64-column store per box.
+        const uint32_t stg = smem_u32(scratch);
+        const uint32_t row_addr = stg + (uint32_t)lane * 128u;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * 256;
+        const int ncols = min(BN, N - n0);
+        boxes = 0;
+#pragma unroll 1
+        for (int cb = half * 64; cb < ncols; cb += 64 * P_EPI_GROUPS) {
+          if (g.dbg & 2) break;
+          uint32_t hw[32];
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t v[32];
+            tmem_ld_32x32(trow + cb + 32 * hc, v);
+            tmem_ld_wait();
+            if (hc == 1 && cb + 64 * P_EPI_GROUPS >= ncols) {
+              // that was this warp's last read of the accumulator: hand the TMEM buffer back to the MMA
+              // issuer now, not after the math / staging / store of this box and the tile-end barrier
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
+              released = true;
+            }
+            const float* sp = sparam + cb + 32 * hc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = lds_f4(sp + 4 * j);
+              const float4 s4 = lds_f4(sp + 256 + 4 * j);
+              float4 x;
+              x.x = fmaf(__uint_as_float(v[4 * j]), alpha, b4.x); x.y = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b4.y);
+              x.z = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b4.z); x.w = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b4.w);
+              x.x = x.x > 0.f ? x.x : x.x * s4.x; x.y = x.y > 0.f ? x.y : x.y * s4.y;      // NaN propagates
+              x.z = x.z > 0.f ? x.z : x.z * s4.z; x.w = x.w > 0.f ? x.w : x.w * s4.w;
+              const uint2 w2 = pack_half4(x);
+              hw[16 * hc + 2 * j] = w2.x;
+              hw[16 * hc + 2 * j + 1] = w2.y;
+              sat_acc = half2_track(half2_track(sat_acc, w2.x), w2.y);
+            }
+          }
+          F2G_PROF(3);
+          if (g.dbg & 1) continue;
+          // the previous tile's stores were issued a decode, an accumulator wait and a box of math ago
+          // (>= 1.5 us): publish it here rather than at the end of this tile (a tile later is late enough to
+          // hold up consumers on other pairs); otherwise only the engine's read of the previous box matters
+          if (pend_done || stg_busy) store_sync();
+          F2G_PROF(4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            sts_u4(row_addr + ((((uint32_t)i) ^ swz) << 4), hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows > 0) tma_store_2d(&pr.map_c, stg, n0 + cb, row_base);
+          stg_busy = true;
+          ++boxes;
+          F2G_PROF(5);
+        }
+      } else
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 32 * P_EPI_GROUPS) {
         if (n0 + c0 >= N || (g.dbg & 2)) break;
@@ -725,21 +891,28 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
       }
       F2G_PROF(6);
       if (F16 && sat_p && half2_out_of_range(sat_acc)) atomicOr(sat_p, 1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ab ? lead_empty1 : lead_empty0);
+      }
+      cp_async_wait_all();
       // one barrier per tile: the next tile's staged parameters become visible, this tile's buffer half
       // may be refilled (by the tile after next), and all 256 threads' stores precede the publish below
       asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");
-      if (et == 0 && done_p) {
+      if (tma_c) {               // every warp publishes its own rows once its stores have completed
+        if (pend_done) publish(rows > 0 ? boxes : 0);
+        pend_done = done_p ? done_p + done_idx : nullptr;
+      } else if (et == 0 && done_p) {
         __threadfence();
-        atomicAdd(done_p + done_idx, 1);
+        atomicAdd(done_p + done_idx, pr.tma_c ? P_EPI_WARPS : 1);     // store-path problems count warps
       }
       ab ^= 1;
       if (ab == 0) ab_phase ^= 1;
       tc = tn;
       F2G_PROF(7);
     }
+    if (pend_done || stg_busy) store_sync();   // shared memory must outlive the store engine's reads
 #ifdef F2G_BRINGUP
     if ((g.dbg & 16) && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 5))
       printf("epi prof warp %d tiles %d cycles: decode %lld params+bar %lld wait_mma %lld ldtm %lld sts+lds_params %lld "
@@ -835,7 +1008,7 @@ static int pick_bn(int N, bool b_mn) {
 static void build_schedule(PGroup& g, int pairs) {
   g.use_sched = 0;
   const int T = g.total_tiles;
-  if (T > P_MAX_SCHED || pairs > P_MAX_PAIRS || T <= pairs) return;
+  if (T > P_MAX_SCHED || pairs > P_MAX_PAIRS) return;
   static thread_local int cost[P_MAX_SCHED];
   static thread_local uint16_t order[P_MAX_SCHED];
   // tiles are laid out problem by problem (problems already sorted by decreasing K), every tile
@@ -855,7 +1028,7 @@ static void build_schedule(PGroup& g, int pairs) {
       ++n;
     }
   }
-  if (cost[0] == cost[n - 1] && sorted) return;   // homogeneous tiles: round-robin is already optimal
+  const bool round_robin = (cost[0] == cost[n - 1] && sorted) || T <= pairs;   // homogeneous tiles / one wave
   if (!sorted) {
     for (int i = 1; i < n; ++i) {          // insertion sort by cost (few distinct values, mostly sorted)
       const uint16_t o = order[i];
@@ -870,6 +1043,11 @@ static void build_schedule(PGroup& g, int pairs) {
   int count[P_MAX_PAIRS];
   for (int i = 0; i < pairs; ++i) { load[i] = 0; heap[i] = i; count[i] = 0; }
   for (int i = 0; i < n; ++i) {
+    if (round_robin) {
+      owner[i] = (uint16_t)(i % pairs);
+      ++count[i % pairs];
+      continue;
+    }
     const int p = heap[0];                // least-loaded pair (ties: lowest index first)
     owner[i] = (uint16_t)p;
     load[p] += cost[order[i]] & ((1 << 24) - 1);
@@ -888,7 +1066,20 @@ static void build_schedule(PGroup& g, int pairs) {
   int start[P_MAX_PAIRS];
   for (int i = 0; i < pairs; ++i) { g.pair_off[i] = (uint16_t)off; start[i] = off; off += count[i]; }
   g.pair_off[pairs] = (uint16_t)off;
-  for (int i = 0; i < n; ++i) g.sched[start[owner[i]]++] = order[i];
+  for (int i = 0; i < n; ++i) {
+    const int tile = order[i];
+    int pi = 0;
+    for (int j = 1; j < g.n_problems; ++j)
+      if (tile >= g.p[j].tile_begin) pi = j;
+    const PProblem& p = g.p[pi];
+    int local = tile - p.tile_begin;
+    const int mn = p.n_tiles * p.m_tiles;
+    const int ks = local / mn;
+    local -= ks * mn;
+    const int mt = local / p.n_tiles, nt = local % p.n_tiles;
+    if (ks > 511 || mt > 1023 || nt > 1023 || pi > 7) return;      // does not fit the packed entry: round-robin
+    g.sched[start[owner[i]]++] = (uint32_t)pi | ((uint32_t)ks << 3) | ((uint32_t)mt << 12) | ((uint32_t)nt << 22);
+  }
   g.use_sched = 1;
 }
 
@@ -1037,6 +1228,15 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     rc = b_mn ? pair_encode_2d(&p.map_b, d.b, d.N, d.K, d.ldb, 32, true)
               : pair_encode_2d(&p.map_b, d.b, d.K, d.N, d.ldb, bn / 2, false, f16);
     if (rc) return rc;
+    // fp16 bias+activation destinations leave through TMA stores when the tile splits into whole 64-column boxes
+    static const int no_tma_c = bringup_int("F2G_PAIR_NO_TMA_STORE", 0);
+    p.tma_c = 0;
+    if (!no_tma_c && f16 && d.c_f16 && d.bias && (d.act == F2G_ACT_PRELU || d.act == F2G_ACT_LEAKY) && bn % 64 == 0 &&
+        (d.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(d.c) & 15) == 0) {
+      rc = pair_encode_2d(&p.map_c, d.c, d.N, d.M, d.ldc, 32, false, true);
+      if (rc) return rc;
+      p.tma_c = 1;
+    }
     p.c = d.c; p.ldc = d.ldc; p.c_pre = d.c_pre; p.ld_pre = d.ld_pre;
     p.bias = d.bias; p.slope = d.slope; p.res = d.res; p.res_scale = d.res_scale;
     p.row_scale = d.row_scale; p.gate = d.gate;
@@ -1073,7 +1273,9 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
       set_error("gemm wait_counter without a producer (done_counter of a non-waiting problem with the same M) in the group");
       return F2G_EINVAL;
     }
-    c.wait_count = 2 * prod->n_tiles;
+    c.wait_count = 2 * prod->n_tiles * (prod->tma_c ? P_EPI_WARPS : 1);   // per-warp publishes on the store path
+    static const int no_wait = bringup_int("F2G_PAIR_NO_CHAIN_WAIT", 0);   // timing experiment: what the chain waits cost
+    if (no_wait) c.wait_count = 0;
   }
   g.n_problems = n;
   g.total_tiles = tiles;

@@ -46,6 +46,12 @@ F2G_SIMT_DEV float4 unpack_half4(uint2 u) {
   const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only): costs no registers while in flight
+F2G_SIMT_DEV void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+F2G_SIMT_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 F2G_SIMT_DEV float simt_fmul(float a, float b) { return __fmul_rn(a, b); }
 F2G_SIMT_DEV float simt_fadd(float a, float b) { return __fadd_rn(a, b); }
 F2G_SIMT_DEV double simt_dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -413,6 +419,8 @@ F2G_SIMT_DEV float4 unpack_half4(uint2 u) {
 }
 F2G_SIMT_DEV void pdl_wait() {}
 F2G_SIMT_DEV void pdl_launch() {}
+F2G_SIMT_DEV void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+F2G_SIMT_DEV void cp_async_wait_all() {}
 // the compiler flags of the emulated build forbid contraction (-ffp-contract=off)
 F2G_SIMT_DEV void simt_block_sum(float v, float* dst) { *dst += v; }
 F2G_SIMT_DEV void simt_block_max_nonneg(float v, float* dst) {
