@@ -1231,8 +1231,10 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
     // fp16 bias+activation destinations leave through TMA stores when the tile splits into whole 64-column boxes
     static const int no_tma_c = bringup_int("F2G_PAIR_NO_TMA_STORE", 0);
     p.tma_c = 0;
+    // (N % 8: measured -- a store box clipped at an extent that is not a multiple of 16 bytes zeroed the rest of
+    // that 16-byte granule outside the tensor; tests/test_kernels_gpu.py keeps N = 250 on the plain-store path)
     if (!no_tma_c && f16 && d.c_f16 && d.bias && (d.act == F2G_ACT_PRELU || d.act == F2G_ACT_LEAKY) && bn % 64 == 0 &&
-        (d.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(d.c) & 15) == 0) {
+        (d.N & 7) == 0 && (d.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(d.c) & 15) == 0) {
       rc = pair_encode_2d(&p.map_c, d.c, d.N, d.M, d.ldc, 32, false, true);
       if (rc) return rc;
       p.tma_c = 1;

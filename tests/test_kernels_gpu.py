@@ -128,6 +128,8 @@ def test_gemm_grouped(L):
 @pytest.mark.parametrize("M,N,K,epi", [
     (1520, 2304, 768, "prelu_f16"), (6032, 1152, 384, "prelu_f16"), (300, 256, 96, "prelu_f16"),
     (1505, 1536, 512, "prelu_f16"), (333, 160, 72, "prelu_f16"),
+    (333, 120, 72, "prelu_f16"), (300, 248, 96, "prelu_f16"),     # TMA-store path, last box clipped in N and M
+    (300, 250, 96, "prelu_f16"),                                  # N % 8 != 0: plain-store path (16-byte clip granule)
     (1520, 768, 2304, "res"), (6032, 384, 1152, "res"), (97, 514, 776, "plain"), (421, 384, 160, "res_round"),
 ])
 def test_gemm_f16_operands(L, M, N, K, epi):

@@ -31,7 +31,7 @@ for fn in sorted(os.listdir(CSRC)):
         base = op.split(".")[0]
         if base in OPS:
             cnt[base] += 1
-        if base in ("UTCHMMA", "UTMALDG", "UTCBAR", "LDTM", "SHFL"):
+        if base in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTCBAR", "LDTM", "LDGSTS", "SHFL"):
             variants[op] += 1
     rows.append((fn, kernels, cnt, variants))
 md = [f"# SASS opcode census, round {tag}", "",
