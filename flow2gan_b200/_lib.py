@@ -103,6 +103,7 @@ _SIGS = {
     "f2g_last_error": ([], C.c_char_p),
     "f2g_check_device": ([], _i),
     "f2g_chain_watchdog": ([C.POINTER(_i)], _i),
+    "f2g_gemm_plan": ([C.c_void_p, _i, _i, C.POINTER(_i), _i], _i),
     "f2g_gemm_tf32": ([C.POINTER(F2GGemm), _i, _fp], _i),
     "f2g_stft": ([_fp, _i, _i, _i, _i, _i, _i, _fp, _fp, _i, _f, _fp, _i, _i, _fp, _fp], _i),
     "f2g_dc_peak": ([_fp, _i, _i, _i, _fp, _fp], _i),
@@ -172,7 +173,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.f2g_abi_version() != 7:
+        if lib.f2g_abi_version() != 8:
             raise RuntimeError("flow2gan_b200: ABI version mismatch, rebuild the library")
         _lib = lib
     return _lib
@@ -257,6 +258,29 @@ def gemm_group(descs: Sequence[F2GGemm]) -> None:
     if PROFILE is not None:      # bench.py: record the launch (descriptors + FLOPs) for replay
         PROFILE.append((arr, n, sum(2.0 * d.M * d.N * d.K for d in descs), bool(descs[0].ab_f16)))
     _check(lib().f2g_gemm_tf32(arr, n, stream()))
+
+
+def gemm_plan(descs: Sequence[F2GGemm], pairs: int = 74) -> dict:
+    """Host-side plan of a CTA-pair launch (f2g_gemm_plan: no device, nothing launched): problems in launch
+    order and, per CTA pair, the (problem, row tile, column tile, K split) tiles it would run."""
+    n = len(descs)
+    arr = (F2GGemm * n)(*descs)
+    cap = 4 + 12 * 8 + 80 + 1024
+    out = (C.c_int * cap)()
+    rc = load().f2g_gemm_plan(C.cast(arr, C.c_void_p), n, pairs, out, cap)
+    if rc <= 0:
+        raise RuntimeError(f"f2g_gemm_plan failed (rc={rc}): " + load().f2g_last_error().decode(errors="replace"))
+    v = list(out[:rc])
+    scheduled, n_prob, tiles, used = v[:4]
+    names = ("M", "N", "K", "bn", "m_tiles", "n_tiles", "tile_begin", "split_k", "waits", "wait_count", "publishes", "tma_c")
+    probs = [dict(zip(names, v[4 + 12 * i:16 + 12 * i])) for i in range(n_prob)]
+    o = 4 + 12 * n_prob
+    off = v[o:o + used + 1]
+    lists = []
+    if scheduled:
+        ent = [e & 0xffffffff for e in v[o + used + 1:o + used + 1 + tiles]]
+        lists = [[(e & 7, (e >> 12) & 1023, e >> 22, (e >> 3) & 511) for e in ent[off[q]:off[q + 1]]] for q in range(used)]
+    return {"scheduled": bool(scheduled), "tiles": tiles, "pairs": used, "problems": probs, "lists": lists}
 
 
 def gemm_replay(arr, n) -> None:

@@ -940,6 +940,15 @@ typedef CUresult (*PEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// f2g_gemm_plan (host logic only, no device needed): the group is planned -- tile geometry, chaining, the
+// per-pair schedule -- exactly as for a launch, but tensor maps are not encoded and nothing is launched.
+struct PlanOut {
+  int pairs;
+  PGroup* g;
+  int used_pairs;
+};
+static thread_local PlanOut* g_plan_out = nullptr;
+
 static PEncodeTiledFn pair_encode_fn() {
   static PEncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -959,15 +968,16 @@ static PEncodeTiledFn pair_encode_fn() {
 // SMALLER than the row length (overlapping rows: the implicit im2col view of a strided conv).
 static int pair_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
                           uint64_t outer_stride_elems, uint32_t box_rows, bool mn_major, bool f16 = false) {
-  PEncodeTiledFn fn = pair_encode_fn();
-  if (!fn) return F2G_EDRIVER;
   const uint64_t esize = f16 ? 2 : 4;
+  if (g_plan_out == nullptr && pair_encode_fn() == nullptr) return F2G_EDRIVER;
+  PEncodeTiledFn fn = g_plan_out ? nullptr : pair_encode_fn();
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (outer_stride_elems * esize) % 16 != 0) {
     set_error("gemm operand must be 16B aligned with a row pitch multiple of 16 bytes "
               "(ptr=%p ld=%llu %s)", (const void*)base, (unsigned long long)outer_stride_elems,
               f16 ? "fp16" : "fp32");
     return F2G_EINVAL;
   }
+  if (!fn) return 0;                       // plan only
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstride[1] = {outer_stride_elems * esize};
   cuuint32_t box[2] = {f16 ? 64u : 32u, box_rows};      // 128 B = one swizzle row either way
@@ -1085,6 +1095,13 @@ static void build_schedule(PGroup& g, int pairs) {
 
 template <int A_MN, int B_MN, int EPI, int F16 = 0>
 static int pair_launch(PGroup& g, cudaStream_t stream) {
+  if (g_plan_out) {
+    const int pairs = g.total_tiles < g_plan_out->pairs ? g.total_tiles : g_plan_out->pairs;
+    build_schedule(g, pairs);
+    *g_plan_out->g = g;
+    g_plan_out->used_pairs = pairs;
+    return 0;
+  }
   static int max_pairs = 0;
   auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, F16>;
   if (!max_pairs) {
@@ -1281,7 +1298,7 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
   }
   g.n_problems = n;
   g.total_tiles = tiles;
-  g.watchdog = chained ? chain_watchdog_dev() : nullptr;
+  g.watchdog = (chained && !g_plan_out) ? chain_watchdog_dev() : nullptr;
   static const int dbg = bringup_int("F2G_PAIR_DBG", 0);
   g.dbg = dbg;
 
@@ -1327,3 +1344,36 @@ int gemm_pair_group(const F2GGemm* descs, int n, cudaStream_t stream) {
 }
 
 }  // namespace f2g
+
+// out: {use_sched, n_problems, total_tiles, pairs used} ; per problem (launch order) 12 ints {M, N, K, bn,
+// m_tiles, n_tiles, tile_begin, split_k, waits (0/1), wait_count, publishes (0/1), tma_c} ; pairs + 1 offsets ;
+// then total_tiles entries -- packed (pdecode_packed's format) when use_sched, else absent.
+extern "C" int f2g_gemm_plan(const F2GGemm* problems, int n_problems, int pairs, int* out, int out_ints) {
+  using namespace f2g;
+  if (pairs < 1 || pairs > P_MAX_PAIRS) {
+    set_error("f2g_gemm_plan: pairs=%d out of range (1..%d)", pairs, P_MAX_PAIRS);
+    return F2G_EINVAL;
+  }
+  static thread_local PGroup g;
+  PlanOut po = {pairs, &g, 0};
+  g_plan_out = &po;
+  const int rc = gemm_pair_group(problems, n_problems, nullptr);
+  g_plan_out = nullptr;
+  if (rc) return rc;
+  const int need = 4 + 12 * g.n_problems + po.used_pairs + 1 + (g.use_sched ? g.total_tiles : 0);
+  if (out_ints < need) {
+    set_error("f2g_gemm_plan: out needs %d ints", need);
+    return F2G_EINVAL;
+  }
+  int* o = out;
+  *o++ = g.use_sched; *o++ = g.n_problems; *o++ = g.total_tiles; *o++ = po.used_pairs;
+  for (int i = 0; i < g.n_problems; ++i) {
+    const PProblem& p = g.p[i];
+    *o++ = p.M; *o++ = p.N; *o++ = p.K; *o++ = p.bn; *o++ = p.m_tiles; *o++ = p.n_tiles; *o++ = p.tile_begin;
+    *o++ = p.split_k; *o++ = p.wait ? 1 : 0; *o++ = p.wait_count; *o++ = p.done ? 1 : 0; *o++ = p.tma_c;
+  }
+  for (int i = 0; i <= po.used_pairs; ++i) *o++ = g.use_sched ? (int)g.pair_off[i] : 0;
+  if (g.use_sched)
+    for (int i = 0; i < g.total_tiles; ++i) *o++ = (int)g.sched[i];
+  return need;
+}

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define F2G_ABI_VERSION 7
+#define F2G_ABI_VERSION 8
 #define F2G_GEMM_MAX_PROBLEMS 8
 
 enum { F2G_ACT_NONE = 0, F2G_ACT_PRELU = 1, F2G_ACT_LEAKY = 2, F2G_ACT_SILU = 3 };
@@ -113,6 +113,15 @@ typedef struct F2GGemm {
  * not run concurrently on one device (serialise them across streams -- the Python host layer does,
  * engine.py::_chain_guard).  Returns the flag; out = the record. */
 int f2g_chain_watchdog(int out[4]);
+
+/* Host logic of a CTA-pair launch without a device: plans the group exactly as f2g_gemm_group would (N tiles,
+ * chaining, the per-pair longest-processing-time tile schedule for `pairs` CTA pairs) and writes it to `out`:
+ * {scheduled (0/1), problems, tiles, pairs used}, 12 ints per problem in launch order {M, N, K, N tile, row
+ * tiles, column tiles, first tile, K splits, waits, expected count, publishes, TMA-store epilogue}, pairs + 1
+ * list offsets, then one packed entry per tile: problem | K split << 3 | row tile << 12 | column tile << 22.
+ * Returns the number of ints written (> 0) or a negative F2G_E* code.  Test / inspection entry: no reference
+ * counterpart (the reference leaves scheduling to cuBLAS). */
+int f2g_gemm_plan(const F2GGemm* problems, int n_problems, int pairs, int* out, int out_ints);
 
 int f2g_gemm_tf32(const F2GGemm* problems, int n_problems, void* stream);
 

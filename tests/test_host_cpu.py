@@ -21,7 +21,7 @@ def test_abi_library_loads_and_exports_all_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/flow2gan_b200.h but not exported"
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
-    assert lib.f2g_abi_version() == 7
+    assert lib.f2g_abi_version() == 8
 
 
 def test_state_dict_layout_matches_reference_spec():
