@@ -586,10 +586,11 @@ gemm_pair_kernel(const __grid_constant__ PGroup g) {
     // the write latency, but never past a point where this CTA could block on its own consumers (below).
     int* pend_done = nullptr;
     bool stg_busy = false;
-    // publish the pending tile once its stores are complete, allowing the `keep` most recent groups (this
-    // tile's own boxes) to stay in flight: the completion of a TMA store takes ~1.4 us (measured: waiting for
-    // it right after the tile cost 2700 cycles per tile), so a producer tile is published one tile late --
-    // or at once when this CTA is about to idle or to depend on it
+    // publish the pending tile once its stores are complete, optionally allowing the `keep` most recent groups
+    // (a later tile's own boxes) to stay in flight.  The completion of a TMA store takes ~1.4 us (measured:
+    // waiting for it right after the tile cost 2700 cycles per tile), so a producer tile is published at the
+    // next tile's first box (store_sync) -- or at once when this CTA is about to idle or to depend on it, or
+    // at the end of the next tile if that tile had no box for this warp
     auto publish = [&](int keep) {
       if (lane == 0) {
         if (keep >= 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
