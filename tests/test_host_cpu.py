@@ -258,3 +258,24 @@ def test_limit_param_value_flip_matches_reference_in_place():
         assert torch.equal(_limit_apply(torch.tensor(1.0), grad, x, lo, hi), got)
         assert torch.equal(_limit_apply(torch.tensor(0.0), grad, x, lo, hi), grad)
         assert int((got != grad).sum()) > 100
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line with the contract's keys, timed on the
+    UNMODIFIED reference staged under baseline/_ref (kind "reference"); needs no GPU."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "flow2gan")):
+        pytest.skip("reference not staged (tools/stage_reference.sh needs /root/reference)")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["warmup"] >= 3
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("mel_24k_base 1-step inference") and d["value"] > 0
